@@ -1,0 +1,85 @@
+"""ctypes loader for libbirda_b200.so.  Fails loudly when the library has not been built."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libbirda_b200.so")
+
+
+class BirdaError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"birda_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+if not os.path.exists(lib_path):
+    raise ImportError(
+        f"{lib_path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C birda_b200/csrc`). birda_b200 has no CPU fallback.")
+
+lib = C.CDLL(lib_path)
+
+u8p, u32p, u64p, i32p, i64p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                               C.POINTER(C.c_int32), C.POINTER(C.c_int64))
+f32p = C.POINTER(C.c_float)
+vp = C.c_void_p
+
+
+class PostCfg(C.Structure):
+    _fields_ = [("activation", C.c_int32), ("min_confidence", C.c_float), ("top_k", C.c_uint32),
+                ("range_threshold", C.c_float), ("keep_unmatched", C.c_int32), ("rerank", C.c_int32)]
+
+
+# name -> (restype, argtypes).  tests/test_abi.py checks this list against include/birda_b200.h.
+SIGNATURES = {
+    "bb_rule_segment_samples": (C.c_int32, [C.c_float, C.c_float, C.c_uint32, C.c_int32, u64p, u64p]),
+    "bb_rule_source_window": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u64p]),
+    "bb_rule_segment_count": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint64, u64p]),
+    "bb_rule_segment_table": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, u64p, u64p, u64p]),
+    "bb_rule_chunk_times": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, f32p, f32p]),
+    "bb_rule_estimate_segment_count": (C.c_int32, [C.c_double, C.c_int32, C.c_float, C.c_float, i64p]),
+    "bb_rule_effective_batch_size": (C.c_uint32, [C.c_uint32, C.c_int64]),
+    "bb_rule_resampler_blocks": (C.c_int32, [C.c_uint32, C.c_uint32, u32p, u32p, u32p, f32p]),
+    "bb_rule_resampler_taps": (C.c_int32, [C.c_uint32, C.c_uint32, f32p, C.c_uint32]),
+    "bb_rule_resampled_len": (C.c_int32, [C.c_uint64, C.c_uint32, C.c_uint32, u64p]),
+    "bb_rule_date_to_week": (C.c_uint32, [C.c_uint32, C.c_uint32]),
+    "bb_rule_week_to_start_day": (C.c_uint32, [C.c_uint32]),
+    "bb_rule_day_of_year_to_date": (None, [C.c_uint32, u32p, u32p]),
+    "bb_version": (C.c_uint32, []),
+    "bb_device_count": (C.c_int32, [i32p]),
+    "bb_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(vp)]),
+    "bb_ctx_create_on_stream": (C.c_int32, [C.c_int32, vp, C.POINTER(vp)]),
+    "bb_ctx_destroy": (None, [vp]),
+    "bb_last_error": (C.c_char_p, [vp]),
+    "bb_ctx_stream": (vp, [vp]),
+    "bb_sync": (C.c_int32, [vp]),
+    "bb_ctx_kernel_launches": (C.c_uint64, [vp]),
+    "bb_host_alloc": (C.c_int32, [C.c_uint64, C.POINTER(vp)]),
+    "bb_host_free": (None, [vp]),
+    "bb_plan_create": (C.c_int32, [vp, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
+    "bb_plan_destroy": (None, [vp]),
+    "bb_plan_source_window": (C.c_int32, [vp, u64p, u64p]),
+    "bb_plan_segment_count": (C.c_int32, [vp, C.c_uint64, u64p]),
+    "bb_frontend_run": (C.c_int32, [vp, vp, C.c_uint64, C.c_int32, C.c_uint64, C.c_int32, C.c_uint32, vp, C.c_uint64,
+                                    C.POINTER(vp), u64p, f32p, f32p, u64p, u64p, u64p]),
+    "bb_post_run_device": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostCfg), vp, vp, vp, vp, vp]),
+    "bb_post_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostCfg), vp, vp, u32p, f32p, u32p]),
+    "bb_dev_alloc": (C.c_int32, [vp, C.c_uint64, C.POINTER(vp)]),
+    "bb_dev_free": (None, [vp, vp]),
+    "bb_memcpy_h2d": (C.c_int32, [vp, vp, vp, C.c_uint64]),
+    "bb_memcpy_d2h": (C.c_int32, [vp, vp, vp, C.c_uint64]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here == the .so does not export the symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(code: int, ctx=None) -> None:
+    if code != 0:
+        msg = lib.bb_last_error(ctx)
+        raise BirdaError(code, msg.decode("utf-8", "replace") if msg else "")

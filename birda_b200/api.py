@@ -1,0 +1,266 @@
+"""Python mirror of the C ABI (tests, bench and Python hosts).  No compute happens here."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import BirdaError, PostCfg, check, lib
+
+FMT_S16, FMT_S32, FMT_F32 = 1, 2, 3
+ACT_NONE, ACT_SIGMOID, ACT_SOFTMAX = 0, 1, 2
+_NP_FMT = {np.dtype(np.int16): FMT_S16, np.dtype(np.int32): FMT_S32, np.dtype(np.float32): FMT_F32}
+
+
+class rules:
+    """Host rules (pure arithmetic in the library; no GPU).  Names follow the reference."""
+
+    @staticmethod
+    def segment_samples(segment_duration: float, overlap: float, target_rate: int, bat_mode: bool = False) -> Tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib.bb_rule_segment_samples(segment_duration, overlap, target_rate, int(bat_mode), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @staticmethod
+    def source_window(seg: int, ovl: int, src_rate: int, tgt_rate: int) -> Tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib.bb_rule_source_window(seg, ovl, src_rate, tgt_rate, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @staticmethod
+    def segment_count(total_frames: int, src_seg: int, src_ovl: int) -> int:
+        n = C.c_uint64()
+        check(lib.bb_rule_segment_count(total_frames, src_seg, src_ovl, C.byref(n)))
+        return n.value
+
+    @staticmethod
+    def segment_table(total_frames: int, src_seg: int, src_ovl: int, first: int = 0, capacity: Optional[int] = None):
+        if capacity is None:
+            capacity = rules.segment_count(total_frames, src_seg, src_ovl)
+        st = np.zeros(max(capacity, 1), np.uint64)
+        tk = np.zeros(max(capacity, 1), np.uint64)
+        w = C.c_uint64()
+        check(lib.bb_rule_segment_table(total_frames, src_seg, src_ovl, first, capacity,
+                                        st.ctypes.data_as(_lib.u64p), tk.ctypes.data_as(_lib.u64p), C.byref(w)))
+        return st[: w.value], tk[: w.value]
+
+    @staticmethod
+    def chunk_times(start_sample: int, src_rate: int, seg: int, tgt_rate: int) -> Tuple[np.float32, np.float32]:
+        a, b = C.c_float(), C.c_float()
+        check(lib.bb_rule_chunk_times(start_sample, src_rate, seg, tgt_rate, C.byref(a), C.byref(b)))
+        return np.float32(a.value), np.float32(b.value)
+
+    @staticmethod
+    def estimate_segment_count(duration: Optional[float], segment_duration: float, overlap: float) -> Optional[int]:
+        e = C.c_int64()
+        check(lib.bb_rule_estimate_segment_count(0.0 if duration is None else duration, int(duration is not None),
+                                                 segment_duration, overlap, C.byref(e)))
+        return None if e.value < 0 else e.value
+
+    @staticmethod
+    def effective_batch_size(batch: int, estimate: Optional[int]) -> int:
+        return lib.bb_rule_effective_batch_size(batch, -1 if estimate is None else estimate)
+
+    @staticmethod
+    def resampler_blocks(src_rate: int, tgt_rate: int):
+        a, b, c, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_float()
+        check(lib.bb_rule_resampler_blocks(src_rate, tgt_rate, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, np.float32(d.value)
+
+    @staticmethod
+    def resampler_taps(src_rate: int, tgt_rate: int) -> np.ndarray:
+        n_in = rules.resampler_blocks(src_rate, tgt_rate)[0]
+        t = np.zeros(n_in, np.float32)
+        check(lib.bb_rule_resampler_taps(src_rate, tgt_rate, t.ctypes.data_as(_lib.f32p), n_in))
+        return t
+
+    @staticmethod
+    def resampled_len(src_len: int, src_rate: int, tgt_rate: int) -> int:
+        n = C.c_uint64()
+        check(lib.bb_rule_resampled_len(src_len, src_rate, tgt_rate, C.byref(n)))
+        return n.value
+
+    date_to_week = staticmethod(lambda m, d: lib.bb_rule_date_to_week(m, d))
+    week_to_start_day = staticmethod(lambda w: lib.bb_rule_week_to_start_day(w))
+
+    @staticmethod
+    def day_of_year_to_date(doy: int) -> Tuple[int, int]:
+        a, b = C.c_uint32(), C.c_uint32()
+        lib.bb_rule_day_of_year_to_date(doy, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+
+def device_count() -> int:
+    n = C.c_int32()
+    rc = lib.bb_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+class Context:
+    """One GPU + one stream (``bb_ctx``).  ``stream``: an existing cudaStream_t handle (int),
+    e.g. ``torch.cuda.current_stream().cuda_stream``, so torch events time the kernels."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._h = C.c_void_p()
+        if stream is None:
+            check(lib.bb_ctx_create(device, C.byref(self._h)))
+        else:
+            check(lib.bb_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(self._h)))
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        check(lib.bb_sync(self._h), self._h)
+
+    @property
+    def kernel_launches(self) -> int:
+        return lib.bb_ctx_kernel_launches(self._h)
+
+    def close(self):
+        if self._h:
+            lib.bb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- post-inference ---------------------------------------------------------------
+    def post_run(self, d_scores: int, B: int, Cc: int, valid_B: int, cfg: "PostConfig",
+                 d_mask: Optional[int] = None, d_species_keep: Optional[int] = None):
+        """Host-output variant: returns (index [valid,k] u32, conf [valid,k] f32, count [valid] u32)."""
+        k = cfg.top_k
+        idx = np.zeros((max(valid_B, 1), k), np.uint32)
+        conf = np.zeros((max(valid_B, 1), k), np.float32)
+        cnt = np.zeros(max(valid_B, 1), np.uint32)
+        c = cfg.to_c()
+        check(lib.bb_post_run(self._h, C.c_void_p(d_scores), B, Cc, valid_B, C.byref(c),
+                              C.c_void_p(d_mask) if d_mask else None, C.c_void_p(d_species_keep) if d_species_keep else None,
+                              idx.ctypes.data_as(_lib.u32p), conf.ctypes.data_as(_lib.f32p), cnt.ctypes.data_as(_lib.u32p)),
+              self._h)
+        return idx[:valid_B], conf[:valid_B], cnt[:valid_B]
+
+    def post_run_device(self, d_scores: int, B: int, Cc: int, valid_B: int, cfg: "PostConfig",
+                        d_mask: Optional[int], d_species_keep: Optional[int], d_index: int, d_conf: int, d_count: int):
+        c = cfg.to_c()
+        check(lib.bb_post_run_device(self._h, C.c_void_p(d_scores), B, Cc, valid_B, C.byref(c),
+                                     C.c_void_p(d_mask) if d_mask else None,
+                                     C.c_void_p(d_species_keep) if d_species_keep else None,
+                                     C.c_void_p(d_index), C.c_void_p(d_conf), C.c_void_p(d_count)), self._h)
+
+
+@dataclass
+class PostConfig:
+    activation: int = ACT_SIGMOID
+    min_confidence: float = 0.1          # src/constants.rs:25
+    top_k: int = 5                       # src/constants.rs:178
+    range_threshold: float = 0.01        # src/constants.rs:333
+    keep_unmatched: bool = True
+    rerank: bool = False
+
+    def to_c(self) -> PostCfg:
+        return PostCfg(self.activation, self.min_confidence, self.top_k, self.range_threshold,
+                       int(self.keep_unmatched), int(self.rerank))
+
+
+@dataclass
+class Segments:
+    """Result of one front-end run: a device tensor [rows, segment_samples] f32 plus host tables."""
+    device_ptr: int
+    nseg: int
+    rows: int
+    segment_samples: int
+    start_sample: np.ndarray
+    start_time: np.ndarray
+    end_time: np.ndarray
+    consumed_frames: int
+    device: int = 0
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.rows, self.segment_samples), "typestr": "<f4", "data": (self.device_ptr, False),
+                "version": 3, "strides": None}
+
+    def torch(self):
+        import torch
+        return torch.as_tensor(self, device=f"cuda:{self.device}")
+
+
+class FrontEndPlan:
+    """``bb_plan``: one (src_rate, channels, fmt, tgt_rate, segment, overlap) configuration."""
+
+    def __init__(self, ctx: Context, src_rate: int, channels: int, fmt: int, tgt_rate: int,
+                 segment_samples: int, overlap_samples: int):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        check(lib.bb_plan_create(ctx.handle, src_rate, channels, fmt, tgt_rate, segment_samples, overlap_samples,
+                                 C.byref(self._h)), ctx.handle)
+        self.src_rate, self.tgt_rate, self.channels, self.fmt = src_rate, tgt_rate, channels, fmt
+        self.segment_samples, self.overlap_samples = segment_samples, overlap_samples
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib.bb_plan_source_window(self._h, C.byref(a), C.byref(b)))
+        self.src_segment, self.src_overlap = a.value, b.value
+
+    def segment_count(self, total_frames: int) -> int:
+        n = C.c_uint64()
+        check(lib.bb_plan_segment_count(self._h, total_frames, C.byref(n)))
+        return n.value
+
+    def run(self, pcm, frames: Optional[int] = None, *, is_device: Optional[bool] = None, first_start_sample: int = 0,
+            is_eof: bool = True, pad_to_batch: int = 0, out_ptr: Optional[int] = None,
+            out_capacity_rows: int = 0, want_tables: bool = True) -> Segments:
+        """``pcm``: numpy array (host, interleaved) or anything with ``data_ptr()`` (torch CUDA tensor) or an int
+        device pointer (then ``frames`` and ``is_device=True`` are required)."""
+        keep = None
+        if isinstance(pcm, np.ndarray):
+            if _NP_FMT.get(pcm.dtype) != self.fmt:
+                raise BirdaError(-4, f"pcm dtype {pcm.dtype} does not match the plan's sample format")
+            pcm = np.ascontiguousarray(pcm)
+            keep = pcm
+            ptr = pcm.ctypes.data
+            n = pcm.size // self.channels if frames is None else frames
+            dev = False if is_device is None else is_device
+        elif hasattr(pcm, "data_ptr"):
+            ptr = pcm.data_ptr()
+            n = pcm.numel() // self.channels if frames is None else frames
+            dev = bool(pcm.is_cuda) if is_device is None else is_device
+            keep = pcm
+        else:
+            ptr, n, dev = int(pcm), int(frames), bool(is_device)
+        nseg_max = rules.segment_count(n, self.src_segment, self.src_overlap)
+        rows_max = nseg_max
+        if pad_to_batch > 1 and nseg_max % pad_to_batch:
+            rows_max = (nseg_max // pad_to_batch + 1) * pad_to_batch
+        cap = max(rows_max, out_capacity_rows, 1)
+        ss = np.zeros(cap, np.uint64)
+        st = np.zeros(cap, np.float32)
+        et = np.zeros(cap, np.float32)
+        d_seg = C.c_void_p()
+        nseg, rows, consumed = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib.bb_frontend_run(self._h, C.c_void_p(ptr), n, int(dev), first_start_sample, int(is_eof), pad_to_batch,
+                                  C.c_void_p(out_ptr) if out_ptr else None, cap,
+                                  C.byref(d_seg), ss.ctypes.data_as(_lib.u64p), st.ctypes.data_as(_lib.f32p),
+                                  et.ctypes.data_as(_lib.f32p), C.byref(nseg), C.byref(rows), C.byref(consumed)),
+              self.ctx.handle)
+        self._keepalive = keep          # host PCM must outlive the async H2D copy
+        return Segments(d_seg.value or 0, nseg.value, rows.value, self.segment_samples, ss[: nseg.value],
+                        st[: nseg.value], et[: nseg.value], consumed.value, self.ctx.device)
+
+    def close(self):
+        if self._h:
+            lib.bb_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,375 @@
+// extern "C" surface of birda_b200 (see include/birda_b200.h for the contract and the
+// reference file:line each entry point replaces).  No exceptions cross this boundary.
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace bb {
+static thread_local std::string g_tls_error;
+void set_tls_error(const std::string& m) { g_tls_error = m; }
+}  // namespace bb
+
+using namespace bb;
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------ rules
+int32_t bb_rule_segment_samples(float segment_duration, float overlap, uint32_t target_rate,
+                                int32_t bat_mode, uint64_t* seg, uint64_t* ovl) {
+    if (!seg || !ovl) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
+    segment_samples(segment_duration, overlap, target_rate, bat_mode != 0, seg, ovl);
+    return BB_OK;
+}
+
+int32_t bb_rule_source_window(uint64_t seg, uint64_t ovl, uint32_t sr, uint32_t tr, uint64_t* sseg, uint64_t* sovl) {
+    if (!sseg || !sovl || sr == 0 || tr == 0) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "bad argument");
+    source_window(seg, ovl, sr, tr, sseg, sovl);
+    return BB_OK;
+}
+
+int32_t bb_rule_segment_count(uint64_t total, uint64_t sseg, uint64_t sovl, uint64_t* nseg) {
+    if (!nseg) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
+    WindowSeq w;
+    if (!make_window_seq(total, sseg, sovl, false, &w))
+        BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_OVERLAP_GE_SEGMENT,
+                   "overlap_samples (" + std::to_string(sovl) + ") must be less than segment_samples (" + std::to_string(sseg) + ")");
+    *nseg = w.nseg;
+    return BB_OK;
+}
+
+int32_t bb_rule_segment_table(uint64_t total, uint64_t sseg, uint64_t sovl, uint64_t first, uint64_t capacity,
+                              uint64_t* start_sample, uint64_t* take, uint64_t* written) {
+    WindowSeq w;
+    if (!make_window_seq(total, sseg, sovl, false, &w))
+        BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_OVERLAP_GE_SEGMENT, "overlap_samples must be less than segment_samples");
+    uint64_t n = 0;
+    for (uint64_t i = first; i < w.nseg && n < capacity; ++i, ++n) {
+        Window x = w.at(i);
+        if (start_sample) start_sample[n] = x.start;
+        if (take) take[n] = x.take;
+    }
+    if (written) *written = n;
+    return BB_OK;
+}
+
+int32_t bb_rule_chunk_times(uint64_t start_sample, uint32_t sr, uint64_t seg, uint32_t tr, float* st, float* et) {
+    if (!st || !et || sr == 0 || tr == 0) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "bad argument");
+    chunk_times(start_sample, sr, seg, tr, st, et);
+    return BB_OK;
+}
+
+int32_t bb_rule_estimate_segment_count(double duration, int32_t has_duration, float seg_dur, float overlap, int64_t* est) {
+    if (!est) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
+    *est = estimate_segment_count(duration, has_duration != 0, seg_dur, overlap);
+    return BB_OK;
+}
+
+uint32_t bb_rule_effective_batch_size(uint32_t batch, int64_t est) { return effective_batch_size(batch, est); }
+
+int32_t bb_rule_resampler_blocks(uint32_t sr, uint32_t tr, uint32_t* n_in, uint32_t* n_out, uint32_t* n_keep, float* cutoff) {
+    ResamplerSpec s; std::string err;
+    if (!make_resampler_spec(sr, tr, false, &s, &err)) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_UNSUPPORTED_RATE, err);
+    if (n_in) *n_in = s.n_in; if (n_out) *n_out = s.n_out; if (n_keep) *n_keep = s.n_keep; if (cutoff) *cutoff = s.cutoff;
+    return BB_OK;
+}
+
+int32_t bb_rule_resampler_taps(uint32_t sr, uint32_t tr, float* taps, uint32_t n) {
+    ResamplerSpec s; std::string err;
+    if (!make_resampler_spec(sr, tr, false, &s, &err)) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_UNSUPPORTED_RATE, err);
+    if (!taps || n != s.n_in) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "taps buffer must hold n_in floats");
+    std::memcpy(taps, s.taps.data(), sizeof(float) * n);
+    return BB_OK;
+}
+
+int32_t bb_rule_resampled_len(uint64_t src_len, uint32_t sr, uint32_t tr, uint64_t* out_len) {
+    if (!out_len) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
+    if (sr == tr) { *out_len = src_len; return BB_OK; }
+    ResamplerSpec s; std::string err;
+    if (!make_resampler_spec(sr, tr, false, &s, &err)) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_UNSUPPORTED_RATE, err);
+    *out_len = resampled_len(src_len, s);
+    return BB_OK;
+}
+
+uint32_t bb_rule_date_to_week(uint32_t month, uint32_t day) { return date_to_week(month, day); }
+uint32_t bb_rule_week_to_start_day(uint32_t week) { return week_to_start_day(week); }
+void     bb_rule_day_of_year_to_date(uint32_t doy, uint32_t* m, uint32_t* d) { uint32_t a, b; day_of_year_to_date(doy, &a, &b); if (m) *m = a; if (d) *d = b; }
+
+// ---------------------------------------------------------------------------------- context
+uint32_t bb_version(void) { return (BB_VERSION_MAJOR << 16) | BB_VERSION_MINOR; }
+
+int32_t bb_device_count(int32_t* count) {
+    if (!count) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; cudaGetLastError(); BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *count = n;
+    return BB_OK;
+}
+
+static int32_t ctx_create_impl(int32_t device, void* stream, bool have_stream, bb_ctx** out) {
+    if (!out) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_NO_DEVICE,
+                   "no CUDA device: birda_b200 has no CPU fallback (" + std::string(e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") + ")");
+    }
+    if (device < 0 || device >= n) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "device index out of range");
+    BB_CUDA_OK((bb_ctx*)nullptr, cudaSetDevice(device));
+    bb_ctx* c = new (std::nothrow) bb_ctx();
+    if (!c) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_OOM, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (have_stream) { c->stream = (cudaStream_t)stream; c->owns_stream = false; }
+    else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+        c->owns_stream = true;
+    }
+    *out = c;
+    return BB_OK;
+}
+
+int32_t bb_ctx_create(int32_t device, bb_ctx** out) { return ctx_create_impl(device, nullptr, false, out); }
+int32_t bb_ctx_create_on_stream(int32_t device, void* stream, bb_ctx** out) { return ctx_create_impl(device, stream, true, out); }
+
+void bb_ctx_destroy(bb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->d_post_index) cudaFree(c->d_post_index);
+    if (c->d_post_conf) cudaFree(c->d_post_conf);
+    if (c->d_post_count) cudaFree(c->d_post_count);
+    if (c->owns_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* bb_last_error(const bb_ctx* c) { return c ? c->last_error.c_str() : g_tls_error.c_str(); }
+void* bb_ctx_stream(bb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t bb_ctx_kernel_launches(const bb_ctx* c) { return c ? c->launches : 0; }
+
+int32_t bb_sync(bb_ctx* c) {
+    if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
+    BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BB_OK;
+}
+
+int32_t bb_host_alloc(uint64_t bytes, void** out) {
+    if (!out) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
+    BB_CUDA_OK((bb_ctx*)nullptr, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return BB_OK;
+}
+void bb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int32_t bb_dev_alloc(bb_ctx* c, uint64_t bytes, void** out) {
+    if (!c || !out) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "bad argument");
+    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    BB_CUDA_OK(c, cudaMalloc(out, bytes ? bytes : 1));
+    return BB_OK;
+}
+void bb_dev_free(bb_ctx* c, void* p) { if (c && p) { cudaSetDevice(c->device); cudaFree(p); } }
+
+int32_t bb_memcpy_h2d(bb_ctx* c, void* dst, const void* src, uint64_t bytes) {
+    if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
+    BB_CUDA_OK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return BB_OK;
+}
+int32_t bb_memcpy_d2h(bb_ctx* c, void* dst, const void* src, uint64_t bytes) {
+    if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
+    BB_CUDA_OK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return BB_OK;
+}
+
+// ------------------------------------------------------------------------------------- plan
+int32_t bb_plan_create(bb_ctx* c, uint32_t src_rate, uint32_t channels, bb_sample_fmt fmt, uint32_t tgt_rate,
+                       uint64_t seg, uint64_t ovl, bb_plan** out) {
+    if (!c || !out) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "bad argument");
+    *out = nullptr;
+    if (src_rate == 0 || tgt_rate == 0 || channels == 0 || seg == 0)
+        BB_SET_ERR(c, BB_ERR_INVALID_ARG, "rates, channels and segment_samples must be > 0");
+    if (fmt != BB_S16 && fmt != BB_S32 && fmt != BB_F32)
+        BB_SET_ERR(c, BB_ERR_UNSUPPORTED_FORMAT, "unsupported sample format (S16, S32, F32 are converted; decode.rs:353-411)");
+    bb_plan* p = new (std::nothrow) bb_plan();
+    if (!p) BB_SET_ERR(c, BB_ERR_OOM, "out of host memory");
+    p->ctx = c; p->src_rate = src_rate; p->tgt_rate = tgt_rate; p->channels = channels; p->fmt = fmt;
+    p->bytes_per_sample = fmt == BB_S16 ? 2 : 4;
+    p->seg = seg; p->ovl = ovl;
+    source_window(seg, ovl, src_rate, tgt_rate, &p->src_seg, &p->src_ovl);
+    if (p->src_ovl >= p->src_seg) {
+        std::string m = "overlap_samples (" + std::to_string(p->src_ovl) + ") must be less than segment_samples (" + std::to_string(p->src_seg) + ")";
+        delete p;
+        BB_SET_ERR(c, BB_ERR_OVERLAP_GE_SEGMENT, m);
+    }
+    p->resample = src_rate != tgt_rate;
+    if (p->resample) {
+        std::string err;
+        if (!make_resampler_spec(src_rate, tgt_rate, true, &p->spec, &err)) { delete p; BB_SET_ERR(c, BB_ERR_UNSUPPORTED_RATE, err); }
+        p->resampled_len = resampled_len(p->src_seg, p->spec);
+        cudaSetDevice(c->device);
+        cudaError_t e = resampler_dev_init(p->spec, &p->rs);
+        if (e != cudaSuccess) {
+            resampler_dev_free(&p->rs); delete p;
+            if (e == cudaErrorInvalidConfiguration)
+                BB_SET_ERR(c, BB_ERR_UNSUPPORTED_RATE, "resampler blocks for " + std::to_string(src_rate) + " -> " + std::to_string(tgt_rate) + " do not fit in shared memory");
+            BB_SET_ERR(c, e == cudaErrorMemoryAllocation ? BB_ERR_OOM : BB_ERR_CUDA, std::string("resampler init: ") + cudaGetErrorString(e));
+        }
+    }
+    *out = p;
+    return BB_OK;
+}
+
+void bb_plan_destroy(bb_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    if (p->d_pcm) cudaFree(p->d_pcm);
+    if (p->d_out) cudaFree(p->d_out);
+    resampler_dev_free(&p->rs);
+    delete p;
+}
+
+int32_t bb_plan_source_window(const bb_plan* p, uint64_t* sseg, uint64_t* sovl) {
+    if (!p) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null plan");
+    if (sseg) *sseg = p->src_seg; if (sovl) *sovl = p->src_ovl;
+    return BB_OK;
+}
+
+int32_t bb_plan_segment_count(const bb_plan* p, uint64_t total_frames, uint64_t* nseg) {
+    if (!p || !nseg) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "bad argument");
+    WindowSeq w; make_window_seq(total_frames, p->src_seg, p->src_ovl, false, &w);
+    *nseg = w.nseg;
+    return BB_OK;
+}
+
+int32_t bb_frontend_run(bb_plan* p, const void* pcm, uint64_t frames, int32_t pcm_is_device,
+                        uint64_t first_start_sample, int32_t is_eof, uint32_t pad_to_batch,
+                        float* d_out_user, uint64_t capacity_rows,
+                        float** d_segments, uint64_t* start_sample, float* start_time, float* end_time,
+                        uint64_t* nseg_out, uint64_t* nseg_padded, uint64_t* consumed_frames) {
+    if (!p) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null plan");
+    bb_ctx* c = p->ctx;
+    if (frames > 0 && !pcm) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null pcm");
+    WindowSeq w;
+    if (!make_window_seq(frames, p->src_seg, p->src_ovl, is_eof == 0, &w))
+        BB_SET_ERR(c, BB_ERR_OVERLAP_GE_SEGMENT, "overlap_samples must be less than segment_samples");
+    const uint64_t nseg = w.nseg;
+    uint64_t rows = nseg;
+    if (pad_to_batch > 1 && nseg % pad_to_batch) rows = (nseg / pad_to_batch + 1) * pad_to_batch;
+    if (nseg_out) *nseg_out = nseg;
+    if (nseg_padded) *nseg_padded = rows;
+    if (consumed_frames) *consumed_frames = is_eof ? frames : nseg * w.hop;
+    if ((start_sample || start_time || end_time || d_out_user) && capacity_rows < (d_out_user ? rows : nseg))
+        BB_SET_ERR(c, BB_ERR_CAPACITY, "capacity_rows (" + std::to_string(capacity_rows) + ") < rows produced (" + std::to_string(rows) + ")");
+    for (uint64_t i = 0; i < nseg; ++i) {
+        const uint64_t st = first_start_sample + w.at(i).start;
+        if (start_sample) start_sample[i] = st;
+        if (start_time || end_time) {
+            float a, b; chunk_times(st, p->src_rate, p->seg, p->tgt_rate, &a, &b);
+            if (start_time) start_time[i] = a; if (end_time) end_time[i] = b;
+        }
+    }
+    if (d_segments) *d_segments = nullptr;
+    if (rows == 0) return BB_OK;
+
+    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    // stage PCM
+    const void* d_pcm = pcm;
+    const uint64_t pcm_bytes = frames * p->channels * p->bytes_per_sample;
+    if (!pcm_is_device) {
+        if (p->d_pcm_bytes < pcm_bytes) {
+            BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+            if (p->d_pcm) cudaFree(p->d_pcm);
+            p->d_pcm = nullptr; p->d_pcm_bytes = 0;
+            BB_CUDA_OK(c, cudaMalloc(&p->d_pcm, pcm_bytes));
+            p->d_pcm_bytes = pcm_bytes;
+        }
+        if (pcm_bytes) BB_CUDA_OK(c, cudaMemcpyAsync(p->d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, c->stream));
+        d_pcm = p->d_pcm;
+    }
+    float* d_out = d_out_user;
+    if (!d_out) {
+        if (p->d_out_rows < rows) {
+            BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+            if (p->d_out) cudaFree(p->d_out);
+            p->d_out = nullptr; p->d_out_rows = 0;
+            BB_CUDA_OK(c, cudaMalloc(&p->d_out, rows * p->seg * sizeof(float)));
+            p->d_out_rows = rows;
+        }
+        d_out = p->d_out;
+    }
+    cudaError_t e;
+    if (!p->resample) {
+        e = launch_pack(c->stream, c->sm_count, d_pcm, p->fmt, p->channels, frames, p->src_seg, w.hop, nseg,
+                        w.last_start, rows, d_out);
+        c->launches += 1;
+    } else {
+        int n = 0;
+        e = launch_resample(c->stream, c->sm_count, p->rs, d_pcm, p->fmt, p->channels, frames, p->src_seg, w.hop,
+                            nseg, w.last_start, rows, p->seg, p->resampled_len, d_out, &n);
+        c->launches += n;
+    }
+    BB_CUDA_OK(c, e);
+    if (d_segments) *d_segments = d_out;
+    return BB_OK;
+}
+
+// ------------------------------------------------------------------------------------- post
+static int32_t post_check(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B, const bb_post_cfg* cfg,
+                          const float* d_mask, const uint8_t* d_keep) {
+    if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
+    if (!cfg || (!d_scores && valid_B)) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null argument");
+    if (valid_B > B) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "valid_B > B");
+    if (C == 0) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "C must be > 0");
+    if (cfg->top_k < 1 || cfg->top_k > BB_MAX_TOP_K) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "top_k must be in [1, BB_MAX_TOP_K]");
+    if (cfg->activation < BB_ACT_NONE || cfg->activation > BB_ACT_SOFTMAX) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "unknown activation");
+    if (d_mask && d_keep) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "range mask and species list are mutually exclusive (lib.rs:502-520)");
+    return BB_OK;
+}
+
+int32_t bb_post_run_device(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B,
+                           const bb_post_cfg* cfg, const float* d_mask, const uint8_t* d_keep,
+                           uint32_t* d_index, float* d_conf, uint32_t* d_count) {
+    int32_t rc = post_check(c, d_scores, B, C, valid_B, cfg, d_mask, d_keep);
+    if (rc != BB_OK) return rc;
+    if (valid_B && (!d_index || !d_conf || !d_count)) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null output");
+    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    BB_CUDA_OK(c, launch_post(c->stream, d_scores, B, C, valid_B, *cfg, d_mask, d_keep, d_index, d_conf, d_count));
+    if (valid_B) c->launches += 1;
+    return BB_OK;
+}
+
+int32_t bb_post_run(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B,
+                    const bb_post_cfg* cfg, const float* d_mask, const uint8_t* d_keep,
+                    uint32_t* h_index, float* h_conf, uint32_t* h_count) {
+    int32_t rc = post_check(c, d_scores, B, C, valid_B, cfg, d_mask, d_keep);
+    if (rc != BB_OK) return rc;
+    if (valid_B == 0) return BB_OK;
+    if (!h_index || !h_conf || !h_count) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null output");
+    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    if (c->post_capacity_rows < valid_B || c->post_capacity_k < cfg->top_k) {
+        BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        if (c->d_post_index) cudaFree(c->d_post_index);
+        if (c->d_post_conf) cudaFree(c->d_post_conf);
+        if (c->d_post_count) cudaFree(c->d_post_count);
+        c->d_post_index = nullptr; c->d_post_conf = nullptr; c->d_post_count = nullptr; c->post_capacity_rows = 0;
+        const uint64_t rows = valid_B > 512 ? valid_B : 512;
+        BB_CUDA_OK(c, cudaMalloc(&c->d_post_index, rows * BB_MAX_TOP_K * sizeof(uint32_t)));
+        BB_CUDA_OK(c, cudaMalloc(&c->d_post_conf, rows * BB_MAX_TOP_K * sizeof(float)));
+        BB_CUDA_OK(c, cudaMalloc(&c->d_post_count, rows * sizeof(uint32_t)));
+        c->post_capacity_rows = rows; c->post_capacity_k = BB_MAX_TOP_K;
+    }
+    BB_CUDA_OK(c, launch_post(c->stream, d_scores, B, C, valid_B, *cfg, d_mask, d_keep, c->d_post_index, c->d_post_conf, c->d_post_count));
+    c->launches += 1;
+    const uint64_t n = (uint64_t)valid_B * cfg->top_k;
+    BB_CUDA_OK(c, cudaMemcpyAsync(h_index, c->d_post_index, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    BB_CUDA_OK(c, cudaMemcpyAsync(h_conf, c->d_post_conf, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    BB_CUDA_OK(c, cudaMemcpyAsync(h_count, c->d_post_count, (uint64_t)valid_B * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return BB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Internal types of the birda_b200 library (product code).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "rules.hpp"
+#include "../../include/birda_b200.h"
+
+struct bb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    std::string last_error;
+    uint64_t launches = 0;
+    // scratch for bb_post_run (host-output variant)
+    uint32_t* d_post_index = nullptr; float* d_post_conf = nullptr; uint32_t* d_post_count = nullptr;
+    uint64_t post_capacity_rows = 0; uint32_t post_capacity_k = 0;
+};
+
+namespace bb {
+
+// Device-side description of the resampler for one (from, to) pair.
+struct ResamplerDev {
+    uint32_t n_in = 0, n_out = 0, n_keep = 0;
+    int nstage_fwd = 0, nstage_inv = 0;
+    int radix_fwd[16] = {0}, radix_inv[16] = {0};
+    float2* d_tw_fwd = nullptr;     // [n_in]   exp(-2*pi*i*k/n_in)
+    float2* d_tw_inv = nullptr;     // [n_out]  exp(+2*pi*i*k/n_out)
+    float2* d_split_fwd = nullptr;  // [n_in+1] exp(-2*pi*i*k/(2*n_in))
+    float2* d_split_inv = nullptr;  // [n_out]  exp(+2*pi*i*k/(2*n_out))
+    float2* d_filt = nullptr;       // [n_keep] filter spectrum
+    uint32_t buf_len = 0;           // complex elements per ping/pong buffer
+};
+
+}  // namespace bb
+
+struct bb_plan {
+    bb_ctx* ctx = nullptr;
+    uint32_t src_rate = 0, tgt_rate = 0, channels = 0;
+    int fmt = 0;
+    uint32_t bytes_per_sample = 0;
+    uint64_t seg = 0, ovl = 0;            // target-rate counts
+    uint64_t src_seg = 0, src_ovl = 0;    // source-rate window
+    bool resample = false;
+    bb::ResamplerSpec spec;
+    bb::ResamplerDev rs;
+    uint64_t resampled_len = 0;           // samples resample() returns for src_seg inputs
+    // device buffers
+    void* d_pcm = nullptr; uint64_t d_pcm_bytes = 0;
+    float* d_out = nullptr; uint64_t d_out_rows = 0;
+};
+
+#define BB_SET_ERR(ctx, code, msg) do { if (ctx) (ctx)->last_error = (msg); else bb::set_tls_error(msg); return (code); } while (0)
+#define BB_CUDA_OK(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+        std::string _m = std::string(#expr) + ": " + cudaGetErrorString(_e); \
+        if (ctx) (ctx)->last_error = _m; else bb::set_tls_error(_m); \
+        return _e == cudaErrorMemoryAllocation ? BB_ERR_OOM : BB_ERR_CUDA; } } while (0)
+
+namespace bb {
+void set_tls_error(const std::string& m);
+
+// K1: convert + downmix + window gather + pack (no resampling).  k1_pack.cu
+cudaError_t launch_pack(cudaStream_t st, int sm_count, const void* d_pcm, int fmt, uint32_t channels,
+                        uint64_t total_frames, uint64_t seg, uint64_t hop, uint64_t nseg,
+                        uint64_t last_start, uint64_t rows_total, float* d_out);
+
+// K2: convert + downmix + window gather + per-window block-FFT resample + pack.  k2_resample.cu
+cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
+                            uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
+                            uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
+                            uint64_t resampled_len, float* d_out, int* launches);
+cudaError_t resampler_dev_init(const ResamplerSpec& spec, ResamplerDev* rs);
+void        resampler_dev_free(ResamplerDev* rs);
+
+// K3: activation + top-k + threshold + mask + threshold.  k3_post.cu
+cudaError_t launch_post(cudaStream_t st, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B,
+                        const bb_post_cfg& cfg, const float* d_mask, const uint8_t* d_keep,
+                        uint32_t* d_index, float* d_conf, uint32_t* d_count);
+}  // namespace bb

@@ -1,0 +1,162 @@
+// K1 — sample conversion + channel downmix + overlapped window gather + pack into the model
+// input tensor, for the paths that do not resample (source rate == model rate, and bat mode).
+//
+// Replaces, in one pass over HBM: append_samples (src/audio/decode.rs:353-411),
+// StreamingDecoder::next_segment's copy + zero pad (src/audio/decode.rs:175-181) and the
+// [B, sample_count] tensor pack inside birdnet_onnx::Classifier::predict_batch*.
+//
+// HBM-bound streaming kernel: algorithmic bytes = frames*channels*sizeof(sample) read once +
+// rows*segment*4 written once.  Overlapped windows re-read their shared
+// frames from L2.  128-bit stores always; 64/128-bit loads whenever the window start is
+// aligned (warp-uniform test per row), scalar loads otherwise.
+#include "common.cuh"
+
+namespace bb {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll  = 4;                       // float4 stores per thread per tile
+constexpr int kTile    = kThreads * kUnroll * 4;  // output floats per tile
+
+template <int FMT> struct SampleT;
+template <> struct SampleT<BB_S16> { using type = int16_t; };
+template <> struct SampleT<BB_S32> { using type = int32_t; };
+template <> struct SampleT<BB_F32> { using type = float; };
+
+// exact conversions of src/audio/decode.rs:371-398 (division by a power of two == exact scaling)
+__device__ __forceinline__ float conv(int16_t s) { return __fmul_rn(__int2float_rn((int)s), 1.0f / 32768.0f); }
+__device__ __forceinline__ float conv(int32_t s) { return __fmul_rn(__int2float_rn(s), 1.0f / 2147483648.0f); }
+__device__ __forceinline__ float conv(float s)   { return s; }
+
+// mono value of one frame: sum = 0; sum += conv(ch) left to right; sum / channels   (decode.rs:362-367)
+template <typename S>
+__device__ __forceinline__ float downmix_frame(const S* __restrict__ p, uint32_t channels, float fch) {
+    if (channels == 1) return conv(p[0]);
+    float sum = 0.0f;
+    for (uint32_t c = 0; c < channels; ++c) sum = __fadd_rn(sum, conv(p[c]));
+    return __fdiv_rn(sum, fch);
+}
+
+template <typename S, int CH> struct Vec4Frames;   // 4 consecutive frames of CH channels as one aligned load
+template <> struct Vec4Frames<int16_t, 1> { using V = short4; static constexpr int n = 1; };
+template <> struct Vec4Frames<int16_t, 2> { using V = int4;   static constexpr int n = 1; };
+template <> struct Vec4Frames<int32_t, 1> { using V = int4;   static constexpr int n = 1; };
+template <> struct Vec4Frames<int32_t, 2> { using V = int4;   static constexpr int n = 2; };
+template <> struct Vec4Frames<float, 1>   { using V = float4; static constexpr int n = 1; };
+template <> struct Vec4Frames<float, 2>   { using V = float4; static constexpr int n = 2; };
+
+template <typename S, int CH>
+__device__ __forceinline__ float4 load4_aligned(const S* __restrict__ p) {
+    using VF = Vec4Frames<S, CH>;
+    typename VF::V v[VF::n];
+    const typename VF::V* vp = reinterpret_cast<const typename VF::V*>(p);
+#pragma unroll
+    for (int i = 0; i < VF::n; ++i) v[i] = __ldg(vp + i);
+    const S* s = reinterpret_cast<const S*>(v);
+    float4 o;
+    if (CH == 1) {
+        o.x = conv(s[0]); o.y = conv(s[1]); o.z = conv(s[2]); o.w = conv(s[3]);
+    } else {
+        // sum = 0 + l + r ; / 2  — same operation order as the reference
+        o.x = __fdiv_rn(__fadd_rn(__fadd_rn(0.0f, conv(s[0])), conv(s[1])), 2.0f);
+        o.y = __fdiv_rn(__fadd_rn(__fadd_rn(0.0f, conv(s[2])), conv(s[3])), 2.0f);
+        o.z = __fdiv_rn(__fadd_rn(__fadd_rn(0.0f, conv(s[4])), conv(s[5])), 2.0f);
+        o.w = __fdiv_rn(__fadd_rn(__fadd_rn(0.0f, conv(s[6])), conv(s[7])), 2.0f);
+    }
+    return o;
+}
+
+// CH_T: 1 or 2 = compile-time channel count with vector loads; 0 = runtime channel count.
+template <int FMT, int CH_T>
+__global__ void __launch_bounds__(kThreads)
+pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_frames,
+            uint64_t seg, uint64_t hop, uint64_t nseg, uint64_t last_start, uint64_t rows_total,
+            float* __restrict__ out, uint32_t tiles_per_row, uint64_t ntiles) {
+    using S = typename SampleT<FMT>::type;
+    const S* __restrict__ pcm = static_cast<const S*>(pcm_v);
+    const float fch = (float)channels;
+    const bool row_vec = (seg % 4 == 0);           // rows are 16-byte aligned
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t row = tile / tiles_per_row;
+        const uint64_t j0  = (tile - row * tiles_per_row) * (uint64_t)kTile;
+        uint64_t start = 0, take = 0;
+        if (row < nseg) {
+            start = (row + 1 == nseg) ? last_start : row * hop;
+            take  = total_frames - start < seg ? total_frames - start : seg;
+        }
+        float* __restrict__ orow = out + row * seg;
+        if (row_vec) {
+            bool in_vec = false;
+            if (CH_T != 0) {
+                constexpr int ch = CH_T == 0 ? 1 : CH_T;
+                constexpr size_t align = 4 * ch * sizeof(S) > 16 ? 16 : 4 * ch * sizeof(S);
+                in_vec = ((reinterpret_cast<uintptr_t>(pcm) + start * ch * sizeof(S)) % align) == 0;
+            }
+            float4 v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const uint64_t j = j0 + ((uint64_t)u * kThreads + threadIdx.x) * 4;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < seg) {
+                    if (CH_T != 0 && in_vec && j + 4 <= take) {
+                        constexpr int ch = CH_T == 0 ? 1 : CH_T;
+                        v[u] = load4_aligned<S, ch>(pcm + (start + j) * ch);
+                    } else {
+                        float t[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            t[e] = (j + e < take) ? downmix_frame(pcm + (start + j + e) * channels, channels, fch) : 0.0f;
+                        v[u] = make_float4(t[0], t[1], t[2], t[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const uint64_t j = j0 + ((uint64_t)u * kThreads + threadIdx.x) * 4;
+                if (j < seg) *reinterpret_cast<float4*>(orow + j) = v[u];
+            }
+        } else {
+            for (uint32_t e = threadIdx.x; e < (uint32_t)kTile; e += kThreads) {
+                const uint64_t j = j0 + e;
+                if (j < seg)
+                    orow[j] = (j < take) ? downmix_frame(pcm + (start + j) * channels, channels, fch) : 0.0f;
+            }
+        }
+    }
+}
+
+template <int FMT>
+cudaError_t launch_fmt(cudaStream_t st, int sm_count, const void* d_pcm, uint32_t channels,
+                       uint64_t total_frames, uint64_t seg, uint64_t hop, uint64_t nseg,
+                       uint64_t last_start, uint64_t rows_total, float* d_out) {
+    const uint32_t tiles_per_row = (uint32_t)((seg + kTile - 1) / kTile);
+    const uint64_t ntiles = rows_total * tiles_per_row;
+    if (ntiles == 0) return cudaSuccess;
+    uint64_t want = (uint64_t)sm_count * 8;
+    unsigned grid = (unsigned)(ntiles < want ? ntiles : want);
+    if (channels == 1)
+        pack_kernel<FMT, 1><<<grid, kThreads, 0, st>>>(d_pcm, channels, total_frames, seg, hop, nseg, last_start,
+                                                       rows_total, d_out, tiles_per_row, ntiles);
+    else if (channels == 2)
+        pack_kernel<FMT, 2><<<grid, kThreads, 0, st>>>(d_pcm, channels, total_frames, seg, hop, nseg, last_start,
+                                                       rows_total, d_out, tiles_per_row, ntiles);
+    else
+        pack_kernel<FMT, 0><<<grid, kThreads, 0, st>>>(d_pcm, channels, total_frames, seg, hop, nseg, last_start,
+                                                       rows_total, d_out, tiles_per_row, ntiles);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_pack(cudaStream_t st, int sm_count, const void* d_pcm, int fmt, uint32_t channels,
+                        uint64_t total_frames, uint64_t seg, uint64_t hop, uint64_t nseg,
+                        uint64_t last_start, uint64_t rows_total, float* d_out) {
+    switch (fmt) {
+        case BB_S16: return launch_fmt<BB_S16>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, rows_total, d_out);
+        case BB_S32: return launch_fmt<BB_S32>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, rows_total, d_out);
+        case BB_F32: return launch_fmt<BB_F32>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, rows_total, d_out);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace bb

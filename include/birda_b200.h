@@ -1,0 +1,219 @@
+/*
+ * birda_b200 — C ABI of the B200-native audio front end and post-inference scoring path.
+ *
+ * This header is the drop-in boundary.  The reference (tphakala/birda,
+ * pure Rust) has no FFI for this path today; each entry point below names the Rust
+ * item (file:line under /root/reference) whose work it replaces, so that a maintainer
+ * can bind it from `src/audio`, `src/pipeline` and `src/inference` through a thin
+ * `extern "C"` module built in build.rs (see INTEGRATION.md and rust/).
+ *
+ * Conventions
+ *   - every function returns int32_t: 0 = BB_OK, < 0 = BB_ERR_*; nothing throws or aborts
+ *     across the boundary (the reference forbids panics: Cargo.toml:85-87);
+ *   - `bb_last_error(ctx)` returns a message for the last failure on that context
+ *     (ctx == NULL: the calling thread's last context-free failure);
+ *   - a bb_ctx is one GPU + one CUDA stream; it is NOT thread-safe (one owner thread, as
+ *     BirdClassifier is only used from the main thread: src/pipeline/processor.rs:659-671).
+ *     Several contexts (one per GPU) may run concurrently;
+ *   - the caller owns every host pointer it passes; the library owns device memory held
+ *     by a ctx / plan.  A plan-owned device tensor stays valid until the next run on that
+ *     plan or bb_plan_destroy;
+ *   - there is NO CPU fallback: without a CUDA device bb_ctx_create fails with
+ *     BB_ERR_NO_DEVICE.  The `bb_rule_*` helpers are pure host arithmetic (the reference's
+ *     integer / f32 rules) and work anywhere.
+ */
+#ifndef BIRDA_B200_H
+#define BIRDA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_VERSION_MAJOR 0
+#define BB_VERSION_MINOR 1
+
+typedef struct bb_ctx  bb_ctx;   /* one per GPU                                              */
+typedef struct bb_plan bb_plan;  /* one per (src_rate, channels, fmt, tgt_rate, seg, ovl)     */
+
+typedef enum {
+    BB_OK                     =  0,
+    BB_ERR_INVALID_ARG        = -1,
+    BB_ERR_OVERLAP_GE_SEGMENT = -2,  /* src/audio/decode.rs:156-162 -> Error::Internal        */
+    BB_ERR_UNSUPPORTED_RATE   = -3,  /* -> Error::Resample { reason }                         */
+    BB_ERR_UNSUPPORTED_FORMAT = -4,  /* reference silently drops: src/audio/decode.rs:407-409 */
+    BB_ERR_CUDA               = -5,  /* -> Error::Inference { reason }                        */
+    BB_ERR_OOM                = -6,
+    BB_ERR_INTERNAL           = -7,  /* -> Error::Internal { message }                        */
+    BB_ERR_NO_DEVICE          = -8,
+    BB_ERR_CAPACITY           = -9   /* caller-provided output array too small                */
+} bb_status;
+
+/* interleaved frames, native endian; the formats src/audio/decode.rs:353-411 converts */
+typedef enum { BB_S16 = 1, BB_S32 = 2, BB_F32 = 3 } bb_sample_fmt;
+
+/* ------------------------------------------------------------------------------------------
+ * Host rules — pure arithmetic, no GPU.  Bit-exact restatements of the reference's integer
+ * and f32 rules; the Rust host keeps its own code for these, the C forms exist so that the
+ * library, the tests and non-Rust hosts agree with it.
+ * ---------------------------------------------------------------------------------------- */
+
+/* (segment_duration * rate as f32) as usize etc.; bat_mode -> 144000 / 36000.
+ * src/pipeline/processor.rs:502-522, src/constants.rs:525-541 */
+int32_t bb_rule_segment_samples(float segment_duration, float overlap, uint32_t target_rate,
+                                int32_t bat_mode, uint64_t* segment_samples, uint64_t* overlap_samples);
+
+/* ceil(n * src / tgt) in f64, identity for equal rates.  src/pipeline/processor.rs:61-82 */
+int32_t bb_rule_source_window(uint64_t segment_samples, uint64_t overlap_samples,
+                              uint32_t src_rate, uint32_t tgt_rate,
+                              uint64_t* src_segment, uint64_t* src_overlap);
+
+/* Number of windows StreamingDecoder::next_segment yields for a stream of total_frames
+ * mono samples.  src/audio/decode.rs:150-202.  BB_ERR_OVERLAP_GE_SEGMENT as :156-162. */
+int32_t bb_rule_segment_count(uint64_t total_frames, uint64_t src_segment, uint64_t src_overlap,
+                              uint64_t* nseg);
+
+/* Windows [first, first+capacity) of that sequence: RawSegment.start_sample and the number of
+ * real (non-padding) samples in each.  src/audio/decode.rs:175-196 */
+int32_t bb_rule_segment_table(uint64_t total_frames, uint64_t src_segment, uint64_t src_overlap,
+                              uint64_t first, uint64_t capacity,
+                              uint64_t* start_sample, uint64_t* take, uint64_t* written);
+
+/* AudioChunk.start_time / end_time in f32.  src/pipeline/processor.rs:89-94 */
+int32_t bb_rule_chunk_times(uint64_t start_sample, uint32_t src_rate, uint64_t segment_samples,
+                            uint32_t tgt_rate, float* start_time, float* end_time);
+
+/* estimate_segment_count; *estimate = -1 encodes None.  src/output/progress.rs:80-92 */
+int32_t bb_rule_estimate_segment_count(double duration_secs, int32_t has_duration,
+                                       float segment_duration, float overlap, int64_t* estimate);
+
+/* min(batch, estimate), never 0.  src/pipeline/processor.rs:525-545 */
+uint32_t bb_rule_effective_batch_size(uint32_t batch_size, int64_t estimate);
+
+/* rubato Fft::new(from, to, 1024, 1, FixedSync::Both) block sizes (src/audio/resample.rs:19-30):
+ * input frames per process() call, output frames per call, spectrum bins carried over. */
+int32_t bb_rule_resampler_blocks(uint32_t src_rate, uint32_t tgt_rate,
+                                 uint32_t* n_in, uint32_t* n_out, uint32_t* n_keep, float* cutoff);
+
+/* The anti-alias filter taps (f32, already / (2*n_in)) the resampler convolves with; n = n_in. */
+int32_t bb_rule_resampler_taps(uint32_t src_rate, uint32_t tgt_rate, float* taps, uint32_t n);
+
+/* Length resample() returns for src_len input samples before the resize.
+ * src/audio/resample.rs:35-88 */
+int32_t bb_rule_resampled_len(uint64_t src_len, uint32_t src_rate, uint32_t tgt_rate, uint64_t* out_len);
+
+/* src/utils/date.rs:21-68 */
+uint32_t bb_rule_date_to_week(uint32_t month, uint32_t day);
+uint32_t bb_rule_week_to_start_day(uint32_t week);
+void     bb_rule_day_of_year_to_date(uint32_t day_of_year, uint32_t* month, uint32_t* day);
+
+/* ------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------- */
+
+uint32_t    bb_version(void);                                  /* (major << 16) | minor        */
+int32_t     bb_device_count(int32_t* count);
+int32_t     bb_ctx_create(int32_t device, bb_ctx** out);       /* owns a new non-blocking stream */
+/* Run on a stream the caller owns (e.g. the stream ORT's CUDA EP or torch uses) */
+int32_t     bb_ctx_create_on_stream(int32_t device, void* cuda_stream, bb_ctx** out);
+void        bb_ctx_destroy(bb_ctx*);
+const char* bb_last_error(const bb_ctx*);
+void*       bb_ctx_stream(bb_ctx*);                            /* cudaStream_t                  */
+int32_t     bb_sync(bb_ctx*);                                  /* cudaStreamSynchronize         */
+uint64_t    bb_ctx_kernel_launches(const bb_ctx*);             /* kernels launched so far        */
+
+/* Page-locked host staging (decode straight into it; H2D copies then run at PCIe rate) */
+int32_t bb_host_alloc(uint64_t bytes, void** out);
+void    bb_host_free(void*);
+
+/* ------------------------------------------------------------------------------------------
+ * Front end: decoded PCM -> downmix -> per-window resample -> packed model input
+ * Replaces the decode thread's loop body: StreamingDecoder::next_segment
+ * (src/audio/decode.rs:150-202) + append_samples' conversion/downmix (:353-411) +
+ * resample_chunk (src/audio/resample.rs:97-105) + resize + time stamps
+ * (src/pipeline/processor.rs:84-100) + the tensor pack inside birdnet_onnx::predict_batch*.
+ * ---------------------------------------------------------------------------------------- */
+
+/* segment_samples / overlap_samples are TARGET-rate counts exactly as processor.rs:514-521
+ * computes them (use bb_rule_segment_samples).  tgt_rate == src_rate means "no resampling"
+ * (also the bat path, processor.rs:464-475). */
+int32_t bb_plan_create(bb_ctx*, uint32_t src_rate, uint32_t channels, bb_sample_fmt fmt,
+                       uint32_t tgt_rate, uint64_t segment_samples, uint64_t overlap_samples,
+                       bb_plan** out);
+void    bb_plan_destroy(bb_plan*);
+int32_t bb_plan_source_window(const bb_plan*, uint64_t* src_segment, uint64_t* src_overlap);
+int32_t bb_plan_segment_count(const bb_plan*, uint64_t total_frames, uint64_t* nseg);
+
+/* One piece of a file in, packed segments out.
+ *
+ *   pcm               interleaved frames (host or device memory, see pcm_is_device)
+ *   frames            frames in this piece
+ *   first_start_sample RawSegment.start_sample of the first window of this piece (0 for a
+ *                     whole file); only feeds the start_sample / time outputs
+ *   is_eof            1: this piece ends the file -> emit the zero-padded tail windows
+ *                     (decode.rs:175-196); 0: emit full windows only and report how many
+ *                     frames were consumed so the caller re-presents the rest
+ *   pad_to_batch      > 0: rows up to the next multiple are zero segments
+ *                     (processor.rs:239-260); the tensor has nseg_padded rows
+ *   d_segments        out: device pointer to [nseg_padded, segment_samples] f32, plan-owned.
+ *                     Pass d_out_user != NULL to write into caller-owned device memory
+ *                     (e.g. an ORT IoBinding input) of capacity_rows rows instead.
+ *   start_sample, start_time, end_time   host arrays of capacity_rows entries (may be NULL)
+ *   nseg_out          windows produced (valid rows); consumed_frames: frames fully retired
+ *
+ * Asynchronous w.r.t. the host: device work is enqueued on the ctx stream; the host arrays
+ * are filled before return (they are pure host arithmetic). */
+int32_t bb_frontend_run(bb_plan*, const void* pcm, uint64_t frames, int32_t pcm_is_device,
+                        uint64_t first_start_sample, int32_t is_eof, uint32_t pad_to_batch,
+                        float* d_out_user, uint64_t capacity_rows,
+                        float** d_segments, uint64_t* start_sample, float* start_time,
+                        float* end_time, uint64_t* nseg_out, uint64_t* nseg_padded,
+                        uint64_t* consumed_frames);
+
+/* ------------------------------------------------------------------------------------------
+ * Post-inference: activation -> top-k + threshold -> range / species mask -> threshold
+ * Replaces the tail of birdnet_onnx::Classifier::predict_batch* (configured at
+ * src/inference/classifier.rs:269-273), BirdClassifier::apply_range_filter
+ * (src/inference/classifier.rs:587-645 -> src/inference/geomodel_filter.rs:45-79) and the
+ * second confidence test at src/pipeline/processor.rs:374.
+ * ---------------------------------------------------------------------------------------- */
+
+typedef enum { BB_ACT_NONE = 0, BB_ACT_SIGMOID = 1, BB_ACT_SOFTMAX = 2 } bb_activation;
+
+typedef struct {
+    int32_t  activation;        /* bb_activation                                              */
+    float    min_confidence;    /* --min-confidence (src/constants.rs:25)                     */
+    uint32_t top_k;             /* DEFAULT_TOP_K = 5 (src/constants.rs:178); 1..BB_MAX_TOP_K  */
+    float    range_threshold;   /* FilterSettings.threshold, inclusive                        */
+    int32_t  keep_unmatched;    /* UnmatchedPolicy::Keep                                      */
+    int32_t  rerank;            /* FilterSettings.rerank                                      */
+} bb_post_cfg;
+
+#define BB_MAX_TOP_K 8
+
+/* d_scores: device [B, C] f32 row-major (model output).  Rows [0, valid_B) are processed
+ * (the rest is batch padding).  d_mask: device [C] f32 dense projection of GeomodelScores,
+ * NaN = label has no geomodel entry, NULL = no range filter.  d_species_keep: device [C] u8,
+ * NULL = no species list (mutually exclusive with d_mask: src/lib.rs:502-520).
+ * Outputs (device, caller- or ctx-owned): index [valid_B, top_k] u32, conf [valid_B, top_k]
+ * f32, count [valid_B] u32 — entries beyond count are index 0xFFFFFFFF / conf 0. */
+int32_t bb_post_run_device(bb_ctx*, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B,
+                           const bb_post_cfg*, const float* d_mask, const uint8_t* d_species_keep,
+                           uint32_t* d_index, float* d_conf, uint32_t* d_count);
+
+/* Same, results copied to host arrays and the stream synchronised before return. */
+int32_t bb_post_run(bb_ctx*, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B,
+                    const bb_post_cfg*, const float* d_mask, const uint8_t* d_species_keep,
+                    uint32_t* h_index, float* h_conf, uint32_t* h_count);
+
+/* Device memory helpers for hosts without a CUDA binding of their own (tests, Rust shim) */
+int32_t bb_dev_alloc(bb_ctx*, uint64_t bytes, void** out);
+void    bb_dev_free(bb_ctx*, void*);
+int32_t bb_memcpy_h2d(bb_ctx*, void* dst_dev, const void* src_host, uint64_t bytes);   /* async */
+int32_t bb_memcpy_d2h(bb_ctx*, void* dst_host, const void* src_dev, uint64_t bytes);   /* async */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIRDA_B200_H */

@@ -1,0 +1,122 @@
+"""Parity of the CUDA post-inference step (through the C ABI) against the oracle."""
+import numpy as np
+import pytest
+
+import birda_b200 as b
+from birda_b200.synth import synth_logits
+from oracle import post as opost
+
+pytestmark = pytest.mark.gpu
+CONF_TOL = 1e-4    # north_star: confidences within 1e-4 absolute
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_post(ctx, scores, valid, cfg, mask=None, keep=None):
+    import torch
+    d = torch.from_numpy(scores).cuda()
+    dm = torch.from_numpy(mask).cuda() if mask is not None else None
+    dk = torch.from_numpy(keep.astype(np.uint8)).cuda() if keep is not None else None
+    idx, conf, cnt = ctx.post_run(d.data_ptr(), scores.shape[0], scores.shape[1], valid, cfg,
+                                  dm.data_ptr() if dm is not None else None, dk.data_ptr() if dk is not None else None)
+    return [[(int(idx[r, j]), np.float32(conf[r, j])) for j in range(int(cnt[r]))] for r in range(valid)]
+
+
+def compare(got, ref, conf_ref_all, min_conf):
+    """Identical detection sets except rows whose decision sits within CONF_TOL of a boundary."""
+    assert len(got) == len(ref)
+    for r, (g, o) in enumerate(zip(got, ref)):
+        gi, oi = [i for i, _ in g], [i for i, _ in o]
+        if gi != oi:
+            # tolerated only at a boundary: some confidence within tol of min_conf or of its neighbour
+            c = np.sort(conf_ref_all[r])[::-1][:8].astype(np.float64)
+            near_thr = np.any(np.abs(c - min_conf) <= CONF_TOL)
+            near_tie = np.any(np.abs(np.diff(c)) <= CONF_TOL)
+            assert near_thr or near_tie, (r, g, o)
+            continue
+        for (i1, c1), (i2, c2) in zip(g, o):
+            assert abs(float(c1) - float(c2)) <= CONF_TOL, (r, i1, c1, c2)
+
+
+@pytest.mark.parametrize("classes,act", [(6522, b.ACT_SIGMOID), (14795, b.ACT_SOFTMAX), (11560, b.ACT_NONE), (265, b.ACT_SIGMOID)])
+def test_post_plain(ctx, classes, act):
+    x = synth_logits(classes, 70, classes)
+    if act == b.ACT_NONE:
+        x = opost.activate(x, opost.ACT_SIGMOID)            # graph already applied the sigmoid
+    if act == b.ACT_SOFTMAX:
+        x[6:, :] *= 3.0                                     # peaky rows so something clears 0.1
+    cfg = b.PostConfig(activation=act, min_confidence=0.1)
+    got = gpu_post(ctx, x, 64, cfg)                         # rows 64..69 are batch padding
+    ref = opost.post_process(x, 64, act, 0.1, 5)
+    compare(got, ref, opost.activate(x, act), 0.1)
+    assert sum(len(r) for r in ref) > 50
+
+
+def test_post_adversarial_rows_exact(ctx):
+    x = synth_logits(1, 8, 6522)
+    got = gpu_post(ctx, x, 8, b.PostConfig(min_confidence=0.1))
+    ref = opost.post_process(x, 8, opost.ACT_SIGMOID, 0.1, 5)
+    assert got[0] == [] and ref[0] == []
+    assert [i for i, _ in got[1]] == [0, 5, 17, 300, 301]          # exact ties: lower index wins
+    assert [i for i, _ in got[4]] == [0, 1, 2, 3, 4]
+    assert [i for i, _ in got[5]] == [6519, 6520, 6521]
+    assert [i for i, _ in got[3]] == [i for i, _ in ref[3]] and len(got[3]) == 5
+
+
+@pytest.mark.parametrize("keep_unmatched,rerank", [(True, False), (False, False), (True, True), (False, True)])
+def test_post_range_mask(ctx, keep_unmatched, rerank):
+    """C5's filter: synthetic mask U(0,1)^2 with 305 NaN entries, threshold 0.01."""
+    C = 6522
+    rng = np.random.default_rng(44)
+    x = synth_logits(5, 96, C)
+    mask = (rng.random(C) ** 2).astype(np.float32)
+    mask[rng.choice(C, 305, replace=False)] = np.nan
+    mask[rng.choice(C, 400, replace=False)] = 0.0
+    mask[7] = np.float32(0.01)                              # exactly at the (inclusive) threshold
+    x[10, 7] = 4.0
+    cfg = b.PostConfig(min_confidence=0.1, range_threshold=0.01, keep_unmatched=keep_unmatched, rerank=rerank)
+    got = gpu_post(ctx, x, 96, cfg, mask=mask)
+    ref = opost.post_process(x, 96, opost.ACT_SIGMOID, 0.1, 5, mask,
+                             opost.FilterSettings(0.01, keep_unmatched, rerank))
+    conf_all = opost.activate(x, opost.ACT_SIGMOID)
+    if rerank:
+        conf_all = conf_all * np.nan_to_num(mask, nan=0.0)[None, :]
+    compare(got, ref, conf_all, 0.1)
+    assert any(7 in [i for i, _ in r] for r in got)
+    plain = opost.post_process(x, 96, opost.ACT_SIGMOID, 0.1, 5)
+    assert sum(map(len, ref)) < sum(map(len, plain))        # the mask removed something
+
+
+def test_post_species_list(ctx):
+    C = 6522
+    x = synth_logits(6, 40, C)
+    keep = np.zeros(C, bool); keep[::3] = True
+    got = gpu_post(ctx, x, 40, b.PostConfig(min_confidence=0.1), keep=keep)
+    ref = opost.post_process(x, 40, opost.ACT_SIGMOID, 0.1, 5, species_keep=keep)
+    compare(got, ref, opost.activate(x, opost.ACT_SIGMOID), 0.1)
+    assert all(i % 3 == 0 for r in got for i, _ in r)
+
+
+def test_post_min_conf_zero_and_topk(ctx):
+    x = synth_logits(8, 16, 1000)
+    for k in (1, 3, 8):
+        got = gpu_post(ctx, x, 16, b.PostConfig(min_confidence=0.0, top_k=k))
+        ref = opost.post_process(x, 16, opost.ACT_SIGMOID, 0.0, k)
+        compare(got, ref, opost.activate(x, opost.ACT_SIGMOID), 0.0)
+        assert all(len(r) == k for r in got)
+
+
+def test_post_errors(ctx):
+    import torch
+    d = torch.zeros(4, 10, device="cuda")
+    with pytest.raises(b.BirdaError):
+        ctx.post_run(d.data_ptr(), 4, 10, 5, b.PostConfig())          # valid > B
+    with pytest.raises(b.BirdaError):
+        ctx.post_run(d.data_ptr(), 4, 10, 4, b.PostConfig(top_k=9))
+    with pytest.raises(b.BirdaError):
+        ctx.post_run(d.data_ptr(), 4, 10, 4, b.PostConfig(), d.data_ptr(), d.data_ptr())
