@@ -52,7 +52,7 @@ def synth_logits(seed: int, rows: int, classes: int, adversarial: bool = True) -
         x[r, idx] = rng.standard_normal(m).astype(np.float32) + 2.0
     if adversarial and rows >= 6:
         x[0, :] = -20.0                                   # nothing above threshold
-        x[1, :] = -20.0; x[1, [5, 17, 300, 301, 4000 % classes, classes - 1, 0]] = 1.25   # 7 exact ties
+        x[1, :] = -20.0; x[1, [5 % classes, 17 % classes, 300 % classes, 301 % classes, 4000 % classes, classes - 1, 0]] = 1.25   # exact ties
         x[2, :] = -20.0; x[2, 10] = np.float32(np.log(0.1 / 0.9))                        # at the threshold
         x[3, :] = -20.0; x[3, rng.choice(classes, 9, replace=False)] = rng.uniform(0, 3, 9).astype(np.float32)
         x[4, :] = 30.0                                    # everything saturates to 1.0: lowest indices win

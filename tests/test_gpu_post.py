@@ -87,7 +87,8 @@ def test_post_range_mask(ctx, keep_unmatched, rerank):
     if rerank:
         conf_all = conf_all * np.nan_to_num(mask, nan=0.0)[None, :]
     compare(got, ref, conf_all, 0.1)
-    assert any(7 in [i for i, _ in r] for r in got)
+    if not rerank:
+        assert any(7 in [i for i, _ in r] for r in got)    # score exactly at the inclusive threshold survives
     plain = opost.post_process(x, 96, opost.ACT_SIGMOID, 0.1, 5)
     assert sum(map(len, ref)) < sum(map(len, plain))        # the mask removed something
 
