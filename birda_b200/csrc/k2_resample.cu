@@ -17,7 +17,7 @@
 // Bound: FP32 + shared-memory bandwidth, not HBM; algorithmic HBM
 // bytes are the same as K1's.
 #include "common.cuh"
-#include "dft_consts.cuh"
+#include "fft_butterflies.cuh"
 #include <cmath>
 #include <vector>
 
@@ -49,67 +49,6 @@ struct K2Params {
     const float2 *tw_f, *tw_i, *split_f, *split_i, *filt;
     uint32_t buf_len, G, nblk, R, items_per_row;
     uint64_t nitems;
-};
-
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
-// multiply by -i (forward) / +i (inverse)
-template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
-
-template <int R, bool INV> struct Dft;
-
-template <bool INV> struct Dft<2, INV> {
-    static __device__ __forceinline__ void run(float2 (&a)[2]) { float2 t = a[0]; a[0] = cadd(t, a[1]); a[1] = csub(t, a[1]); }
-};
-template <bool INV> struct Dft<4, INV> {
-    static __device__ __forceinline__ void run(float2 (&a)[4]) {
-        float2 t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]), t2 = cadd(a[1], a[3]), t3 = rot90<INV>(csub(a[1], a[3]));
-        a[0] = cadd(t0, t2); a[2] = csub(t0, t2); a[1] = cadd(t1, t3); a[3] = csub(t1, t3);
-    }
-};
-template <bool INV> struct Dft<8, INV> {
-    static __device__ __forceinline__ void run(float2 (&a)[8]) {
-        constexpr float h = 0.70710678118654752440f;
-        float2 e[4] = {a[0], a[2], a[4], a[6]}, o[4] = {a[1], a[3], a[5], a[7]};
-        Dft<4, INV>::run(e); Dft<4, INV>::run(o);
-        // o[k] *= w8^k ; w8 = exp(-+ i pi/4)
-        float2 o1 = INV ? make_float2((o[1].x - o[1].y) * h, (o[1].x + o[1].y) * h) : make_float2((o[1].x + o[1].y) * h, (o[1].y - o[1].x) * h);
-        float2 o2 = rot90<INV>(o[2]);
-        float2 o3 = INV ? make_float2((-o[3].x - o[3].y) * h, (o[3].x - o[3].y) * h) : make_float2((o[3].y - o[3].x) * h, (-o[3].x - o[3].y) * h);
-        a[0] = cadd(e[0], o[0]); a[4] = csub(e[0], o[0]);
-        a[1] = cadd(e[1], o1);   a[5] = csub(e[1], o1);
-        a[2] = cadd(e[2], o2);   a[6] = csub(e[2], o2);
-        a[3] = cadd(e[3], o3);   a[7] = csub(e[3], o3);
-    }
-};
-// odd prime R: pair a[j] with a[R-j]
-template <int R, bool INV> struct Dft {
-    static __device__ __forceinline__ void run(float2 (&a)[R]) {
-        constexpr int H = (R - 1) / 2;
-        float2 sp[H + 1], sm[H + 1];
-#pragma unroll
-        for (int j = 1; j <= H; ++j) { sp[j] = cadd(a[j], a[R - j]); sm[j] = csub(a[j], a[R - j]); }
-        float2 a0 = a[0], b0 = a[0];
-#pragma unroll
-        for (int j = 1; j <= H; ++j) b0 = cadd(b0, sp[j]);
-        a[0] = b0;
-#pragma unroll
-        for (int k = 1; k <= H; ++k) {
-            float2 u = a0, v = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int j = 1; j <= H; ++j) {
-                const float c = DftConst<R>::c((j * k) % R), s = DftConst<R>::s((j * k) % R);
-                u.x = fmaf(sp[j].x, c, u.x); u.y = fmaf(sp[j].y, c, u.y);
-                v.x = fmaf(sm[j].x, s, v.x); v.y = fmaf(sm[j].y, s, v.y);
-            }
-            // forward: b_k = u - i v, b_{R-k} = u + i v ; inverse swaps them
-            float2 miv = make_float2(v.y, -v.x);
-            if (INV) { a[k] = csub(u, miv); a[R - k] = cadd(u, miv); }
-            else     { a[k] = cadd(u, miv); a[R - k] = csub(u, miv); }
-        }
-    }
 };
 
 // One Stockham DIF stage over the G blocks of a round:  y[q + s*(r*p + k)] = DFT_r(x[i + j*nb])_k * w^(s*p*k)
@@ -343,6 +282,7 @@ cudaError_t resampler_dev_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     h.resize(spec.n_keep);
     for (uint32_t k = 0; k < spec.n_keep; ++k) h[k] = make_float2(spec.filt_re[k], spec.filt_im[k]);
     if ((e = upload(h, &rs->d_filt)) != cudaSuccess) return e;
+    if (fast_plan_available(spec.n_in, spec.n_out)) return fast_tables_init(spec, rs);
     return cudaSuccess;
 }
 
@@ -352,6 +292,7 @@ void resampler_dev_free(ResamplerDev* rs) {
     if (rs->d_split_fwd) cudaFree(rs->d_split_fwd);
     if (rs->d_split_inv) cudaFree(rs->d_split_inv);
     if (rs->d_filt) cudaFree(rs->d_filt);
+    fast_tables_free(rs);
     *rs = ResamplerDev();
 }
 
@@ -359,6 +300,9 @@ cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& r
                             uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
                             uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
                             uint64_t resampled_len, float* d_out, int* launches) {
+    if (rs.fast)
+        return launch_resample_fast(st, sm_count, rs, d_pcm, fmt, channels, total_frames, src_seg, hop, nseg, last_start,
+                                    rows_total, seg, resampled_len, d_out, launches);
     if (launches) *launches = 0;
     if (rows_total == 0) return cudaSuccess;
     K2Params P{};
