@@ -155,6 +155,32 @@ def test_resample_parity(ctx, sr, tr, seg, ovl, channels, seconds):
     assert rel_err(out[: res.nseg], ref32.segments.astype(np.float64)) <= RESAMPLE_TOL
 
 
+def test_resample_generic_kernel_path(ctx, monkeypatch):
+    """Rates without a compile-time plan use the generic Stockham kernel; force it for a planned pair too."""
+    monkeypatch.setenv("BIRDA_K2_GENERIC", "1")
+    pcm = synth_pcm(5, 8.0, 44_100, 2)
+    ref = ofe.decode_and_stream(pcm, 2, 44_100, 48_000, 144_000, 72_000, precision="f64")
+    res, out = run_gpu(ctx, pcm, 2, 44_100, 48_000, 144_000, 72_000, b.FMT_S16)
+    assert_tables(res, ref)
+    assert rel_err(out[: res.nseg], ref.segments.astype(np.float64)) <= RESAMPLE_TOL
+    monkeypatch.delenv("BIRDA_K2_GENERIC")
+    # 24 kHz -> 48 kHz (1024 -> 2048 blocks) has no compile-time plan
+    pcm = synth_pcm(6, 7.0, 24_000, 1)
+    ref = ofe.decode_and_stream(pcm, 1, 24_000, 48_000, 144_000, 0, precision="f64")
+    res, out = run_gpu(ctx, pcm, 1, 24_000, 48_000, 144_000, 0, b.FMT_S16)
+    assert_tables(res, ref)
+    assert rel_err(out[: res.nseg], ref.segments.astype(np.float64)) <= RESAMPLE_TOL
+
+
+@pytest.mark.parametrize("dtype,fmt,channels", [(np.int32, b.FMT_S32, 2), (np.float32, b.FMT_F32, 1), (np.int16, b.FMT_S16, 3)])
+def test_resample_other_formats(ctx, dtype, fmt, channels):
+    pcm = synth_pcm(40 + channels, 6.4, 44_100, channels, dtype)
+    ref = ofe.decode_and_stream(pcm, channels, 44_100, 48_000, 144_000, 0, precision="f64")
+    res, out = run_gpu(ctx, pcm, channels, 44_100, 48_000, 144_000, 0, fmt)
+    assert_tables(res, ref)
+    assert rel_err(out[: res.nseg], ref.segments.astype(np.float64)) <= RESAMPLE_TOL
+
+
 def test_resample_many_windows_split_runs(ctx):
     """Few windows -> the kernel splits each window into runs of blocks (recomputed carry)."""
     pcm = synth_pcm(21, 3.4, 44_100, 1)
