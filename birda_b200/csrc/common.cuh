@@ -32,8 +32,9 @@ struct ResamplerDev {
     float2* d_split_inv = nullptr;  // [n_out]  exp(+2*pi*i*k/(2*n_out))
     float2* d_filt = nullptr;       // [n_keep] filter spectrum
     uint32_t buf_len = 0;           // complex elements per ping/pong buffer
-    // fast path (compile-time plan, k2_fast.cu)
+    // warp-per-block path (runtime plan, k2_warp.cu)
     bool fast = false;
+    alignas(8) unsigned char plan_blob[768] = {0};
     float2 *f_twf = nullptr, *f_twi = nullptr, *f_P = nullptr, *f_Q = nullptr, *f_WI = nullptr;
     uint16_t *f_pos_f = nullptr, *f_pos_i = nullptr;
     unsigned long long* f_counter = nullptr;
@@ -77,11 +78,11 @@ cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& r
                             uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
                             uint64_t resampled_len, float* d_out, int* launches);
 cudaError_t resampler_dev_init(const ResamplerSpec& spec, ResamplerDev* rs);
-// K2 fast path: warp-per-block kernels for the compile-time plans of k2_plans.cuh.  k2_fast.cu
-bool        fast_plan_available(uint32_t n_in, uint32_t n_out);
-cudaError_t fast_tables_init(const ResamplerSpec& spec, ResamplerDev* rs);
-void        fast_tables_free(ResamplerDev* rs);
-cudaError_t launch_resample_fast(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
+// K2 warp-per-block kernel (runtime plans; even N_out with supported radices).  k2_warp.cu
+bool        warp_plan_available(const ResamplerSpec& spec);
+cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs);
+void        warp_tables_free(ResamplerDev* rs);
+cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
                                  uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
                                  uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
                                  uint64_t resampled_len, float* d_out, int* launches);

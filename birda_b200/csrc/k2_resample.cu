@@ -282,7 +282,7 @@ cudaError_t resampler_dev_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     h.resize(spec.n_keep);
     for (uint32_t k = 0; k < spec.n_keep; ++k) h[k] = make_float2(spec.filt_re[k], spec.filt_im[k]);
     if ((e = upload(h, &rs->d_filt)) != cudaSuccess) return e;
-    if (fast_plan_available(spec.n_in, spec.n_out)) return fast_tables_init(spec, rs);
+    if (warp_plan_available(spec)) return warp_tables_init(spec, rs);
     return cudaSuccess;
 }
 
@@ -292,7 +292,7 @@ void resampler_dev_free(ResamplerDev* rs) {
     if (rs->d_split_fwd) cudaFree(rs->d_split_fwd);
     if (rs->d_split_inv) cudaFree(rs->d_split_inv);
     if (rs->d_filt) cudaFree(rs->d_filt);
-    fast_tables_free(rs);
+    warp_tables_free(rs);
     *rs = ResamplerDev();
 }
 
@@ -301,7 +301,7 @@ cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& r
                             uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
                             uint64_t resampled_len, float* d_out, int* launches) {
     if (rs.fast)
-        return launch_resample_fast(st, sm_count, rs, d_pcm, fmt, channels, total_frames, src_seg, hop, nseg, last_start,
+        return launch_resample_warp(st, sm_count, rs, d_pcm, fmt, channels, total_frames, src_seg, hop, nseg, last_start,
                                     rows_total, seg, resampled_len, d_out, launches);
     if (launches) *launches = 0;
     if (rows_total == 0) return cudaSuccess;

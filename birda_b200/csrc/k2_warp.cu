@@ -1,0 +1,333 @@
+// K2 warp-per-block resampler kernel (runtime plans; design notes in k2_warp.cuh) and launcher.
+#include "common.cuh"
+#include "k2_warp.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace bb {
+namespace {
+
+using namespace bb::k2w;
+
+constexpr int kMaxWarps = 12;
+constexpr size_t kSmemMax = 227 * 1024;
+
+struct WarpParams {
+    RtPlan plan;
+    const void* pcm; int fmt; uint32_t channels; uint64_t total_frames;
+    uint64_t src_seg, hop, nseg, last_start, rows_total, seg;
+    uint32_t out_len; float* out;
+    const float2 *twf, *twi, *Pt, *Qt, *WI; const uint16_t *pos_f, *pos_i;
+    uint32_t nblk, R, items_per_row; uint64_t nitems;
+    unsigned long long* counter;
+    // shared memory layout (bytes)
+    uint32_t off_twi, off_posf, off_posi, off_P, off_Q, off_WI, tables, per_warp, off_B, off_carry;
+    int warps;
+};
+
+struct DevExec {
+    template <class F> static BB_HD void each(F&& f) {
+#ifdef __CUDA_ARCH__
+        f((int)(threadIdx.x & 31));
+        __syncwarp();
+#endif
+    }
+};
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Sample conversion + downmix of one frame, bit-identical to decode.rs:353-411.  For S16 the integer
+// channel sum is exact (|sum| < 2^24), so (sum * 2^-15) / C equals the reference's f32 sequence.
+struct Source {
+    const void* pcm; const char* pcm_end; int fmt; uint32_t ch; float fch;
+    int kind;          // 0: S16 stereo staged in A   1: S16 mono staged in A   2: direct loads
+    __device__ __noinline__ float direct(uint64_t f) const {
+        if (fmt == BB_S16) {
+            const short* p = reinterpret_cast<const short*>(pcm) + f * ch;
+            int s = 0;
+            for (uint32_t c = 0; c < ch; ++c) s += (int)__ldg(p + c);
+            const float v = __fmul_rn(__int2float_rn(s), 1.0f / 32768.0f);
+            return ch == 1 ? v : __fdiv_rn(v, fch);
+        } else if (fmt == BB_S32) {
+            const int* p = reinterpret_cast<const int*>(pcm) + f * ch;
+            if (ch == 1) return __fmul_rn(__int2float_rn(__ldg(p)), 1.0f / 2147483648.0f);
+            float s = 0.0f;
+            for (uint32_t c = 0; c < ch; ++c) s = __fadd_rn(s, __fmul_rn(__int2float_rn(__ldg(p + c)), 1.0f / 2147483648.0f));
+            return __fdiv_rn(s, fch);
+        } else {
+            const float* p = reinterpret_cast<const float*>(pcm) + f * ch;
+            if (ch == 1) return __ldg(p);
+            float s = 0.0f;
+            for (uint32_t c = 0; c < ch; ++c) s = __fadd_rn(s, __ldg(p + c));
+            return __fdiv_rn(s, fch);
+        }
+    }
+};
+
+// z[n] = x[2n] + i x[2n+1] of one block; `valid` = real samples in the block (zero above)
+struct BlockLoader {
+    const Source* src; const float2* A; uint64_t base; int valid; int shift;
+    __device__ __forceinline__ float2 operator()(int n) const {
+        const int i0 = 2 * n;
+        float re = 0.f, im = 0.f;
+        if (src->kind == 0) {                // slot n holds frames (2n, 2n+1) as two packed L|R words
+            const int2 v = *reinterpret_cast<const int2*>(A + n);
+            re = __fmul_rn(__int2float_rn((int)(short)(v.x & 0xffff) + (v.x >> 16)), 1.0f / 65536.0f);
+            im = __fmul_rn(__int2float_rn((int)(short)(v.y & 0xffff) + (v.y >> 16)), 1.0f / 65536.0f);
+        } else if (src->kind == 1) {         // slot n holds the aligned word(s) covering frames (2n, 2n+1)
+            const int2 v = *reinterpret_cast<const int2*>(A + n);
+            const int w = __funnelshift_r(v.x, v.y, shift);
+            re = __fmul_rn(__int2float_rn((int)(short)(w & 0xffff)), 1.0f / 32768.0f);
+            im = __fmul_rn(__int2float_rn(w >> 16), 1.0f / 32768.0f);
+        } else {
+            if (i0 < valid) re = src->direct(base + i0);
+            if (i0 + 1 < valid) im = src->direct(base + i0 + 1);
+            return make_float2(re, im);
+        }
+        if (i0 >= valid) re = 0.f;
+        if (i0 + 1 >= valid) im = 0.f;
+        return make_float2(re, im);
+    }
+};
+
+// stage the raw PCM of one block into A with cp.async (A is dead between the split pass of the
+// previous block and the first stage of this one).  Returns the funnel shift for mono.
+__device__ __forceinline__ int prefetch_block(const Source& s, float2* A, uint64_t base, int valid, int half_in, int lane) {
+    int shift = 0;
+    if (s.kind == 0) {
+        const char* g0 = reinterpret_cast<const char*>(s.pcm) + base * 4;
+        const bool al8 = (reinterpret_cast<uintptr_t>(g0) & 7) == 0;
+        for (int n = lane; n < half_in; n += 32) {
+            if (2 * n >= valid) break;
+            const char* g = g0 + (size_t)n * 8;
+            const long long room = s.pcm_end - g;
+            if (al8) cp_async8(A + n, g, room >= 8 ? 8 : (room > 0 ? (int)room : 0));
+            else {
+                cp_async4(A + n, g, room >= 4 ? 4 : 0);
+                cp_async4(reinterpret_cast<char*>(A + n) + 4, g + 4, room >= 8 ? 4 : 0);
+            }
+        }
+    } else if (s.kind == 1) {
+        const char* g0 = reinterpret_cast<const char*>(s.pcm) + base * 2;
+        const bool odd = (reinterpret_cast<uintptr_t>(g0) & 3) != 0;    // frame pair starts mid-word
+        shift = odd ? 16 : 0;
+        g0 -= odd ? 2 : 0;
+        for (int n = lane; n < half_in; n += 32) {
+            if (2 * n >= valid) break;
+            const char* g = g0 + (size_t)n * 4;
+            const long long room = s.pcm_end - g;
+            cp_async4(A + n, g, room >= 4 ? 4 : (room > 0 ? (int)room : 0));
+            if (odd) cp_async4(reinterpret_cast<char*>(A + n) + 4, g + 4, room >= 8 ? 4 : (room > 4 ? (int)(room - 4) : 0));
+        }
+    }
+    return shift;
+}
+
+struct DevSink {
+    float* p; int lim; bool vec;
+    __device__ __forceinline__ void operator()(int n, float2 y) const {
+        const int o = 2 * n;
+        if (vec && o + 1 < lim) *reinterpret_cast<float2*>(p + o) = y;
+        else { if (o < lim) p[o] = y.x; if (o + 1 < lim) p[o + 1] = y.y; }
+    }
+};
+
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+resample_warp_kernel(const __grid_constant__ WarpParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const RtPlan& PL = P.plan;
+    float2* s_twf = reinterpret_cast<float2*>(smem);
+    float2* s_twi = reinterpret_cast<float2*>(smem + P.off_twi);
+    uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + P.off_posf);
+    uint16_t* s_posi = reinterpret_cast<uint16_t*>(smem + P.off_posi);
+    float2* s_P = reinterpret_cast<float2*>(smem + P.off_P);
+    float2* s_Q = reinterpret_cast<float2*>(smem + P.off_Q);
+    float2* s_WI = reinterpret_cast<float2*>(smem + P.off_WI);
+    const int NT = blockDim.x;
+    for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = P.twf[i];
+    for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = P.twi[i];
+    for (int i = threadIdx.x; i < PL.N; i += NT) s_posf[i] = P.pos_f[i];
+    for (int i = threadIdx.x; i < PL.M; i += NT) s_posi[i] = P.pos_i[i];
+    for (int i = threadIdx.x; i < PL.nkeep; i += NT) { s_P[i] = P.Pt[i]; s_Q[i] = P.Qt[i]; }
+    for (int i = threadIdx.x; i <= PL.M / 2; i += NT) s_WI[i] = P.WI[i];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem + P.tables + (size_t)warp * P.per_warp;
+    float2* A = reinterpret_cast<float2*>(wbase);
+    float2* B = reinterpret_cast<float2*>(wbase + P.off_B);
+    float2* carry = reinterpret_cast<float2*>(wbase + P.off_carry);
+    const Tables T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
+    const int N = PL.N, M = PL.M;
+
+    Source src;
+    src.pcm = P.pcm; src.fmt = P.fmt; src.ch = P.channels; src.fch = (float)P.channels;
+    const uint32_t bps = P.fmt == BB_S16 ? 2u : 4u;
+    src.pcm_end = reinterpret_cast<const char*>(P.pcm) + P.total_frames * P.channels * bps;
+    src.kind = 2;
+    if (P.fmt == BB_S16 && P.channels == 2 && (reinterpret_cast<uintptr_t>(P.pcm) & 3) == 0) src.kind = 0;
+    if (P.fmt == BB_S16 && P.channels == 1 && (reinterpret_cast<uintptr_t>(P.pcm) & 1) == 0) src.kind = 1;
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(P.counter, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= P.nitems) break;
+        const uint64_t row = item / P.items_per_row;
+        const uint32_t it = (uint32_t)(item - row * P.items_per_row);
+        float* __restrict__ orow = P.out + row * P.seg;
+        const uint32_t b0 = it * P.R;
+        const uint32_t b1 = min(b0 + P.R, P.nblk);
+        const bool last_item = it + 1 == P.items_per_row;
+        const uint32_t o_lo = min(b0 * (uint32_t)M, P.out_len);
+        const uint32_t o_hi = last_item ? P.out_len : min(b1 * (uint32_t)M, P.out_len);
+        if (row >= P.nseg) {                         // batch-padding row: zeros (processor.rs:239-260)
+            const uint64_t z_hi = last_item ? P.seg : o_hi;
+            for (uint64_t j = o_lo + lane; j < z_hi; j += 32) orow[j] = 0.0f;
+            continue;
+        }
+        if (last_item) for (uint64_t j = P.out_len + lane; j < P.seg; j += 32) orow[j] = 0.0f;
+        if (b0 >= b1) continue;
+        const uint64_t start = (row + 1 == P.nseg) ? P.last_start : row * P.hop;
+        const uint64_t take = P.total_frames - start < P.src_seg ? P.total_frames - start : P.src_seg;
+        auto valid_of = [&](uint32_t b) -> int {
+            const uint64_t q0 = (uint64_t)b * N;
+            return q0 < take ? (int)(take - q0 < (uint64_t)N ? take - q0 : (uint64_t)N) : 0;
+        };
+
+        for (int j = lane; j < M / 2; j += 32) carry[j] = make_float2(0.f, 0.f);
+        const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 7) == 0);      // M is even: b*M keeps 8-byte alignment
+        const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
+        __syncwarp();
+        int shift = prefetch_block(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), PL.half_in, lane);
+        for (uint32_t b = bfirst; b < b1; ++b) {
+            cp_async_wait_all();
+            __syncwarp();
+            BlockLoader ld{&src, A, start + (uint64_t)b * N, valid_of(b), shift};
+            DevSink sink;
+            const int64_t lim = (int64_t)o_hi - (int64_t)b * M;
+            sink.p = orow + (size_t)b * M;
+            sink.lim = b < b0 ? 0 : (int)(lim < 0 ? 0 : (lim > M ? M : lim));   // recomputed block: carry only
+            sink.vec = vec;
+            int next_shift = 0;
+            process_block<DevExec>(PL, T, A, B, carry, ld, sink, [&] {
+                if (b + 1 < b1) next_shift = prefetch_block(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), PL.half_in, lane);
+            });
+            shift = next_shift;
+        }
+    }
+}
+
+}  // namespace
+
+bool warp_plan_available(const ResamplerSpec& spec) {
+    if (const char* g = std::getenv("BIRDA_K2_GENERIC")) if (g[0] == '1') return false;
+    RtPlan P; std::vector<int> f, i;
+    if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &f, &i)) return false;
+    const size_t per_warp = (size_t)spec.n_in * 8 + (size_t)spec.n_out * 8 + (size_t)spec.n_out * 4 + 48;
+    return per_warp + 64 * 1024 < kSmemMax;      // at least one warp next to the tables
+}
+
+cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
+    RtPlan P; std::vector<int> fwd, inv;
+    if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
+    std::vector<uint16_t> pf(P.N), pi_(P.M);
+    build_pos_tables(fwd, inv, P.N, P.M, pf.data(), pi_.data());
+    std::vector<float2> Pt(P.nkeep), Qt(P.nkeep), WI(P.M / 2 + 1), twf(P.twf_len), twi(P.twi_len);
+    build_split_tables(P.N, P.M, P.nkeep, spec.filt_re.data(), spec.filt_im.data(), Pt.data(), Qt.data(), WI.data());
+    build_twiddles(P, twf.data(), twi.data());
+    auto up = [](const void* h, size_t bytes, void** d) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e;
+    if ((e = up(twf.data(), twf.size() * 8, (void**)&rs->f_twf)) != cudaSuccess) return e;
+    if ((e = up(twi.data(), twi.size() * 8, (void**)&rs->f_twi)) != cudaSuccess) return e;
+    if ((e = up(pf.data(), pf.size() * 2, (void**)&rs->f_pos_f)) != cudaSuccess) return e;
+    if ((e = up(pi_.data(), pi_.size() * 2, (void**)&rs->f_pos_i)) != cudaSuccess) return e;
+    if ((e = up(Pt.data(), Pt.size() * 8, (void**)&rs->f_P)) != cudaSuccess) return e;
+    if ((e = up(Qt.data(), Qt.size() * 8, (void**)&rs->f_Q)) != cudaSuccess) return e;
+    if ((e = up(WI.data(), WI.size() * 8, (void**)&rs->f_WI)) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&rs->f_counter, sizeof(unsigned long long))) != cudaSuccess) return e;
+    static_assert(sizeof(RtPlan) <= sizeof(rs->plan_blob), "plan blob too small");
+    memcpy(rs->plan_blob, &P, sizeof(P));
+    rs->fast = true;
+    return cudaSuccess;
+}
+
+void warp_tables_free(ResamplerDev* rs) {
+    void* ptrs[] = {rs->f_twf, rs->f_twi, rs->f_pos_f, rs->f_pos_i, rs->f_P, rs->f_Q, rs->f_WI, rs->f_counter};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    rs->f_twf = rs->f_twi = rs->f_P = rs->f_Q = rs->f_WI = nullptr; rs->f_pos_f = rs->f_pos_i = nullptr; rs->f_counter = nullptr;
+    rs->fast = false;
+}
+
+cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
+                                 uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
+                                 uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
+                                 uint64_t resampled_len, float* d_out, int* launches) {
+    if (launches) *launches = 0;
+    if (rows_total == 0) return cudaSuccess;
+    WarpParams P{};
+    memcpy(&P.plan, rs.plan_blob, sizeof(RtPlan));
+    const RtPlan& PL = P.plan;
+    P.pcm = d_pcm; P.fmt = fmt; P.channels = channels; P.total_frames = total_frames;
+    P.src_seg = src_seg; P.hop = hop; P.nseg = nseg; P.last_start = last_start; P.rows_total = rows_total; P.seg = seg;
+    P.out_len = (uint32_t)(resampled_len < seg ? resampled_len : seg);
+    P.out = d_out;
+    P.twf = rs.f_twf; P.twi = rs.f_twi; P.Pt = rs.f_P; P.Qt = rs.f_Q; P.WI = rs.f_WI; P.pos_f = rs.f_pos_f; P.pos_i = rs.f_pos_i;
+    P.counter = rs.f_counter;
+    P.nblk = (P.out_len + rs.n_out - 1) / rs.n_out;
+    if (P.nblk == 0) P.nblk = 1;
+    auto a16 = [](size_t x) { return (uint32_t)((x + 15) & ~(size_t)15); };
+    P.off_twi = a16((size_t)PL.twf_len * 8);
+    P.off_posf = P.off_twi + a16((size_t)PL.twi_len * 8);
+    P.off_posi = P.off_posf + a16((size_t)PL.N * 2);
+    P.off_P = P.off_posi + a16((size_t)PL.M * 2);
+    P.off_Q = P.off_P + a16((size_t)PL.nkeep * 8);
+    P.off_WI = P.off_Q + a16((size_t)PL.nkeep * 8);
+    P.tables = P.off_WI + a16((size_t)(PL.M / 2 + 1) * 8);
+    P.off_B = a16((size_t)PL.N * 8);
+    P.off_carry = P.off_B + a16((size_t)PL.M * 8);
+    P.per_warp = P.off_carry + a16((size_t)(PL.M / 2) * 8);
+    int warps = (int)((kSmemMax - P.tables) / P.per_warp);
+    if (warps > kMaxWarps) warps = kMaxWarps;
+    if (warps < 1) return cudaErrorInvalidConfiguration;
+    P.warps = warps;
+    const size_t smem = P.tables + (size_t)warps * P.per_warp;
+    const uint64_t total_warps = (uint64_t)sm_count * warps;
+    // blocks per work item: aim for >= 8 items per warp, keep the recomputed block a small fraction
+    uint32_t R = P.nblk;
+    const uint64_t want_items = total_warps * 8;
+    if (rows_total < want_items) {
+        uint64_t per_row = (want_items + rows_total - 1) / rows_total;
+        R = (uint32_t)((P.nblk + per_row - 1) / per_row);
+        if (R < 16) R = 16;
+        if (R > P.nblk) R = P.nblk;
+    }
+    P.R = R;
+    P.items_per_row = (P.nblk + R - 1) / R;
+    P.nitems = rows_total * P.items_per_row;
+    cudaError_t e = cudaFuncSetAttribute(resample_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    uint64_t ctas = (P.nitems + warps - 1) / warps;
+    if (ctas > (uint64_t)sm_count) ctas = sm_count;
+    resample_warp_kernel<<<(unsigned)ctas, warps * 32, smem, st>>>(P);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && launches) *launches = 1;
+    return e;
+}
+
+}  // namespace bb

@@ -1,0 +1,335 @@
+// K2 warp-per-block resampler core with RUNTIME plans (product code).
+//
+// One warp owns a run of consecutive resampler blocks of one window:
+//   * forward half-length complex FFT in place (decimation in frequency: natural order in,
+//     digit-reversed out) in buffer A; inverse in place (decimation in time: digit-reversed in,
+//     natural order out) in buffer B; the fused split / filter / re-bin / inverse-pack pass
+//     between them absorbs both permutations through two small index tables;
+//   * radices and strides come from a small stage table, so ONE code body per (radix,
+//     direction) serves every stage and every rate pair — the kernel stays a few thousand
+//     instructions and lives in the instruction cache (the fully unrolled compile-time-plan
+//     variant was 190 KB of SASS and stalled 29 % of the time on instruction fetch);
+//   * twiddles: one conflict-free table read (w^1) per butterfly plus an in-register power chain;
+//   * the overlap-add carry is per-warp shared memory; the last inverse stage adds it and stores
+//     straight to the output tensor.
+// Everything is __host__ __device__ so tests/host_k2_check.cu runs the same code on the CPU.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <vector>
+#include "fft_butterflies.cuh"
+
+namespace bb {
+namespace k2w {
+
+constexpr int kMaxStages = 8;
+
+struct RtStage {
+    int radix;      // butterfly size
+    int span;       // DIF: sub-transform length n_t;  DIT: n_t = m * radix
+    int m;          // DIF: n_t / radix;               DIT: product of the previous radices
+    int nbf;        // butterflies in the stage = total / radix
+    int tw_off;     // offset of this stage's compact twiddle table (entries p in [0, m)); -1 = none
+    uint32_t magic; // ceil(2^32 / m) for q / m  (0 when m == 1)
+};
+
+struct RtPlan {
+    int N, M, nkeep, half_in;    // half_in = ceil(N/2): non-zero inputs of the forward transform
+    int nf, ni;
+    RtStage f[kMaxStages], i[kMaxStages];
+    int twf_len, twi_len;        // compact twiddle table sizes (float2 entries)
+};
+
+BB_HD int fast_div(int q, const RtStage& s) {
+#ifdef __CUDA_ARCH__
+    return s.m == 1 ? q : (int)__umulhi((unsigned)q, s.magic);
+#else
+    return q / s.m;
+#endif
+}
+
+template <int R> BB_HD void twiddle_chain(float2 (&a)[R], float2 w) {
+    float2 pw[R];
+    pw[1] = w;
+#pragma unroll
+    for (int k = 2; k < R; ++k) pw[k] = cmul(pw[k / 2], pw[k - k / 2]);
+#pragma unroll
+    for (int k = 1; k < R; ++k) a[k] = cmul(a[k], pw[k]);
+}
+
+// ---- forward DIF stage, in place
+template <int R>
+BB_HD void dif_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int lane) {
+    const int m = s.m;
+#pragma unroll 1
+    for (int q = lane; q < s.nbf; q += 32) {
+        const int sb = fast_div(q, s), p = q - sb * m;
+        float2* __restrict__ e = buf + sb * s.span + p;
+        float2 a[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j] = e[j * m];
+        Dft<R, false>::run(a);
+        if (s.tw_off >= 0) twiddle_chain<R>(a, tw[s.tw_off + p]);
+#pragma unroll
+        for (int k = 0; k < R; ++k) e[k * m] = a[k];
+    }
+}
+
+// first forward stage: input z[n] comes from `ld(n)` for n < half_in, zero above
+template <int R, class Loader>
+BB_HD void dif_first(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int half_in,
+                     const Loader& ld, int lane) {
+    const int m = s.m;
+#pragma unroll 1
+    for (int q = lane; q < m; q += 32) {
+        float2 a[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int n = q + j * m;
+            a[j] = n < half_in ? ld(n) : make_float2(0.f, 0.f);
+        }
+        Dft<R, false>::run(a);
+        if (s.tw_off >= 0) twiddle_chain<R>(a, tw[s.tw_off + q]);
+        float2* __restrict__ e = buf + q;
+#pragma unroll
+        for (int k = 0; k < R; ++k) e[k * m] = a[k];
+    }
+}
+
+// ---- inverse DIT stage, in place
+template <int R>
+BB_HD void dit_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int lane) {
+    const int m = s.m;
+#pragma unroll 1
+    for (int q = lane; q < s.nbf; q += 32) {
+        const int sb = fast_div(q, s), p = q - sb * m;
+        float2* __restrict__ e = buf + sb * s.span + p;
+        float2 a[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j] = e[j * m];
+        if (s.tw_off >= 0) twiddle_chain<R>(a, tw[s.tw_off + p]);
+        Dft<R, true>::run(a);
+#pragma unroll
+        for (int k = 0; k < R; ++k) e[k * m] = a[k];
+    }
+}
+
+// last inverse stage (span == M): output z'[n] = (y[2n], y[2n+1]).  n < M/2: add the carry and emit;
+// n >= M/2: becomes the carry of the next block.  R even, so both halves of one carry slot belong
+// to the same butterfly (no cross-lane hazard).
+template <int R, class Sink>
+BB_HD void dit_last(const float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s,
+                    float2* __restrict__ carry, const Sink& sink, int lane) {
+    const int m = s.m;
+#pragma unroll 1
+    for (int p = lane; p < m; p += 32) {
+        float2 a[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j] = buf[p + j * m];
+        if (s.tw_off >= 0) twiddle_chain<R>(a, tw[s.tw_off + p]);
+        Dft<R, true>::run(a);
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) {
+            const int n = p + k * m;
+            const float2 c = carry[n];
+            sink(n, make_float2(a[k].x + c.x, a[k].y + c.y));
+            carry[n] = a[k + R / 2];
+        }
+    }
+}
+
+// ---- fused split / filter / re-bin / inverse pack:  A (digit-reversed forward result) -> B
+//   Y(k)  = P[k] Z[k] + Q[k] conj(Z[N-k])                       (k < nkeep, else 0)
+//   Z'(k) = Y(k) + conj(Y(M-k)) + i wi[k] (Y(k) - conj(Y(M-k)))
+BB_HD void split_pass(const float2* __restrict__ A, float2* __restrict__ B, const uint16_t* __restrict__ pos_f,
+                      const uint16_t* __restrict__ pos_i, const float2* __restrict__ Pt, const float2* __restrict__ Qt,
+                      const float2* __restrict__ WI, int N, int M, int nkeep, int lane) {
+    const int half = M / 2;
+#pragma unroll 1
+    for (int k = lane; k <= half; k += 32) {
+        const int k2 = M - k;
+        float2 yk = make_float2(0.f, 0.f), yk2 = make_float2(0.f, 0.f);
+        if (k < nkeep) {
+            const float2 zk = A[pos_f[k == N ? 0 : k]], zn = cconj(A[pos_f[k == 0 ? 0 : N - k]]);
+            yk = cadd(cmul(Pt[k], zk), cmul(Qt[k], zn));
+        }
+        if (k2 < nkeep) {
+            const float2 zk = A[pos_f[k2 == N ? 0 : k2]], zn = cconj(A[pos_f[N - k2]]);
+            yk2 = cadd(cmul(Pt[k2], zk), cmul(Qt[k2], zn));
+        }
+        if (k == 0) { yk.y = 0.f; yk2.y = 0.f; }           // DC / Nyquist are real (realfft ignores their imag)
+        const float2 wi = WI[k];
+        {
+            const float2 e = cadd(yk, cconj(yk2)), o = cmul(wi, csub(yk, cconj(yk2)));
+            B[pos_i[k]] = make_float2(e.x - o.y, e.y + o.x);
+        }
+        if (k != 0 && k2 != k) {
+            const float2 wi2 = make_float2(-wi.x, wi.y);    // exp(i pi (M-k)/M) = -conj(wi)
+            const float2 e = cadd(yk2, cconj(yk)), o = cmul(wi2, csub(yk2, cconj(yk)));
+            B[pos_i[k2]] = make_float2(e.x - o.y, e.y + o.x);
+        }
+    }
+}
+
+// radix dispatch: one code body per (radix, direction) in the whole kernel
+#define BB_K2W_RADIX_SWITCH(R_EXPR, CALL)                                                       \
+    switch (R_EXPR) {                                                                           \
+        case 2: { constexpr int R = 2; CALL; } break;   case 3: { constexpr int R = 3; CALL; } break;   \
+        case 4: { constexpr int R = 4; CALL; } break;   case 5: { constexpr int R = 5; CALL; } break;   \
+        case 6: { constexpr int R = 6; CALL; } break;   case 7: { constexpr int R = 7; CALL; } break;   \
+        case 8: { constexpr int R = 8; CALL; } break;   case 9: { constexpr int R = 9; CALL; } break;   \
+        case 16: { constexpr int R = 16; CALL; } break; case 19: { constexpr int R = 19; CALL; } break; \
+        case 11: { constexpr int R = 11; CALL; } break; case 13: { constexpr int R = 13; CALL; } break; \
+        default: break;                                                                         \
+    }
+#define BB_K2W_EVEN_RADIX_SWITCH(R_EXPR, CALL)                                                  \
+    switch (R_EXPR) {                                                                           \
+        case 2: { constexpr int R = 2; CALL; } break;   case 4: { constexpr int R = 4; CALL; } break;   \
+        case 6: { constexpr int R = 6; CALL; } break;   case 8: { constexpr int R = 8; CALL; } break;   \
+        case 16: { constexpr int R = 16; CALL; } break;                                         \
+        default: break;                                                                         \
+    }
+
+struct Tables {
+    const float2* twf; const float2* twi; const uint16_t* pos_f; const uint16_t* pos_i;
+    const float2* Pt; const float2* Qt; const float2* WI;
+};
+
+// One block.  Exec::each(f) runs f(lane) for every lane of the warp and orders memory between
+// calls (device: __syncwarp; host harness: a loop).  after_split() is called once the forward
+// buffer A is dead (the device kernel starts the next block's PCM prefetch there).
+template <class Exec, class Loader, class Sink, class AfterSplit>
+BB_HD void process_block(const RtPlan& P, const Tables& T, float2* A, float2* B, float2* carry,
+                         const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
+    Exec::each([&](int lane) {
+        BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R>(A, T.twf, P.f[0], P.half_in, ld, lane)))
+    });
+    for (int t = 1; t < P.nf; ++t)
+        Exec::each([&](int lane) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R>(A, T.twf, P.f[t], lane))) });
+    Exec::each([&](int lane) { split_pass(A, B, T.pos_f, T.pos_i, T.Pt, T.Qt, T.WI, P.N, P.M, P.nkeep, lane); });
+    after_split();
+    for (int t = 0; t + 1 < P.ni; ++t)
+        Exec::each([&](int lane) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R>(B, T.twi, P.i[t], lane))) });
+    Exec::each([&](int lane) {
+        BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R>(B, T.twi, P.i[P.ni - 1], carry, sink, lane)))
+    });
+}
+
+// ------------------------------------------------------------------ host-side plan construction
+inline bool radix_supported(int r) {
+    switch (r) { case 2: case 3: case 4: case 5: case 6: case 7: case 8: case 9: case 11: case 13: case 16: case 19: return true; default: return false; }
+}
+
+// factorise into supported radices; `last_even`: the final entry must be even (inverse plan).
+// Order: DIF wants large contiguous runs first and odd strides last; DIT is the mirror image.
+inline bool choose_radices(int n, bool inverse, std::vector<int>* out) {
+    out->clear();
+    std::vector<int> odd, even;
+    int m = n;
+    while (m % 19 == 0) { odd.push_back(19); m /= 19; }
+    while (m % 13 == 0) { odd.push_back(13); m /= 13; }
+    while (m % 11 == 0) { odd.push_back(11); m /= 11; }
+    while (m % 7 == 0) { odd.push_back(7); m /= 7; }
+    while (m % 5 == 0) { odd.push_back(5); m /= 5; }
+    while (m % 9 == 0) { odd.push_back(9); m /= 9; }
+    while (m % 3 == 0) { odd.push_back(3); m /= 3; }
+    int e = 0;
+    while (m % 2 == 0) { ++e; m /= 2; }
+    if (m != 1) return false;
+    if (e > 0) {                         // 2^e as ceil(e/4) radices of 2..16, bits spread evenly
+        const int ns = (e + 3) / 4;
+        for (int t = 0; t < ns; ++t) { int bits = e / ns + (t < e % ns ? 1 : 0); even.push_back(1 << bits); }
+    }
+    // fuse a lone 2 with a 3 into a 6 (one pass less)
+    for (size_t i = 0; i < even.size(); ++i)
+        if (even[i] == 2) {
+            for (size_t j = 0; j < odd.size(); ++j)
+                if (odd[j] == 3) { odd.erase(odd.begin() + j); even[i] = 6; break; }
+            break;
+        }
+    if (inverse) {                       // DIT: odd radices first (odd strides), even ones last
+        if (even.empty()) return false;  // last stage must be even
+        // largest even radix last
+        for (size_t i = 0; i + 1 < even.size(); ++i) if (even[i] > even.back()) std::swap(even[i], even.back());
+        *out = odd; out->insert(out->end(), even.begin(), even.end());
+    } else {                             // DIF: even radices first, odd ones last
+        *out = even; out->insert(out->end(), odd.begin(), odd.end());
+    }
+    if ((int)out->size() > kMaxStages) return false;
+    return true;
+}
+
+inline bool build_plan(int N, int M, int nkeep, RtPlan* P, std::vector<int>* fwd, std::vector<int>* inv) {
+    if (M % 2 != 0 || N >= 65536 || M >= 65536) return false;
+    if (!choose_radices(N, false, fwd) || !choose_radices(M, true, inv)) return false;
+    P->N = N; P->M = M; P->nkeep = nkeep; P->half_in = (N + 1) / 2;
+    P->nf = (int)fwd->size(); P->ni = (int)inv->size();
+    int span = N, off = 0;
+    for (int t = 0; t < P->nf; ++t) {
+        RtStage& s = P->f[t];
+        s.radix = (*fwd)[t]; s.span = span; s.m = span / s.radix; s.nbf = N / s.radix;
+        s.tw_off = (t + 1 < P->nf) ? off : -1;
+        if (s.tw_off >= 0) off += s.m;
+        s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
+        span = s.m;
+    }
+    P->twf_len = off > 0 ? off : 1;
+    int prev = 1; off = 0;
+    for (int t = 0; t < P->ni; ++t) {
+        RtStage& s = P->i[t];
+        s.radix = (*inv)[t]; s.m = prev; s.span = prev * s.radix; s.nbf = M / s.radix;
+        s.tw_off = t > 0 ? off : -1;
+        if (s.tw_off >= 0) off += s.m;
+        s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
+        prev = s.span;
+    }
+    P->twi_len = off > 0 ? off : 1;
+    return true;
+}
+
+// compact per-stage twiddle tables: forward stage t holds exp(-2 pi i p / span_t), p < m_t;
+// inverse stage t holds exp(+2 pi i p / span_t), p < m_t
+inline void build_twiddles(const RtPlan& P, float2* twf, float2* twi) {
+    const double pi = 3.14159265358979323846;
+    for (int t = 0; t < P.nf; ++t) if (P.f[t].tw_off >= 0)
+        for (int p = 0; p < P.f[t].m; ++p) { double a = -2 * pi * p / P.f[t].span; twf[P.f[t].tw_off + p] = make_float2((float)cos(a), (float)sin(a)); }
+    for (int t = 0; t < P.ni; ++t) if (P.i[t].tw_off >= 0)
+        for (int p = 0; p < P.i[t].m; ++p) { double a = 2 * pi * p / P.i[t].span; twi[P.i[t].tw_off + p] = make_float2((float)cos(a), (float)sin(a)); }
+}
+
+inline void build_pos_tables(const std::vector<int>& fwd, const std::vector<int>& inv, int N, int M,
+                             uint16_t* pos_f, uint16_t* pos_i) {
+    for (int k = 0; k < N; ++k) {           // DIF: k = k1 + r1 (k2 + r2 (...)), pos = sum k_t * N/(r1..rt)
+        int rem = k, pos = 0, prod = 1;
+        for (size_t t = 0; t < fwd.size(); ++t) { int d = rem % fwd[t]; rem /= fwd[t]; prod *= fwd[t]; pos += d * (N / prod); }
+        pos_f[k] = (uint16_t)pos;
+    }
+    for (int n = 0; n < M; ++n) {           // DIT: n = j_S + q_S (j_{S-1} + ...), pos = sum j_t * (q1..q_{t-1})
+        int rem = n, pos = 0;
+        for (int t = (int)inv.size() - 1; t >= 0; --t) {
+            int d = rem % inv[t]; rem /= inv[t];
+            int prev = 1; for (int u = 0; u < t; ++u) prev *= inv[u];
+            pos += d * prev;
+        }
+        pos_i[n] = (uint16_t)pos;
+    }
+}
+
+// P = A + B, Q = A - B with A = 0.5 Hf, B = -0.5 i exp(-i pi k / N) Hf;  WI[k] = exp(+i pi k / M)
+inline void build_split_tables(int N, int M, int nkeep, const float* filt_re, const float* filt_im,
+                               float2* Pt, float2* Qt, float2* WI) {
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < nkeep; ++k) {
+        const double hr = filt_re[k], hi = filt_im[k];
+        const double ar = 0.5 * hr, ai = 0.5 * hi;
+        const double wr = cos(-pi * k / N), wi = sin(-pi * k / N);
+        const double xr = wr * hr - wi * hi, xi = wr * hi + wi * hr;      // w H
+        const double br = 0.5 * xi, bi = -0.5 * xr;                        // -0.5 i (w H)
+        Pt[k] = make_float2((float)(ar + br), (float)(ai + bi));
+        Qt[k] = make_float2((float)(ar - br), (float)(ai - bi));
+    }
+    for (int k = 0; k <= M / 2; ++k) WI[k] = make_float2((float)cos(pi * k / M), (float)sin(pi * k / M));
+}
+
+}  // namespace k2w
+}  // namespace bb
