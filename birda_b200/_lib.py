@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libbirda_b200.so")
+lib_path = os.environ.get("BIRDA_B200_LIB") or os.path.join(_HERE, "libbirda_b200.so")   # override: A/B kernel variants
 
 
 class BirdaError(RuntimeError):

@@ -10,7 +10,8 @@ namespace {
 
 using namespace bb::k2w;
 
-constexpr int kMaxWarps = 12;
+constexpr int kMaxThreads = 576;     // 18 warps: register cap 112 per thread
+constexpr int kMaxGroups = 15;       // one named barrier per group (ids 1..15)
 constexpr size_t kSmemMax = 227 * 1024;
 
 struct WarpParams {
@@ -22,15 +23,20 @@ struct WarpParams {
     uint32_t nblk, R, items_per_row; uint64_t nitems;
     unsigned long long* counter;
     // shared memory layout (bytes)
-    uint32_t off_twi, off_posf, off_posi, off_P, off_Q, off_WI, tables, per_warp, off_B, off_carry;
-    int warps;
+    uint32_t off_twi, off_posf, off_posi, off_P, off_Q, off_WI, off_items, tables, per_group, off_B, off_carry;
+    int groups, gw;                    // thread groups per CTA, warps per group (a group owns one block at a time)
 };
 
 struct DevExec {
-    template <class F> static BB_HD void each(F&& f) {
+    int glane, nl, bar_id;
+    __device__ __forceinline__ void sync() const {
+        if (nl == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nl) : "memory");
+    }
+    template <class F> BB_HD void each(F&& f) const {
 #ifdef __CUDA_ARCH__
-        f((int)(threadIdx.x & 31));
-        __syncwarp();
+        f(glane, nl);
+        sync();
 #endif
     }
 };
@@ -101,12 +107,12 @@ struct BlockLoader {
 
 // stage the raw PCM of one block into A with cp.async (A is dead between the split pass of the
 // previous block and the first stage of this one).  Returns the funnel shift for mono.
-__device__ __forceinline__ int prefetch_block(const Source& s, float2* A, uint64_t base, int valid, int half_in, int lane) {
+__device__ __forceinline__ int prefetch_block(const Source& s, float2* A, uint64_t base, int valid, int half_in, int lane, int nl) {
     int shift = 0;
     if (s.kind == 0) {
         const char* g0 = reinterpret_cast<const char*>(s.pcm) + base * 4;
         const bool al8 = (reinterpret_cast<uintptr_t>(g0) & 7) == 0;
-        for (int n = lane; n < half_in; n += 32) {
+        for (int n = lane; n < half_in; n += nl) {
             if (2 * n >= valid) break;
             const char* g = g0 + (size_t)n * 8;
             const long long room = s.pcm_end - g;
@@ -121,7 +127,7 @@ __device__ __forceinline__ int prefetch_block(const Source& s, float2* A, uint64
         const bool odd = (reinterpret_cast<uintptr_t>(g0) & 3) != 0;    // frame pair starts mid-word
         shift = odd ? 16 : 0;
         g0 -= odd ? 2 : 0;
-        for (int n = lane; n < half_in; n += 32) {
+        for (int n = lane; n < half_in; n += nl) {
             if (2 * n >= valid) break;
             const char* g = g0 + (size_t)n * 4;
             const long long room = s.pcm_end - g;
@@ -141,7 +147,7 @@ struct DevSink {
     }
 };
 
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 resample_warp_kernel(const __grid_constant__ WarpParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const RtPlan& PL = P.plan;
@@ -161,11 +167,18 @@ resample_warp_kernel(const __grid_constant__ WarpParams P) {
     for (int i = threadIdx.x; i <= PL.M / 2; i += NT) s_WI[i] = P.WI[i];
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem + P.tables + (size_t)warp * P.per_warp;
-    float2* A = reinterpret_cast<float2*>(wbase);
-    float2* B = reinterpret_cast<float2*>(wbase + P.off_B);
-    float2* carry = reinterpret_cast<float2*>(wbase + P.off_carry);
+    const int warp = threadIdx.x >> 5;
+    const int group = warp / P.gw;
+    DevExec ex;
+    ex.nl = P.gw * 32;
+    ex.glane = (warp - group * P.gw) * 32 + (int)(threadIdx.x & 31);
+    ex.bar_id = 1 + group;
+    const int lane = ex.glane, nl = ex.nl;
+    unsigned long long* s_items = reinterpret_cast<unsigned long long*>(smem + P.off_items);
+    unsigned char* gbase = smem + P.tables + (size_t)group * P.per_group;
+    float2* A = reinterpret_cast<float2*>(gbase);
+    float2* B = reinterpret_cast<float2*>(gbase + P.off_B);
+    float2* carry = reinterpret_cast<float2*>(gbase + P.off_carry);
     const Tables T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
     const int N = PL.N, M = PL.M;
 
@@ -178,9 +191,10 @@ resample_warp_kernel(const __grid_constant__ WarpParams P) {
     if (P.fmt == BB_S16 && P.channels == 1 && (reinterpret_cast<uintptr_t>(P.pcm) & 1) == 0) src.kind = 1;
 
     for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(P.counter, 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
+        if (lane == 0) s_items[group] = atomicAdd(P.counter, 1ull);
+        ex.sync();
+        const unsigned long long item = s_items[group];
+        ex.sync();
         if (item >= P.nitems) break;
         const uint64_t row = item / P.items_per_row;
         const uint32_t it = (uint32_t)(item - row * P.items_per_row);
@@ -192,10 +206,10 @@ resample_warp_kernel(const __grid_constant__ WarpParams P) {
         const uint32_t o_hi = last_item ? P.out_len : min(b1 * (uint32_t)M, P.out_len);
         if (row >= P.nseg) {                         // batch-padding row: zeros (processor.rs:239-260)
             const uint64_t z_hi = last_item ? P.seg : o_hi;
-            for (uint64_t j = o_lo + lane; j < z_hi; j += 32) orow[j] = 0.0f;
+            for (uint64_t j = o_lo + lane; j < z_hi; j += nl) orow[j] = 0.0f;
             continue;
         }
-        if (last_item) for (uint64_t j = P.out_len + lane; j < P.seg; j += 32) orow[j] = 0.0f;
+        if (last_item) for (uint64_t j = P.out_len + lane; j < P.seg; j += nl) orow[j] = 0.0f;
         if (b0 >= b1) continue;
         const uint64_t start = (row + 1 == P.nseg) ? P.last_start : row * P.hop;
         const uint64_t take = P.total_frames - start < P.src_seg ? P.total_frames - start : P.src_seg;
@@ -204,14 +218,13 @@ resample_warp_kernel(const __grid_constant__ WarpParams P) {
             return q0 < take ? (int)(take - q0 < (uint64_t)N ? take - q0 : (uint64_t)N) : 0;
         };
 
-        for (int j = lane; j < M / 2; j += 32) carry[j] = make_float2(0.f, 0.f);
+        for (int j = lane; j < M / 2; j += nl) carry[j] = make_float2(0.f, 0.f);
         const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 7) == 0);      // M is even: b*M keeps 8-byte alignment
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
-        __syncwarp();
-        int shift = prefetch_block(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), PL.half_in, lane);
+        int shift = prefetch_block(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), PL.half_in, lane, nl);
         for (uint32_t b = bfirst; b < b1; ++b) {
             cp_async_wait_all();
-            __syncwarp();
+            ex.sync();
             BlockLoader ld{&src, A, start + (uint64_t)b * N, valid_of(b), shift};
             DevSink sink;
             const int64_t lim = (int64_t)o_hi - (int64_t)b * M;
@@ -219,8 +232,8 @@ resample_warp_kernel(const __grid_constant__ WarpParams P) {
             sink.lim = b < b0 ? 0 : (int)(lim < 0 ? 0 : (lim > M ? M : lim));   // recomputed block: carry only
             sink.vec = vec;
             int next_shift = 0;
-            process_block<DevExec>(PL, T, A, B, carry, ld, sink, [&] {
-                if (b + 1 < b1) next_shift = prefetch_block(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), PL.half_in, lane);
+            process_block(ex, PL, T, A, B, carry, ld, sink, [&] {
+                if (b + 1 < b1) next_shift = prefetch_block(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), PL.half_in, lane, nl);
             });
             shift = next_shift;
         }
@@ -233,8 +246,8 @@ bool warp_plan_available(const ResamplerSpec& spec) {
     if (const char* g = std::getenv("BIRDA_K2_GENERIC")) if (g[0] == '1') return false;
     RtPlan P; std::vector<int> f, i;
     if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &f, &i)) return false;
-    const size_t per_warp = (size_t)spec.n_in * 8 + (size_t)spec.n_out * 8 + (size_t)spec.n_out * 4 + 48;
-    return per_warp + 64 * 1024 < kSmemMax;      // at least one warp next to the tables
+    const size_t per_group = (size_t)spec.n_in * 8 + (size_t)spec.n_out * 8 + (size_t)spec.n_out * 4 + 48;
+    return per_group + 80 * 1024 < kSmemMax;     // at least one block in flight next to the tables
 }
 
 cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
@@ -296,16 +309,22 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     P.off_P = P.off_posi + a16((size_t)PL.M * 2);
     P.off_Q = P.off_P + a16((size_t)PL.nkeep * 8);
     P.off_WI = P.off_Q + a16((size_t)PL.nkeep * 8);
-    P.tables = P.off_WI + a16((size_t)(PL.M / 2 + 1) * 8);
+    P.off_items = P.off_WI + a16((size_t)(PL.M / 2 + 1) * 8);
+    P.tables = P.off_items + a16((size_t)kMaxGroups * 8);
     P.off_B = a16((size_t)PL.N * 8);
     P.off_carry = P.off_B + a16((size_t)PL.M * 8);
-    P.per_warp = P.off_carry + a16((size_t)(PL.M / 2) * 8);
-    int warps = (int)((kSmemMax - P.tables) / P.per_warp);
-    if (warps > kMaxWarps) warps = kMaxWarps;
-    if (warps < 1) return cudaErrorInvalidConfiguration;
-    P.warps = warps;
-    const size_t smem = P.tables + (size_t)warps * P.per_warp;
-    const uint64_t total_warps = (uint64_t)sm_count * warps;
+    P.per_group = P.off_carry + a16((size_t)(PL.M / 2) * 8);
+    int groups = (int)((kSmemMax - P.tables) / P.per_group);
+    if (groups > kMaxGroups) groups = kMaxGroups;
+    if (groups < 1) return cudaErrorInvalidConfiguration;
+    int gw = (kMaxThreads / 32) / groups;               // warps cooperating on one block
+    if (gw < 1) { gw = 1; groups = kMaxThreads / 32; }
+    if (gw > 4) gw = 4;
+    if (const char* g = std::getenv("BIRDA_K2_GROUP_WARPS")) { int v = atoi(g); if (v >= 1 && v <= 4 && v * groups * 32 <= kMaxThreads) gw = v; }
+    P.groups = groups; P.gw = gw;
+    const int warps = groups;                           // work items are per group
+    const size_t smem = P.tables + (size_t)groups * P.per_group;
+    const uint64_t total_warps = (uint64_t)sm_count * groups;
     // blocks per work item: aim for >= 8 items per warp, keep the recomputed block a small fraction
     uint32_t R = P.nblk;
     const uint64_t want_items = total_warps * 8;
@@ -324,7 +343,7 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     if (e != cudaSuccess) return e;
     uint64_t ctas = (P.nitems + warps - 1) / warps;
     if (ctas > (uint64_t)sm_count) ctas = sm_count;
-    resample_warp_kernel<<<(unsigned)ctas, warps * 32, smem, st>>>(P);
+    resample_warp_kernel<<<(unsigned)ctas, groups * gw * 32, smem, st>>>(P);
     e = cudaGetLastError();
     if (e == cudaSuccess && launches) *launches = 1;
     return e;

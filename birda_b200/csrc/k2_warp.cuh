@@ -23,6 +23,17 @@ namespace bb {
 namespace k2w {
 
 constexpr int kMaxStages = 8;
+#ifndef BB_K2W_UNROLL
+#define BB_K2W_UNROLL 1
+#endif
+// radices >= this read every twiddle power from a [k][p] table; smaller ones read w^1 and run a
+// power chain in registers (the chain's pw[] array would spill for the big butterflies)
+#ifndef BB_K2W_TABLE_RADIX
+#define BB_K2W_TABLE_RADIX 9
+#endif
+BB_HD constexpr bool tw_table_mode(int radix) { return radix >= BB_K2W_TABLE_RADIX; }
+#define BB_PRAGMA(x) _Pragma(#x)
+#define BB_UNROLL_N(n) BB_PRAGMA(unroll n)
 
 struct RtStage {
     int radix;      // butterfly size
@@ -48,28 +59,34 @@ BB_HD int fast_div(int q, const RtStage& s) {
 #endif
 }
 
-template <int R> BB_HD void twiddle_chain(float2 (&a)[R], float2 w) {
-    float2 pw[R];
-    pw[1] = w;
+// a[k] *= w_span^(p k), k = 1..R-1.  Table layout: chain mode [p] holds w^p; table mode [(k-1)*m + p]
+template <int R> BB_HD void apply_twiddles(float2 (&a)[R], const float2* __restrict__ tw, int m, int p) {
+    if constexpr (tw_table_mode(R)) {
 #pragma unroll
-    for (int k = 2; k < R; ++k) pw[k] = cmul(pw[k / 2], pw[k - k / 2]);
+        for (int k = 1; k < R; ++k) a[k] = cmul(a[k], tw[(k - 1) * m + p]);
+    } else {
+        float2 pw[R];
+        pw[1] = tw[p];
 #pragma unroll
-    for (int k = 1; k < R; ++k) a[k] = cmul(a[k], pw[k]);
+        for (int k = 2; k < R; ++k) pw[k] = cmul(pw[k / 2], pw[k - k / 2]);
+#pragma unroll
+        for (int k = 1; k < R; ++k) a[k] = cmul(a[k], pw[k]);
+    }
 }
 
 // ---- forward DIF stage, in place
 template <int R>
-BB_HD void dif_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int lane) {
+BB_HD void dif_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int lane, int nl) {
     const int m = s.m;
-#pragma unroll 1
-    for (int q = lane; q < s.nbf; q += 32) {
+BB_UNROLL_N(BB_K2W_UNROLL)
+    for (int q = lane; q < s.nbf; q += nl) {
         const int sb = fast_div(q, s), p = q - sb * m;
         float2* __restrict__ e = buf + sb * s.span + p;
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = e[j * m];
         Dft<R, false>::run(a);
-        if (s.tw_off >= 0) twiddle_chain<R>(a, tw[s.tw_off + p]);
+        if (s.tw_off >= 0) apply_twiddles<R>(a, tw + s.tw_off, m, p);
 #pragma unroll
         for (int k = 0; k < R; ++k) e[k * m] = a[k];
     }
@@ -78,10 +95,10 @@ BB_HD void dif_stage(float2* __restrict__ buf, const float2* __restrict__ tw, co
 // first forward stage: input z[n] comes from `ld(n)` for n < half_in, zero above
 template <int R, class Loader>
 BB_HD void dif_first(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int half_in,
-                     const Loader& ld, int lane) {
+                     const Loader& ld, int lane, int nl) {
     const int m = s.m;
-#pragma unroll 1
-    for (int q = lane; q < m; q += 32) {
+BB_UNROLL_N(BB_K2W_UNROLL)
+    for (int q = lane; q < m; q += nl) {
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
@@ -89,7 +106,7 @@ BB_HD void dif_first(float2* __restrict__ buf, const float2* __restrict__ tw, co
             a[j] = n < half_in ? ld(n) : make_float2(0.f, 0.f);
         }
         Dft<R, false>::run(a);
-        if (s.tw_off >= 0) twiddle_chain<R>(a, tw[s.tw_off + q]);
+        if (s.tw_off >= 0) apply_twiddles<R>(a, tw + s.tw_off, m, q);
         float2* __restrict__ e = buf + q;
 #pragma unroll
         for (int k = 0; k < R; ++k) e[k * m] = a[k];
@@ -98,16 +115,16 @@ BB_HD void dif_first(float2* __restrict__ buf, const float2* __restrict__ tw, co
 
 // ---- inverse DIT stage, in place
 template <int R>
-BB_HD void dit_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int lane) {
+BB_HD void dit_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int lane, int nl) {
     const int m = s.m;
-#pragma unroll 1
-    for (int q = lane; q < s.nbf; q += 32) {
+BB_UNROLL_N(BB_K2W_UNROLL)
+    for (int q = lane; q < s.nbf; q += nl) {
         const int sb = fast_div(q, s), p = q - sb * m;
         float2* __restrict__ e = buf + sb * s.span + p;
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = e[j * m];
-        if (s.tw_off >= 0) twiddle_chain<R>(a, tw[s.tw_off + p]);
+        if (s.tw_off >= 0) apply_twiddles<R>(a, tw + s.tw_off, m, p);
         Dft<R, true>::run(a);
 #pragma unroll
         for (int k = 0; k < R; ++k) e[k * m] = a[k];
@@ -119,14 +136,14 @@ BB_HD void dit_stage(float2* __restrict__ buf, const float2* __restrict__ tw, co
 // to the same butterfly (no cross-lane hazard).
 template <int R, class Sink>
 BB_HD void dit_last(const float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s,
-                    float2* __restrict__ carry, const Sink& sink, int lane) {
+                    float2* __restrict__ carry, const Sink& sink, int lane, int nl) {
     const int m = s.m;
-#pragma unroll 1
-    for (int p = lane; p < m; p += 32) {
+BB_UNROLL_N(BB_K2W_UNROLL)
+    for (int p = lane; p < m; p += nl) {
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = buf[p + j * m];
-        if (s.tw_off >= 0) twiddle_chain<R>(a, tw[s.tw_off + p]);
+        if (s.tw_off >= 0) apply_twiddles<R>(a, tw + s.tw_off, m, p);
         Dft<R, true>::run(a);
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) {
@@ -143,10 +160,10 @@ BB_HD void dit_last(const float2* __restrict__ buf, const float2* __restrict__ t
 //   Z'(k) = Y(k) + conj(Y(M-k)) + i wi[k] (Y(k) - conj(Y(M-k)))
 BB_HD void split_pass(const float2* __restrict__ A, float2* __restrict__ B, const uint16_t* __restrict__ pos_f,
                       const uint16_t* __restrict__ pos_i, const float2* __restrict__ Pt, const float2* __restrict__ Qt,
-                      const float2* __restrict__ WI, int N, int M, int nkeep, int lane) {
+                      const float2* __restrict__ WI, int N, int M, int nkeep, int lane, int nl) {
     const int half = M / 2;
-#pragma unroll 1
-    for (int k = lane; k <= half; k += 32) {
+BB_UNROLL_N(BB_K2W_UNROLL)
+    for (int k = lane; k <= half; k += nl) {
         const int k2 = M - k;
         float2 yk = make_float2(0.f, 0.f), yk2 = make_float2(0.f, 0.f);
         if (k < nkeep) {
@@ -195,23 +212,23 @@ struct Tables {
     const float2* Pt; const float2* Qt; const float2* WI;
 };
 
-// One block.  Exec::each(f) runs f(lane) for every lane of the warp and orders memory between
-// calls (device: __syncwarp; host harness: a loop).  after_split() is called once the forward
+// One block.  ex.each(f) runs f(lane, nlanes) for every lane of the thread group that owns the block and
+// orders memory between calls (device: __syncwarp or a named barrier; host harness: a loop).  after_split() is called once the forward
 // buffer A is dead (the device kernel starts the next block's PCM prefetch there).
 template <class Exec, class Loader, class Sink, class AfterSplit>
-BB_HD void process_block(const RtPlan& P, const Tables& T, float2* A, float2* B, float2* carry,
+BB_HD void process_block(const Exec& ex, const RtPlan& P, const Tables& T, float2* A, float2* B, float2* carry,
                          const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
-    Exec::each([&](int lane) {
-        BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R>(A, T.twf, P.f[0], P.half_in, ld, lane)))
+    ex.each([&](int lane, int nl) {
+        BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R>(A, T.twf, P.f[0], P.half_in, ld, lane, nl)))
     });
     for (int t = 1; t < P.nf; ++t)
-        Exec::each([&](int lane) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R>(A, T.twf, P.f[t], lane))) });
-    Exec::each([&](int lane) { split_pass(A, B, T.pos_f, T.pos_i, T.Pt, T.Qt, T.WI, P.N, P.M, P.nkeep, lane); });
+        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R>(A, T.twf, P.f[t], lane, nl))) });
+    ex.each([&](int lane, int nl) { split_pass(A, B, T.pos_f, T.pos_i, T.Pt, T.Qt, T.WI, P.N, P.M, P.nkeep, lane, nl); });
     after_split();
     for (int t = 0; t + 1 < P.ni; ++t)
-        Exec::each([&](int lane) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R>(B, T.twi, P.i[t], lane))) });
-    Exec::each([&](int lane) {
-        BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R>(B, T.twi, P.i[P.ni - 1], carry, sink, lane)))
+        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R>(B, T.twi, P.i[t], lane, nl))) });
+    ex.each([&](int lane, int nl) {
+        BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R>(B, T.twi, P.i[P.ni - 1], carry, sink, lane, nl)))
     });
 }
 
@@ -269,7 +286,7 @@ inline bool build_plan(int N, int M, int nkeep, RtPlan* P, std::vector<int>* fwd
         RtStage& s = P->f[t];
         s.radix = (*fwd)[t]; s.span = span; s.m = span / s.radix; s.nbf = N / s.radix;
         s.tw_off = (t + 1 < P->nf) ? off : -1;
-        if (s.tw_off >= 0) off += s.m;
+        if (s.tw_off >= 0) off += tw_table_mode(s.radix) ? s.m * (s.radix - 1) : s.m;
         s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
         span = s.m;
     }
@@ -279,7 +296,7 @@ inline bool build_plan(int N, int M, int nkeep, RtPlan* P, std::vector<int>* fwd
         RtStage& s = P->i[t];
         s.radix = (*inv)[t]; s.m = prev; s.span = prev * s.radix; s.nbf = M / s.radix;
         s.tw_off = t > 0 ? off : -1;
-        if (s.tw_off >= 0) off += s.m;
+        if (s.tw_off >= 0) off += tw_table_mode(s.radix) ? s.m * (s.radix - 1) : s.m;
         s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
         prev = s.span;
     }
@@ -291,10 +308,17 @@ inline bool build_plan(int N, int M, int nkeep, RtPlan* P, std::vector<int>* fwd
 // inverse stage t holds exp(+2 pi i p / span_t), p < m_t
 inline void build_twiddles(const RtPlan& P, float2* twf, float2* twi) {
     const double pi = 3.14159265358979323846;
-    for (int t = 0; t < P.nf; ++t) if (P.f[t].tw_off >= 0)
-        for (int p = 0; p < P.f[t].m; ++p) { double a = -2 * pi * p / P.f[t].span; twf[P.f[t].tw_off + p] = make_float2((float)cos(a), (float)sin(a)); }
-    for (int t = 0; t < P.ni; ++t) if (P.i[t].tw_off >= 0)
-        for (int p = 0; p < P.i[t].m; ++p) { double a = 2 * pi * p / P.i[t].span; twi[P.i[t].tw_off + p] = make_float2((float)cos(a), (float)sin(a)); }
+    auto fill = [&](const RtStage& s, float2* tw, double sign) {
+        if (s.tw_off < 0) return;
+        const int nk = tw_table_mode(s.radix) ? s.radix - 1 : 1;
+        for (int k = 1; k <= nk; ++k)
+            for (int p = 0; p < s.m; ++p) {
+                const double a = sign * 2 * pi * (double)p * k / s.span;
+                tw[s.tw_off + (k - 1) * s.m + p] = make_float2((float)cos(a), (float)sin(a));
+            }
+    };
+    for (int t = 0; t < P.nf; ++t) fill(P.f[t], twf, -1.0);
+    for (int t = 0; t < P.ni; ++t) fill(P.i[t], twi, 1.0);
 }
 
 inline void build_pos_tables(const std::vector<int>& fwd, const std::vector<int>& inv, int N, int M,

@@ -13,10 +13,11 @@ using namespace bb::k2w;
 typedef std::complex<double> cd;
 
 struct HostExec {
-    template <class F> static void each(F&& f) { for (int l = 0; l < 32; ++l) f(l); }
+    int nl;     // lanes in the group that owns a block (32 = one warp, 64 = two warps, ...)
+    template <class F> void each(F&& f) const { for (int l = 0; l < nl; ++l) f(l, nl); }
 };
 
-static int check(int N, int M) {
+static int check(int N, int M, int nl) {
     const double pi = 3.14159265358979323846;
     const int NKEEP = N < M ? N + 1 : M;
     RtPlan P; std::vector<int> fwd, inv;
@@ -48,7 +49,7 @@ static int check(int N, int M) {
             return make_float2(re, im);
         };
         auto sink = [&](int n, float2 y) { out[b * M + 2 * n] = y.x; out[b * M + 2 * n + 1] = y.y; };
-        process_block<HostExec>(P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
+        process_block(HostExec{nl}, P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
     }
     std::vector<double> ref(NB * M + M, 0.0);
     for (int b = 0; b < NB; ++b) {
@@ -77,7 +78,7 @@ int main() {
     int bad = 0;
     const int cases[][2] = {{1029, 1120}, {1029, 2240}, {1026, 684}, {1024, 512}, {1024, 1536}, {1024, 3072},
                             {1323, 960}, {1323, 1920}, {1024, 2048}, {1026, 342}, {1029, 560}, {1125, 216}, {1024, 256}};
-    for (auto& c : cases) bad += check(c[0], c[1]);
+    for (auto& c : cases) for (int nl : {32, 64}) bad += check(c[0], c[1], nl);
     printf(bad ? "FAILED\n" : "all plans ok\n");
     return bad;
 }
