@@ -228,6 +228,12 @@ void bb_plan_destroy(bb_plan* p) {
     cudaStreamSynchronize(p->ctx->stream);
     if (p->d_pcm) cudaFree(p->d_pcm);
     if (p->d_out) cudaFree(p->d_out);
+    if (p->copy_stream) {
+        cudaStreamSynchronize(p->copy_stream);
+        for (auto& ev : p->ev_piece) if (ev) cudaEventDestroy(ev);
+        if (p->ev_done) cudaEventDestroy(p->ev_done);
+        cudaStreamDestroy(p->copy_stream);
+    }
     resampler_dev_free(&p->rs);
     delete p;
 }
@@ -276,20 +282,8 @@ int32_t bb_frontend_run(bb_plan* p, const void* pcm, uint64_t frames, int32_t pc
     if (rows == 0) return BB_OK;
 
     BB_CUDA_OK(c, cudaSetDevice(c->device));
-    // stage PCM
-    const void* d_pcm = pcm;
-    const uint64_t pcm_bytes = frames * p->channels * p->bytes_per_sample;
-    if (!pcm_is_device) {
-        if (p->d_pcm_bytes < pcm_bytes) {
-            BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-            if (p->d_pcm) cudaFree(p->d_pcm);
-            p->d_pcm = nullptr; p->d_pcm_bytes = 0;
-            BB_CUDA_OK(c, cudaMalloc(&p->d_pcm, pcm_bytes));
-            p->d_pcm_bytes = pcm_bytes;
-        }
-        if (pcm_bytes) BB_CUDA_OK(c, cudaMemcpyAsync(p->d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, c->stream));
-        d_pcm = p->d_pcm;
-    }
+    const uint64_t frame_bytes = (uint64_t)p->channels * p->bytes_per_sample;
+    const uint64_t pcm_bytes = frames * frame_bytes;
     float* d_out = d_out_user;
     if (!d_out) {
         if (p->d_out_rows < rows) {
@@ -301,18 +295,70 @@ int32_t bb_frontend_run(bb_plan* p, const void* pcm, uint64_t frames, int32_t pc
         }
         d_out = p->d_out;
     }
-    cudaError_t e;
-    if (!p->resample) {
-        e = launch_pack(c->stream, c->sm_count, d_pcm, p->fmt, p->channels, frames, p->src_seg, w.hop, nseg,
-                        w.last_start, rows, d_out);
-        c->launches += 1;
-    } else {
+    auto launch_rows = [&](const void* d_pcm, uint64_t row_first, uint64_t row_count) -> cudaError_t {
+        if (row_count == 0) return cudaSuccess;
+        if (!p->resample) {
+            c->launches += 1;
+            return launch_pack(c->stream, c->sm_count, d_pcm, p->fmt, p->channels, frames, p->src_seg, w.hop, nseg,
+                               w.last_start, row_first, row_count, d_out);
+        }
         int n = 0;
-        e = launch_resample(c->stream, c->sm_count, p->rs, d_pcm, p->fmt, p->channels, frames, p->src_seg, w.hop,
-                            nseg, w.last_start, rows, p->seg, p->resampled_len, d_out, &n);
+        cudaError_t e = launch_resample(c->stream, c->sm_count, p->rs, d_pcm, p->fmt, p->channels, frames, p->src_seg, w.hop,
+                                        nseg, w.last_start, row_first, row_count, p->seg, p->resampled_len, d_out, &n);
         c->launches += n;
+        return e;
+    };
+    if (pcm_is_device) {
+        BB_CUDA_OK(c, launch_rows(pcm, 0, rows));
+    } else {
+        // Host PCM: copy in pieces on a second stream so the H2D of piece k+1 overlaps the kernel
+        // of piece k (the copy is the longer leg: PCIe moves ~55 GB/s, the kernels consume faster).
+        if (p->d_pcm_bytes < pcm_bytes) {
+            BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+            if (p->copy_stream) BB_CUDA_OK(c, cudaStreamSynchronize(p->copy_stream));
+            if (p->d_pcm) cudaFree(p->d_pcm);
+            p->d_pcm = nullptr; p->d_pcm_bytes = 0;
+            BB_CUDA_OK(c, cudaMalloc(&p->d_pcm, pcm_bytes ? pcm_bytes : 1));
+            p->d_pcm_bytes = pcm_bytes;
+        }
+        constexpr uint64_t kMinPieceBytes = 8ull << 20;
+        uint64_t npieces = pcm_bytes / kMinPieceBytes;
+        if (npieces > 16) npieces = 16;
+        if (npieces < 1 || nseg < 2) npieces = 1;
+        if (npieces > nseg) npieces = nseg;
+        if (npieces == 1) {
+            if (pcm_bytes) BB_CUDA_OK(c, cudaMemcpyAsync(p->d_pcm, pcm, pcm_bytes, cudaMemcpyHostToDevice, c->stream));
+            BB_CUDA_OK(c, launch_rows(p->d_pcm, 0, rows));
+        } else {
+            if (!p->copy_stream) {
+                BB_CUDA_OK(c, cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+                for (auto& ev : p->ev_piece) BB_CUDA_OK(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                BB_CUDA_OK(c, cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+            }
+            // the copy stream must not overwrite PCM that kernels already queued on the ctx stream still read
+            BB_CUDA_OK(c, cudaEventRecord(p->ev_done, c->stream));
+            BB_CUDA_OK(c, cudaStreamWaitEvent(p->copy_stream, p->ev_done, 0));
+            uint64_t copied = 0, row = 0;
+            for (uint64_t k = 0; k < npieces; ++k) {
+                const uint64_t row_end = (k + 1 == npieces) ? nseg : (nseg * (k + 1)) / npieces;
+                // frames the windows [row, row_end) touch: up to the end of window row_end-1
+                const Window last = w.at(row_end - 1);
+                uint64_t need = last.start + last.take;
+                if (k + 1 == npieces) need = frames;
+                if (need > copied) {
+                    BB_CUDA_OK(c, cudaMemcpyAsync(static_cast<char*>(p->d_pcm) + copied * frame_bytes,
+                                                  static_cast<const char*>(pcm) + copied * frame_bytes,
+                                                  (need - copied) * frame_bytes, cudaMemcpyHostToDevice, p->copy_stream));
+                    copied = need;
+                }
+                BB_CUDA_OK(c, cudaEventRecord(p->ev_piece[k], p->copy_stream));
+                BB_CUDA_OK(c, cudaStreamWaitEvent(c->stream, p->ev_piece[k], 0));
+                const uint64_t rend = (k + 1 == npieces) ? rows : row_end;     // padding rows ride with the last piece
+                BB_CUDA_OK(c, launch_rows(p->d_pcm, row, rend - row));
+                row = rend;
+            }
+        }
     }
-    BB_CUDA_OK(c, e);
     if (d_segments) *d_segments = d_out;
     return BB_OK;
 }

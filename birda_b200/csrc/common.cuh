@@ -55,6 +55,11 @@ struct bb_plan {
     uint64_t resampled_len = 0;           // samples resample() returns for src_seg inputs
     // device buffers
     void* d_pcm = nullptr; uint64_t d_pcm_bytes = 0;
+    // host-input pipeline: H2D pieces on a copy stream overlap the kernels of earlier pieces
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_piece[32] = {nullptr};
+    cudaEvent_t ev_done = nullptr;      // last kernel of the previous run (the copy stream waits on it)
+    bool ev_done_valid = false;
     float* d_out = nullptr; uint64_t d_out_rows = 0;
 };
 
@@ -70,12 +75,12 @@ void set_tls_error(const std::string& m);
 // K1: convert + downmix + window gather + pack (no resampling).  k1_pack.cu
 cudaError_t launch_pack(cudaStream_t st, int sm_count, const void* d_pcm, int fmt, uint32_t channels,
                         uint64_t total_frames, uint64_t seg, uint64_t hop, uint64_t nseg,
-                        uint64_t last_start, uint64_t rows_total, float* d_out);
+                        uint64_t last_start, uint64_t row_first, uint64_t rows_total, float* d_out);
 
 // K2: convert + downmix + window gather + per-window block-FFT resample + pack.  k2_resample.cu
 cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
                             uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
-                            uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
+                            uint64_t nseg, uint64_t last_start, uint64_t row_first, uint64_t rows_total, uint64_t seg,
                             uint64_t resampled_len, float* d_out, int* launches);
 cudaError_t resampler_dev_init(const ResamplerSpec& spec, ResamplerDev* rs);
 // K2 warp-per-block kernel (runtime plans; even N_out with supported radices).  k2_warp.cu
@@ -84,7 +89,7 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs);
 void        warp_tables_free(ResamplerDev* rs);
 cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
                                  uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
-                                 uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
+                                 uint64_t nseg, uint64_t last_start, uint64_t row_first, uint64_t rows_total, uint64_t seg,
                                  uint64_t resampled_len, float* d_out, int* launches);
 void        resampler_dev_free(ResamplerDev* rs);
 

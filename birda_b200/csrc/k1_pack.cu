@@ -70,15 +70,16 @@ __device__ __forceinline__ float4 load4_aligned(const S* __restrict__ p) {
 template <int FMT, int CH_T>
 __global__ void __launch_bounds__(kThreads)
 pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_frames,
-            uint64_t seg, uint64_t hop, uint64_t nseg, uint64_t last_start, uint64_t rows_total,
+            uint64_t seg, uint64_t hop, uint64_t nseg, uint64_t last_start, uint64_t row_first,
             float* __restrict__ out, uint32_t tiles_per_row, uint64_t ntiles) {
     using S = typename SampleT<FMT>::type;
     const S* __restrict__ pcm = static_cast<const S*>(pcm_v);
     const float fch = (float)channels;
     const bool row_vec = (seg % 4 == 0);           // rows are 16-byte aligned
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t row = tile / tiles_per_row;
-        const uint64_t j0  = (tile - row * tiles_per_row) * (uint64_t)kTile;
+        const uint64_t lrow = tile / tiles_per_row;
+        const uint64_t row = row_first + lrow;
+        const uint64_t j0  = (tile - lrow * tiles_per_row) * (uint64_t)kTile;
         uint64_t start = 0, take = 0;
         if (row < nseg) {
             start = (row + 1 == nseg) ? last_start : row * hop;
@@ -128,7 +129,7 @@ pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_fr
 template <int FMT>
 cudaError_t launch_fmt(cudaStream_t st, int sm_count, const void* d_pcm, uint32_t channels,
                        uint64_t total_frames, uint64_t seg, uint64_t hop, uint64_t nseg,
-                       uint64_t last_start, uint64_t rows_total, float* d_out) {
+                       uint64_t last_start, uint64_t row_first, uint64_t rows_total, float* d_out) {
     const uint32_t tiles_per_row = (uint32_t)((seg + kTile - 1) / kTile);
     const uint64_t ntiles = rows_total * tiles_per_row;
     if (ntiles == 0) return cudaSuccess;
@@ -136,13 +137,13 @@ cudaError_t launch_fmt(cudaStream_t st, int sm_count, const void* d_pcm, uint32_
     unsigned grid = (unsigned)(ntiles < want ? ntiles : want);
     if (channels == 1)
         pack_kernel<FMT, 1><<<grid, kThreads, 0, st>>>(d_pcm, channels, total_frames, seg, hop, nseg, last_start,
-                                                       rows_total, d_out, tiles_per_row, ntiles);
+                                                       row_first, d_out, tiles_per_row, ntiles);
     else if (channels == 2)
         pack_kernel<FMT, 2><<<grid, kThreads, 0, st>>>(d_pcm, channels, total_frames, seg, hop, nseg, last_start,
-                                                       rows_total, d_out, tiles_per_row, ntiles);
+                                                       row_first, d_out, tiles_per_row, ntiles);
     else
         pack_kernel<FMT, 0><<<grid, kThreads, 0, st>>>(d_pcm, channels, total_frames, seg, hop, nseg, last_start,
-                                                       rows_total, d_out, tiles_per_row, ntiles);
+                                                       row_first, d_out, tiles_per_row, ntiles);
     return cudaGetLastError();
 }
 
@@ -150,11 +151,11 @@ cudaError_t launch_fmt(cudaStream_t st, int sm_count, const void* d_pcm, uint32_
 
 cudaError_t launch_pack(cudaStream_t st, int sm_count, const void* d_pcm, int fmt, uint32_t channels,
                         uint64_t total_frames, uint64_t seg, uint64_t hop, uint64_t nseg,
-                        uint64_t last_start, uint64_t rows_total, float* d_out) {
+                        uint64_t last_start, uint64_t row_first, uint64_t rows_total, float* d_out) {
     switch (fmt) {
-        case BB_S16: return launch_fmt<BB_S16>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, rows_total, d_out);
-        case BB_S32: return launch_fmt<BB_S32>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, rows_total, d_out);
-        case BB_F32: return launch_fmt<BB_F32>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, rows_total, d_out);
+        case BB_S16: return launch_fmt<BB_S16>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, row_first, rows_total, d_out);
+        case BB_S32: return launch_fmt<BB_S32>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, row_first, rows_total, d_out);
+        case BB_F32: return launch_fmt<BB_F32>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, row_first, rows_total, d_out);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -40,7 +40,7 @@ struct Stage { int radix; uint32_t nb; uint32_t s; FastDiv div_nb, div_s; };
 
 struct K2Params {
     const void* pcm; int fmt; uint32_t channels; uint64_t total_frames;
-    uint64_t src_seg, hop, nseg, last_start, rows_total, seg;
+    uint64_t src_seg, hop, nseg, last_start, rows_total, row_first, seg;
     uint32_t out_len;        // min(resampled_len, seg): samples of each row that come from the resampler
     float* out;
     uint32_t n_in, n_out, n_keep;
@@ -146,8 +146,9 @@ resample_kernel(const K2Params P) {
     for (uint32_t i = threadIdx.x; i < M; i += kThreads) tw_i[i] = __ldg(P.tw_i + i);
 
     for (uint64_t item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-        const uint64_t row = item / P.items_per_row;
-        const uint32_t it  = (uint32_t)(item - row * P.items_per_row);
+        const uint64_t lrow = item / P.items_per_row;
+        const uint64_t row = P.row_first + lrow;
+        const uint32_t it  = (uint32_t)(item - lrow * P.items_per_row);
         float* __restrict__ orow = P.out + row * P.seg;
         const uint32_t b0 = it * P.R;
         const uint32_t b1 = min(b0 + P.R, P.nblk);
@@ -298,16 +299,16 @@ void resampler_dev_free(ResamplerDev* rs) {
 
 cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
                             uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
-                            uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
+                            uint64_t nseg, uint64_t last_start, uint64_t row_first, uint64_t rows_total, uint64_t seg,
                             uint64_t resampled_len, float* d_out, int* launches) {
     if (rs.fast)
         return launch_resample_warp(st, sm_count, rs, d_pcm, fmt, channels, total_frames, src_seg, hop, nseg, last_start,
-                                    rows_total, seg, resampled_len, d_out, launches);
+                                    row_first, rows_total, seg, resampled_len, d_out, launches);
     if (launches) *launches = 0;
     if (rows_total == 0) return cudaSuccess;
     K2Params P{};
     P.pcm = d_pcm; P.fmt = fmt; P.channels = channels; P.total_frames = total_frames;
-    P.src_seg = src_seg; P.hop = hop; P.nseg = nseg; P.last_start = last_start; P.rows_total = rows_total; P.seg = seg;
+    P.src_seg = src_seg; P.hop = hop; P.nseg = nseg; P.last_start = last_start; P.rows_total = rows_total; P.row_first = row_first; P.seg = seg;
     P.out_len = (uint32_t)(resampled_len < seg ? resampled_len : seg);
     P.out = d_out;
     P.n_in = rs.n_in; P.n_out = rs.n_out; P.n_keep = rs.n_keep;

@@ -17,7 +17,7 @@ constexpr size_t kSmemMax = 227 * 1024;
 struct WarpParams {
     RtPlan plan;
     const void* pcm; int fmt; uint32_t channels; uint64_t total_frames;
-    uint64_t src_seg, hop, nseg, last_start, rows_total, seg;
+    uint64_t src_seg, hop, nseg, last_start, rows_total, row_first, seg;
     uint32_t out_len; float* out;
     const float2 *twf, *twi, *Pt, *Qt, *WI; const uint16_t *pos_f, *pos_i;
     uint32_t nblk, R, items_per_row; uint64_t nitems;
@@ -196,8 +196,9 @@ resample_warp_kernel(const __grid_constant__ WarpParams P) {
         const unsigned long long item = s_items[group];
         ex.sync();
         if (item >= P.nitems) break;
-        const uint64_t row = item / P.items_per_row;
-        const uint32_t it = (uint32_t)(item - row * P.items_per_row);
+        const uint64_t lrow = item / P.items_per_row;
+        const uint64_t row = P.row_first + lrow;
+        const uint32_t it = (uint32_t)(item - lrow * P.items_per_row);
         float* __restrict__ orow = P.out + row * P.seg;
         const uint32_t b0 = it * P.R;
         const uint32_t b1 = min(b0 + P.R, P.nblk);
@@ -287,7 +288,7 @@ void warp_tables_free(ResamplerDev* rs) {
 
 cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
                                  uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
-                                 uint64_t nseg, uint64_t last_start, uint64_t rows_total, uint64_t seg,
+                                 uint64_t nseg, uint64_t last_start, uint64_t row_first, uint64_t rows_total, uint64_t seg,
                                  uint64_t resampled_len, float* d_out, int* launches) {
     if (launches) *launches = 0;
     if (rows_total == 0) return cudaSuccess;
@@ -295,7 +296,7 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     memcpy(&P.plan, rs.plan_blob, sizeof(RtPlan));
     const RtPlan& PL = P.plan;
     P.pcm = d_pcm; P.fmt = fmt; P.channels = channels; P.total_frames = total_frames;
-    P.src_seg = src_seg; P.hop = hop; P.nseg = nseg; P.last_start = last_start; P.rows_total = rows_total; P.seg = seg;
+    P.src_seg = src_seg; P.hop = hop; P.nseg = nseg; P.last_start = last_start; P.rows_total = rows_total; P.row_first = row_first; P.seg = seg;
     P.out_len = (uint32_t)(resampled_len < seg ? resampled_len : seg);
     P.out = d_out;
     P.twf = rs.f_twf; P.twi = rs.f_twi; P.Pt = rs.f_P; P.Qt = rs.f_Q; P.WI = rs.f_WI; P.pos_f = rs.f_pos_f; P.pos_i = rs.f_pos_i;
