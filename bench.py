@@ -38,6 +38,16 @@ ALGO_BYTES_FRONT = SECONDS * SRC_RATE * CHANNELS * 2 + 2400 * SEG * 4          #
 ALGO_FLOPS_FRONT = 118_955 * 129 * 2400                                      # 36.8 GFLOP
 
 
+def k2_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch over the bench workload, from the committed
+    ncu --set full capture (profiles/k2_traffic.json); None when no capture exists."""
+    p = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    try:
+        return int(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -128,8 +138,8 @@ def _cpu_worker(args):
     """One bounded sample of the workload through the oracle (reference algorithm restated)."""
     seed, nseg = args
     from birda_b200.synth import synth_logits, synth_pcm
+    from oracle import cport
     from oracle import frontend as ofe
-    from oracle import post as opost
     seconds = (nseg + 1) * 1.5
     pcm = synth_pcm(seed, seconds, SRC_RATE, CHANNELS)
     x = synth_logits(seed, nseg, CLASSES, adversarial=False)
@@ -139,7 +149,7 @@ def _cpu_worker(args):
     t0 = time.perf_counter()
     r = ofe.decode_and_stream(pcm, CHANNELS, SRC_RATE, TGT_RATE, SEG, OVL)
     n = r.segments.shape[0]
-    opost.post_process(x[:n], min(n, nseg), opost.ACT_SIGMOID, 0.1, 5, mask, opost.FilterSettings(0.01, True, False))
+    cport.post(x[:n], min(n, nseg), 1, 0.1, 5, mask, None, 0.01, True, False, threads=1)
     dt = time.perf_counter() - t0
     return dt, seconds
 
@@ -163,7 +173,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nseg = 400                                   # 10 min of audio per worker per step
+    nseg = 200                                   # 5 min of audio per worker per step
     vals = []
     for i in range(args.warmup + args.steps):
         v, wall, _ = cpu_arm(cores, nseg, seed=100 + 1000 * i)
@@ -171,7 +181,8 @@ def run_reference(args):
             vals.append((v, wall))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([w for _, w in vals]) * 1e3)
-    sample = f"{cores} workers x {nseg} windows (10 min of C2 audio each) per step, numpy/pocketfft f32 oracle"
+    sample = (f"{cores} worker processes x {nseg} windows (5 min of C2 audio each) per step; oracle restatement: "
+              "numpy/pocketfft f32 front end + C post step")
     line = {"impl": "reference", "metric": "audio-hours/sec", "value": value, "unit": "audio-h/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -272,7 +283,8 @@ def run_gpu(args):
         e2e = args.steps * hours * world / (ms_e2e / 1e3)
         peak, peak_src = measured_peaks()
         ach = ALGO_BYTES_FRONT / (ms_front / 1e3) / 1e9
-        cpu_v, cpu_wall, _ = cpu_arm(1, 800, seed=7)          # 20 min of audio, one core, ~10 s
+        cores = os.cpu_count() or 1
+        cpu_v, cpu_wall, _ = cpu_arm(cores, 200, seed=7)      # 5 min of audio per core, a few seconds
         line = {
             "metric": "audio-hours/sec", "value": value, "unit": "audio-h/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -284,13 +296,15 @@ def run_gpu(args):
             "e2e": {"value": e2e, "unit": "audio-h/s", "h2d_bytes_per_step": int(h_pcm.numel() * 2),
                     "d2h_bytes_per_step": int(rows * 5 * 8 + rows * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "resample_kernel (K2)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "resample_warp_kernel (K2)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": k2_traffic_bytes(), "algorithmic_bytes": ALGO_BYTES_FRONT,
+                         "peak_source": peak_src,
                          "note": "K2 is FP32/shared-memory bound, not HBM bound (SURVEY 7.3 item 2)",
                          "fp32": {"achieved_tflops": ALGO_FLOPS_FRONT / (ms_front / 1e3) / 1e12, "peak_tflops": 74.5,
                                   "frac": ALGO_FLOPS_FRONT / (ms_front / 1e3) / 1e12 / 74.5}},
-            "cpu_baseline": {"value": cpu_v, "unit": "audio-h/s", "cores": 1, "kind": "port",
-                             "sample": "800 windows (20 min of C2 audio) through the numpy/pocketfft f32 oracle, 1 process"},
+            "cpu_baseline": {"value": cpu_v, "unit": "audio-h/s", "cores": cores, "kind": "port",
+                             "sample": f"{cores} worker processes x 200 windows (5 min of C2 audio each): numpy/pocketfft f32 "
+                                       "front end + C post step (oracle restatement of the reference's CPU path)"},
             "clocks": clocks,
         }
         print(json.dumps(line))

@@ -1,0 +1,117 @@
+//! Raw bindings to `include/birda_b200.h` and the safe wrappers birda's pipeline calls.
+//! Untested source (no Rust toolchain in the build image); the C ABI is what the tests exercise.
+//!
+//! `Cargo.toml:76-77` sets `unsafe_code = "deny"`, so this module carries a scoped allow, as
+//! `src/update/replace.rs:11` does for `libc::getuid`.
+#![allow(unsafe_code)]
+
+use std::ffi::{c_char, c_void, CStr};
+
+use crate::error::{Error, Result};
+
+#[repr(C)] pub struct bb_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct bb_plan { _p: [u8; 0] }
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct bb_post_cfg {
+    pub activation: i32,
+    pub min_confidence: f32,
+    pub top_k: u32,
+    pub range_threshold: f32,
+    pub keep_unmatched: i32,
+    pub rerank: i32,
+}
+
+pub const BB_S16: i32 = 1;
+pub const BB_S32: i32 = 2;
+pub const BB_F32: i32 = 3;
+pub const BB_ERR_OVERLAP_GE_SEGMENT: i32 = -2;
+pub const BB_ERR_UNSUPPORTED_RATE: i32 = -3;
+
+extern "C" {
+    pub fn bb_ctx_create(device: i32, out: *mut *mut bb_ctx) -> i32;
+    pub fn bb_ctx_create_on_stream(device: i32, stream: *mut c_void, out: *mut *mut bb_ctx) -> i32;
+    pub fn bb_ctx_destroy(ctx: *mut bb_ctx);
+    pub fn bb_last_error(ctx: *const bb_ctx) -> *const c_char;
+    pub fn bb_sync(ctx: *mut bb_ctx) -> i32;
+    pub fn bb_host_alloc(bytes: u64, out: *mut *mut c_void) -> i32;
+    pub fn bb_host_free(p: *mut c_void);
+    pub fn bb_plan_create(ctx: *mut bb_ctx, src_rate: u32, channels: u32, fmt: i32, tgt_rate: u32,
+                          segment_samples: u64, overlap_samples: u64, out: *mut *mut bb_plan) -> i32;
+    pub fn bb_plan_destroy(plan: *mut bb_plan);
+    pub fn bb_frontend_run(plan: *mut bb_plan, pcm: *const c_void, frames: u64, pcm_is_device: i32,
+                           first_start_sample: u64, is_eof: i32, pad_to_batch: u32,
+                           d_out_user: *mut f32, capacity_rows: u64, d_segments: *mut *mut f32,
+                           start_sample: *mut u64, start_time: *mut f32, end_time: *mut f32,
+                           nseg_out: *mut u64, nseg_padded: *mut u64, consumed_frames: *mut u64) -> i32;
+    pub fn bb_post_run(ctx: *mut bb_ctx, d_scores: *const f32, b: u32, c: u32, valid_b: u32,
+                       cfg: *const bb_post_cfg, d_mask: *const f32, d_species_keep: *const u8,
+                       h_index: *mut u32, h_conf: *mut f32, h_count: *mut u32) -> i32;
+}
+
+fn check(ctx: *const bb_ctx, code: i32) -> Result<()> {
+    if code == 0 { return Ok(()); }
+    // SAFETY: bb_last_error returns a NUL-terminated string owned by the context (or a thread local).
+    let msg = unsafe { CStr::from_ptr(bb_last_error(ctx)) }.to_string_lossy().into_owned();
+    Err(match code {
+        BB_ERR_OVERLAP_GE_SEGMENT => Error::Internal { message: msg },          // decode.rs:156-162
+        BB_ERR_UNSUPPORTED_RATE => Error::Resample { reason: msg },             // resample.rs:26-28
+        -5 | -6 | -8 => Error::Inference { reason: msg },
+        _ => Error::Internal { message: msg },
+    })
+}
+
+/// One GPU.  Owned by the thread that owns the `BirdClassifier` (processor.rs:659-671).
+pub struct GpuContext { raw: *mut bb_ctx }
+
+impl GpuContext {
+    pub fn new(device: i32) -> Result<Self> {
+        let mut raw = std::ptr::null_mut();
+        // SAFETY: out pointer is valid for the call.
+        check(std::ptr::null(), unsafe { bb_ctx_create(device, &mut raw) })?;
+        Ok(Self { raw })
+    }
+    pub fn sync(&self) -> Result<()> { check(self.raw, unsafe { bb_sync(self.raw) }) }
+}
+impl Drop for GpuContext { fn drop(&mut self) { unsafe { bb_ctx_destroy(self.raw) } } }
+
+/// A batch of packed segments on the device plus the host-side `AudioChunk` time stamps
+/// (`src/audio/chunker.rs:5-12`): what replaces the per-segment `tx.send(Ok(chunk))`.
+pub struct DeviceSegments {
+    pub device_ptr: *mut f32,
+    pub rows: usize,
+    pub valid: usize,
+    pub start_time: Vec<f32>,
+    pub end_time: Vec<f32>,
+}
+
+/// Replaces `StreamingDecoder::next_segment` + `resample_chunk` + resize for one file.
+pub struct GpuFrontEnd { raw: *mut bb_plan, ctx: *const bb_ctx }
+
+impl GpuFrontEnd {
+    pub fn new(ctx: &GpuContext, src_rate: u32, channels: u32, fmt: i32, tgt_rate: u32,
+               segment_samples: usize, overlap_samples: usize) -> Result<Self> {
+        let mut raw = std::ptr::null_mut();
+        check(ctx.raw, unsafe {
+            bb_plan_create(ctx.raw, src_rate, channels, fmt, tgt_rate, segment_samples as u64, overlap_samples as u64, &mut raw)
+        })?;
+        Ok(Self { raw, ctx: ctx.raw })
+    }
+
+    /// `pcm`: interleaved decoded frames in pinned host memory (see `bb_host_alloc`).
+    pub fn run(&mut self, pcm: &[u8], frames: u64, first_start_sample: u64, is_eof: bool, batch: u32,
+               max_rows: usize) -> Result<(DeviceSegments, u64)> {
+        let mut st = vec![0f32; max_rows];
+        let mut et = vec![0f32; max_rows];
+        let (mut d, mut n, mut rows, mut consumed) = (std::ptr::null_mut(), 0u64, 0u64, 0u64);
+        check(self.ctx, unsafe {
+            bb_frontend_run(self.raw, pcm.as_ptr().cast(), frames, 0, first_start_sample, is_eof as i32, batch,
+                            std::ptr::null_mut(), max_rows as u64, &mut d, std::ptr::null_mut(),
+                            st.as_mut_ptr(), et.as_mut_ptr(), &mut n, &mut rows, &mut consumed)
+        })?;
+        st.truncate(n as usize); et.truncate(n as usize);
+        Ok((DeviceSegments { device_ptr: d, rows: rows as usize, valid: n as usize, start_time: st, end_time: et }, consumed))
+    }
+}
+impl Drop for GpuFrontEnd { fn drop(&mut self) { unsafe { bb_plan_destroy(self.raw) } } }
