@@ -1,0 +1,127 @@
+"""Host-side mirror of the reference's per-file pipeline over the C ABI (tests, bench, Python hosts).
+
+Follows `process_file` / `run_streaming_inference` / `process_batch`
+(src/pipeline/processor.rs:418-796, :114-190, :220-410): estimate -> effective batch size -> front end
+-> batches of `batch_size` rows (last one padded with silence) -> classifier -> post step on the valid
+rows -> detections sorted by (start_time asc, confidence desc).  The classifier is any callable mapping
+a device tensor [B, samples] to scores [B, C] (ONNX Runtime with IoBinding in the reference's world; a
+stand-in in the tests) — it is not part of this library.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .api import ACT_SIGMOID, Context, FrontEndPlan, PostConfig, rules
+
+
+@dataclass
+class Detection:
+    """src/output/types.rs:8-23 (fields the writers use)."""
+    scientific_name: str
+    common_name: str
+    confidence: float
+    start_time: float
+    end_time: float
+    index: int
+    segment: int
+
+
+def split_label(label: str) -> Tuple[str, str]:
+    """Detection::from_label: split at the first '_' (src/output/types.rs:58-79)."""
+    if "_" in label:
+        a, b = label.split("_", 1)
+        return a, b
+    return label, label
+
+
+@dataclass
+class ProcessingConfig:
+    """The hot-path subset of src/pipeline/config.rs:32-66 plus the classifier's model facts."""
+    target_rate: int = 48_000
+    segment_duration: float = 3.0
+    overlap: float = 0.0                       # src/constants.rs:28
+    batch_size: int = 64
+    min_confidence: float = 0.1                # src/constants.rs:25
+    top_k: int = 5                             # src/constants.rs:178
+    activation: int = ACT_SIGMOID
+    bat_mode: bool = False                     # processor.rs:464-475
+    range_threshold: float = 0.01
+    keep_unmatched: bool = True
+    rerank: bool = False
+    labels: Optional[Sequence[str]] = None
+    d_mask: Optional[int] = None               # device pointer, [C] f32, NaN = no geomodel entry
+    d_species_keep: Optional[int] = None       # device pointer, [C] u8
+
+
+@dataclass
+class ProcessResult:
+    detections: List[Detection] = field(default_factory=list)
+    segments: int = 0
+    batches: int = 0
+    effective_batch_size: int = 0
+
+
+def sort_detections(dets: List[Detection]) -> List[Detection]:
+    """src/pipeline/processor.rs:178-187 (stable here; the reference's sort is unstable)."""
+    return sorted(dets, key=lambda d: (d.start_time, -d.confidence))
+
+
+class FilePipeline:
+    """One GPU's worker: owns a Context; plans are cached per (rate, channels, format)."""
+
+    def __init__(self, ctx: Context, cfg: ProcessingConfig, classifier: Callable):
+        self.ctx, self.cfg, self.classifier = ctx, cfg, classifier
+        self._plans = {}
+
+    def _plan(self, source_rate: int, channels: int, fmt: int) -> FrontEndPlan:
+        cfg = self.cfg
+        target = source_rate if cfg.bat_mode else cfg.target_rate
+        seg, ovl = rules.segment_samples(cfg.segment_duration, cfg.overlap, target, cfg.bat_mode)
+        key = (source_rate, channels, fmt, target, seg, ovl)
+        if key not in self._plans:
+            self._plans[key] = FrontEndPlan(self.ctx, source_rate, channels, fmt, target, seg, ovl)
+        return self._plans[key]
+
+    def process_pcm(self, pcm, channels: int, source_rate: int, fmt: int, frames: Optional[int] = None) -> ProcessResult:
+        cfg = self.cfg
+        plan = self._plan(source_rate, channels, fmt)
+        n_frames = (pcm.size if isinstance(pcm, np.ndarray) else pcm.numel()) // channels if frames is None else frames
+        seg_dur = float(rules_bat_duration()) if cfg.bat_mode else cfg.segment_duration
+        est = rules.estimate_segment_count(n_frames / source_rate, seg_dur, cfg.overlap)        # processor.rs:525
+        B = max(rules.effective_batch_size(cfg.batch_size, est), 1)                              # processor.rs:531-545
+        segs = plan.run(pcm, frames=n_frames, pad_to_batch=B)
+        res = ProcessResult(segments=segs.nseg, effective_batch_size=B)
+        if segs.nseg == 0:
+            return res
+        x = segs.torch()
+        post = PostConfig(cfg.activation, cfg.min_confidence, cfg.top_k, cfg.range_threshold, cfg.keep_unmatched, cfg.rerank)
+        dets: List[Detection] = []
+        for first in range(0, segs.nseg, B):
+            valid = min(B, segs.nseg - first)
+            scores = self.classifier(x[first:first + B])                                        # [B, C] on the device
+            Bc, C = int(scores.shape[0]), int(scores.shape[1])
+            idx, conf, cnt = self.ctx.post_run(scores.data_ptr(), Bc, C, valid, post, cfg.d_mask, cfg.d_species_keep)
+            res.batches += 1
+            for r in range(valid):                                                               # processor.rs:363-385
+                s = first + r
+                for j in range(int(cnt[r])):
+                    c = float(conf[r, j])
+                    if c >= cfg.min_confidence:
+                        i = int(idx[r, j])
+                        sci, com = split_label(cfg.labels[i]) if cfg.labels is not None else (str(i), str(i))
+                        dets.append(Detection(sci, com, c, float(segs.start_time[s]), float(segs.end_time[s]), i, s))
+        res.detections = sort_detections(dets)
+        return res
+
+    def close(self):
+        for p in self._plans.values():
+            p.close()
+        self._plans.clear()
+
+
+def rules_bat_duration() -> np.float32:
+    """bat::SEGMENT_DURATION = 144000 / 256000 as f32 (src/constants.rs:525-535)."""
+    return np.float32(144_000) / np.float32(256_000)

@@ -1,0 +1,77 @@
+"""Per-file pipeline over the C ABI against the oracle pipeline with the same stand-in classifier."""
+import numpy as np
+import pytest
+
+import birda_b200 as b
+from birda_b200.pipeline import FilePipeline, ProcessingConfig
+from birda_b200.synth import synth_pcm
+from oracle import frontend as ofe
+from oracle import post as opost
+from oracle import rules as orules
+
+pytestmark = pytest.mark.gpu
+
+
+class StandInClassifier:
+    """NOT BirdNET: a fixed random projection of 48 band energies, with the real I/O contract
+    ([B, samples] f32 -> [B, C] f32 logits) so batching / padding / post can be exercised."""
+
+    def __init__(self, samples: int, classes: int, seed: int = 0):
+        import torch
+        g = torch.Generator().manual_seed(seed)
+        self.w = (torch.randn(48, classes, generator=g) * 3.0).cuda()
+        self.bias = (torch.randn(classes, generator=g) * 1.0 - 5.0).cuda()
+        self.frame = samples // 48
+
+    def __call__(self, x):
+        import torch
+        e = x[:, : self.frame * 48].reshape(x.shape[0], 48, self.frame).double().pow(2).mean(dim=2)
+        feat = torch.log10(e + 1e-6).float()
+        return (feat @ self.w + self.bias).contiguous()
+
+
+@pytest.mark.parametrize("sr,channels,overlap,batch,rerank", [(48_000, 1, 0.0, 8, False), (44_100, 2, 1.5, 16, True)])
+def test_pipeline_matches_oracle(sr, channels, overlap, batch, rerank):
+    import torch
+    C = 6522
+    ctx = b.Context(0)
+    labels = [f"Genus{i} species{i}_Common {i}" for i in range(C)]
+    rng = np.random.default_rng(3)
+    mask = (rng.random(C) ** 2).astype(np.float32); mask[rng.choice(C, 305, replace=False)] = np.nan
+    d_mask = torch.from_numpy(mask).cuda()
+    clf = StandInClassifier(144_000, C)
+    cfg = ProcessingConfig(target_rate=48_000, segment_duration=3.0, overlap=overlap, batch_size=batch, min_confidence=0.1,
+                           labels=labels, d_mask=d_mask.data_ptr(), rerank=rerank)
+    pipe = FilePipeline(ctx, cfg, clf)
+    pcm = synth_pcm(11, 61.0, sr, channels)
+    res = pipe.process_pcm(pcm, channels, sr, b.FMT_S16)
+
+    # oracle pipeline: oracle front end, same classifier on the oracle's segments, oracle post
+    seg, ovl = orules.segment_and_overlap_samples(3.0, overlap, 48_000)
+    ref = ofe.decode_and_stream(pcm, channels, sr, 48_000, seg, ovl)
+    est = orules.estimate_segment_count(pcm.size // channels / sr, 3.0, overlap)
+    B = orules.effective_batch_size(batch, est)
+    assert res.effective_batch_size == B and res.segments == ref.segments.shape[0]
+    assert res.batches == len(orules.batch_layout(res.segments, B))
+    dets = []
+    for first, valid, padded in orules.batch_layout(res.segments, B):
+        xb = np.zeros((padded, seg), np.float32); xb[:valid] = ref.segments[first:first + valid]
+        scores = clf(torch.from_numpy(xb).cuda()).cpu().numpy()
+        rows = opost.post_process(scores, valid, opost.ACT_SIGMOID, 0.1, 5, mask, opost.FilterSettings(0.01, True, rerank))
+        dets += opost.extract_detections(rows, ref.start_time, ref.end_time, labels, 0.1, first)
+    dets = opost.sort_detections(dets)
+    got = [(d.segment, d.index) for d in res.detections]
+    want = [(d.segment, d.index) for d in dets]
+    # the stand-in's scores depend on resampled samples (1e-5): allow boundary flips only
+    assert len(set(got) ^ set(want)) <= max(2, len(want) // 50), (len(got), len(want))
+    common = set(got) & set(want)
+    gm = {(d.segment, d.index): d for d in res.detections}
+    for d in dets:
+        if (d.segment, d.index) in common:
+            g = gm[(d.segment, d.index)]
+            assert abs(g.confidence - float(d.confidence)) <= 1e-3
+            assert np.float32(g.start_time) == d.start_time and np.float32(g.end_time) == d.end_time
+            assert g.scientific_name == d.scientific_name
+    st = [d.start_time for d in res.detections]
+    assert st == sorted(st) and len(want) > 10
+    pipe.close(); ctx.close()
