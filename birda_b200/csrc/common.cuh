@@ -35,6 +35,7 @@ struct ResamplerDev {
     // warp-per-block path (runtime plan, k2_warp.cu)
     bool fast = false;
     alignas(8) unsigned char plan_blob[768] = {0};
+    int ct_index = -1;                 // compile-time plan (k2_warp.cuh: BB_K2_CT_PLANS) or -1
     float2 *f_twf = nullptr, *f_twi = nullptr, *f_P = nullptr, *f_Q = nullptr, *f_WI = nullptr;
     uint16_t *f_pos_f = nullptr, *f_pos_i = nullptr;
     unsigned long long* f_counter = nullptr;

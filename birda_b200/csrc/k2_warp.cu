@@ -147,8 +147,30 @@ struct DevSink {
     }
 };
 
-__global__ void __launch_bounds__(kMaxThreads, 1)
-resample_warp_kernel(const __grid_constant__ WarpParams P) {
+// plan views: the runtime plan reads sizes from the stage table, a compile-time plan folds them
+struct RtView {
+    static __device__ __forceinline__ int n(const RtPlan& p) { return p.N; }
+    static __device__ __forceinline__ int m(const RtPlan& p) { return p.M; }
+    static __device__ __forceinline__ int half_in(const RtPlan& p) { return p.half_in; }
+    template <class Exec, class Loader, class Sink, class After>
+    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const Tables& T, float2* A, float2* B,
+                                                 float2* carry, const Loader& ld, const Sink& sink, After&& after) {
+        process_block(ex, p, T, A, B, carry, ld, sink, after);
+    }
+};
+template <class PL> struct CtView {
+    static __device__ __forceinline__ constexpr int n(const RtPlan&) { return PL::N; }
+    static __device__ __forceinline__ constexpr int m(const RtPlan&) { return PL::M; }
+    static __device__ __forceinline__ constexpr int half_in(const RtPlan&) { return PL::HALF_IN; }
+    template <class Exec, class Loader, class Sink, class After>
+    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan&, const Tables& T, float2* A, float2* B,
+                                                 float2* carry, const Loader& ld, const Sink& sink, After&& after) {
+        process_block_ct<PL>(ex, T, A, B, carry, ld, sink, after);
+    }
+};
+
+template <class PV>
+__device__ __forceinline__ void resample_body(const WarpParams& P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const RtPlan& PL = P.plan;
     float2* s_twf = reinterpret_cast<float2*>(smem);
@@ -180,7 +202,7 @@ resample_warp_kernel(const __grid_constant__ WarpParams P) {
     float2* B = reinterpret_cast<float2*>(gbase + P.off_B);
     float2* carry = reinterpret_cast<float2*>(gbase + P.off_carry);
     const Tables T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
-    const int N = PL.N, M = PL.M;
+    const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
 
     Source src;
     src.pcm = P.pcm; src.fmt = P.fmt; src.ch = P.channels; src.fch = (float)P.channels;
@@ -222,7 +244,7 @@ resample_warp_kernel(const __grid_constant__ WarpParams P) {
         for (int j = lane; j < M / 2; j += nl) carry[j] = make_float2(0.f, 0.f);
         const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 7) == 0);      // M is even: b*M keeps 8-byte alignment
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
-        int shift = prefetch_block(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), PL.half_in, lane, nl);
+        int shift = prefetch_block(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), HALF_IN, lane, nl);
         for (uint32_t b = bfirst; b < b1; ++b) {
             cp_async_wait_all();
             ex.sync();
@@ -233,12 +255,35 @@ resample_warp_kernel(const __grid_constant__ WarpParams P) {
             sink.lim = b < b0 ? 0 : (int)(lim < 0 ? 0 : (lim > M ? M : lim));   // recomputed block: carry only
             sink.vec = vec;
             int next_shift = 0;
-            process_block(ex, PL, T, A, B, carry, ld, sink, [&] {
-                if (b + 1 < b1) next_shift = prefetch_block(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), PL.half_in, lane, nl);
+            PV::block(ex, PL, T, A, B, carry, ld, sink, [&] {
+                if (b + 1 < b1) next_shift = prefetch_block(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), HALF_IN, lane, nl);
             });
             shift = next_shift;
         }
     }
+}
+
+__global__ void __launch_bounds__(kMaxThreads, 1)
+resample_warp_kernel(const __grid_constant__ WarpParams P) { resample_body<RtView>(P); }
+
+template <class PL>
+__global__ void __launch_bounds__(kMaxThreads, 1)
+resample_plan_kernel(const __grid_constant__ WarpParams P) { resample_body<CtView<PL>>(P); }
+
+// index of the compile-time plan for (n_in, n_out), -1 when only the runtime plan applies
+int ct_plan_index(uint32_t n_in, uint32_t n_out) {
+    if (const char* g = std::getenv("BIRDA_K2_RUNTIME_PLAN")) if (g[0] == '1') return -1;
+    int i = 0;
+#define BB_CT(NAME, NI, NO, ...) if (n_in == NI && n_out == NO) return i; ++i;
+    BB_K2_CT_PLANS(BB_CT)
+#undef BB_CT
+    return -1;
+}
+
+template <class PL> void ct_radices(std::vector<int>* f, std::vector<int>* v) {
+    f->clear(); v->clear();
+    for (int i = 0; i < PL::Fwd::count; ++i) f->push_back(PL::Fwd::at(i));
+    for (int i = 0; i < PL::Inv::count; ++i) v->push_back(PL::Inv::at(i));
 }
 
 }  // namespace
@@ -253,7 +298,14 @@ bool warp_plan_available(const ResamplerSpec& spec) {
 
 cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     RtPlan P; std::vector<int> fwd, inv;
-    if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
+    rs->ct_index = ct_plan_index(spec.n_in, spec.n_out);
+    if (rs->ct_index >= 0) {
+        int i = 0;
+#define BB_CT(NAME, NI, NO, ...) if (i == rs->ct_index) ct_radices<__VA_ARGS__>(&fwd, &inv); ++i;
+        BB_K2_CT_PLANS(BB_CT)
+#undef BB_CT
+        if (!build_plan_from_radices((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
+    } else if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
     std::vector<uint16_t> pf(P.N), pi_(P.M);
     build_pos_tables(fwd, inv, P.N, P.M, pf.data(), pi_.data());
     std::vector<float2> Pt(P.nkeep), Qt(P.nkeep), WI(P.M / 2 + 1), twf(P.twf_len), twi(P.twi_len);
@@ -338,13 +390,28 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     P.R = R;
     P.items_per_row = (P.nblk + R - 1) / R;
     P.nitems = rows_total * P.items_per_row;
-    cudaError_t e = cudaFuncSetAttribute(resample_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st);
+    cudaError_t e = cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     uint64_t ctas = (P.nitems + warps - 1) / warps;
     if (ctas > (uint64_t)sm_count) ctas = sm_count;
-    resample_warp_kernel<<<(unsigned)ctas, groups * gw * 32, smem, st>>>(P);
+    const unsigned threads = (unsigned)(groups * gw * 32);
+    bool launched = false;
+    int i = 0;
+#define BB_CT(NAME, NI, NO, ...)                                                                                        \
+    if (!launched && i == rs.ct_index) {                                                                                 \
+        e = cudaFuncSetAttribute(resample_plan_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                                  \
+        resample_plan_kernel<__VA_ARGS__><<<(unsigned)ctas, threads, smem, st>>>(P);                                     \
+        launched = true;                                                                                                 \
+    }                                                                                                                    \
+    ++i;
+    BB_K2_CT_PLANS(BB_CT)
+#undef BB_CT
+    if (!launched) {
+        e = cudaFuncSetAttribute(resample_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        resample_warp_kernel<<<(unsigned)ctas, threads, smem, st>>>(P);
+    }
     e = cudaGetLastError();
     if (e == cudaSuccess && launches) *launches = 1;
     return e;

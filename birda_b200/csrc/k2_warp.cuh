@@ -42,6 +42,28 @@ struct RtStage {
     int nbf;        // butterflies in the stage = total / radix
     int tw_off;     // offset of this stage's compact twiddle table (entries p in [0, m)); -1 = none
     uint32_t magic; // ceil(2^32 / m) for q / m  (0 when m == 1)
+    BB_HD int M_() const { return m; }
+    BB_HD int SPAN_() const { return span; }
+    BB_HD int NBF_() const { return nbf; }
+    BB_HD int TWOFF_() const { return tw_off; }
+    BB_HD int div(int q) const {
+#ifdef __CUDA_ARCH__
+        return m == 1 ? q : (int)__umulhi((unsigned)q, magic);
+#else
+        return q / m;
+#endif
+    }
+};
+
+// the same stage with every quantity a compile-time constant (strides become immediate offsets)
+template <int RADIX, int SPAN, int NTOT, int TWOFF>
+struct CtStage {
+    static constexpr int radix = RADIX;
+    static BB_HD constexpr int M_() { return SPAN / RADIX; }
+    static BB_HD constexpr int SPAN_() { return SPAN; }
+    static BB_HD constexpr int NBF_() { return NTOT / RADIX; }
+    static BB_HD constexpr int TWOFF_() { return TWOFF; }
+    static BB_HD constexpr int div(int q) { return q / (SPAN / RADIX); }
 };
 
 struct RtPlan {
@@ -50,14 +72,6 @@ struct RtPlan {
     RtStage f[kMaxStages], i[kMaxStages];
     int twf_len, twi_len;        // compact twiddle table sizes (float2 entries)
 };
-
-BB_HD int fast_div(int q, const RtStage& s) {
-#ifdef __CUDA_ARCH__
-    return s.m == 1 ? q : (int)__umulhi((unsigned)q, s.magic);
-#else
-    return q / s.m;
-#endif
-}
 
 // a[k] *= w_span^(p k), k = 1..R-1.  Table layout: chain mode [p] holds w^p; table mode [(k-1)*m + p]
 template <int R> BB_HD void apply_twiddles(float2 (&a)[R], const float2* __restrict__ tw, int m, int p) {
@@ -75,28 +89,28 @@ template <int R> BB_HD void apply_twiddles(float2 (&a)[R], const float2* __restr
 }
 
 // ---- forward DIF stage, in place
-template <int R>
-BB_HD void dif_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int lane, int nl) {
-    const int m = s.m;
+template <int R, class S>
+BB_HD void dif_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const S& s, int lane, int nl) {
+    const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
-    for (int q = lane; q < s.nbf; q += nl) {
-        const int sb = fast_div(q, s), p = q - sb * m;
-        float2* __restrict__ e = buf + sb * s.span + p;
+    for (int q = lane; q < s.NBF_(); q += nl) {
+        const int sb = s.div(q), p = q - sb * m;
+        float2* __restrict__ e = buf + sb * s.SPAN_() + p;
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = e[j * m];
         Dft<R, false>::run(a);
-        if (s.tw_off >= 0) apply_twiddles<R>(a, tw + s.tw_off, m, p);
+        if (s.TWOFF_() >= 0) apply_twiddles<R>(a, tw + s.TWOFF_(), m, p);
 #pragma unroll
         for (int k = 0; k < R; ++k) e[k * m] = a[k];
     }
 }
 
 // first forward stage: input z[n] comes from `ld(n)` for n < half_in, zero above
-template <int R, class Loader>
-BB_HD void dif_first(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int half_in,
+template <int R, class S, class Loader>
+BB_HD void dif_first(float2* __restrict__ buf, const float2* __restrict__ tw, const S& s, int half_in,
                      const Loader& ld, int lane, int nl) {
-    const int m = s.m;
+    const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < m; q += nl) {
         float2 a[R];
@@ -106,7 +120,7 @@ BB_UNROLL_N(BB_K2W_UNROLL)
             a[j] = n < half_in ? ld(n) : make_float2(0.f, 0.f);
         }
         Dft<R, false>::run(a);
-        if (s.tw_off >= 0) apply_twiddles<R>(a, tw + s.tw_off, m, q);
+        if (s.TWOFF_() >= 0) apply_twiddles<R>(a, tw + s.TWOFF_(), m, q);
         float2* __restrict__ e = buf + q;
 #pragma unroll
         for (int k = 0; k < R; ++k) e[k * m] = a[k];
@@ -114,17 +128,17 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 }
 
 // ---- inverse DIT stage, in place
-template <int R>
-BB_HD void dit_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s, int lane, int nl) {
-    const int m = s.m;
+template <int R, class S>
+BB_HD void dit_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const S& s, int lane, int nl) {
+    const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
-    for (int q = lane; q < s.nbf; q += nl) {
-        const int sb = fast_div(q, s), p = q - sb * m;
-        float2* __restrict__ e = buf + sb * s.span + p;
+    for (int q = lane; q < s.NBF_(); q += nl) {
+        const int sb = s.div(q), p = q - sb * m;
+        float2* __restrict__ e = buf + sb * s.SPAN_() + p;
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = e[j * m];
-        if (s.tw_off >= 0) apply_twiddles<R>(a, tw + s.tw_off, m, p);
+        if (s.TWOFF_() >= 0) apply_twiddles<R>(a, tw + s.TWOFF_(), m, p);
         Dft<R, true>::run(a);
 #pragma unroll
         for (int k = 0; k < R; ++k) e[k * m] = a[k];
@@ -134,16 +148,16 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 // last inverse stage (span == M): output z'[n] = (y[2n], y[2n+1]).  n < M/2: add the carry and emit;
 // n >= M/2: becomes the carry of the next block.  R even, so both halves of one carry slot belong
 // to the same butterfly (no cross-lane hazard).
-template <int R, class Sink>
-BB_HD void dit_last(const float2* __restrict__ buf, const float2* __restrict__ tw, const RtStage& s,
+template <int R, class S, class Sink>
+BB_HD void dit_last(const float2* __restrict__ buf, const float2* __restrict__ tw, const S& s,
                     float2* __restrict__ carry, const Sink& sink, int lane, int nl) {
-    const int m = s.m;
+    const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int p = lane; p < m; p += nl) {
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = buf[p + j * m];
-        if (s.tw_off >= 0) apply_twiddles<R>(a, tw + s.tw_off, m, p);
+        if (s.TWOFF_() >= 0) apply_twiddles<R>(a, tw + s.TWOFF_(), m, p);
         Dft<R, true>::run(a);
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) {
@@ -232,6 +246,85 @@ BB_HD void process_block(const Exec& ex, const RtPlan& P, const Tables& T, float
     });
 }
 
+
+// ------------------------------------------------------------------ compile-time plans
+template <int... Rs> struct RSeq {
+    static constexpr int count = sizeof...(Rs);
+    static constexpr int at(int i) { constexpr int v[] = {Rs...}; return v[i]; }
+    static constexpr int prod_upto(int t) { int p = 1; for (int i = 0; i < t; ++i) p *= at(i); return p; }
+    static constexpr int total() { return prod_upto(count); }
+};
+
+// FWD: DIF radices in application order (product N).  INV: DIT radices in application order (product M,
+// last one even).  Offsets follow build_plan_from_radices exactly (checked on the host at init).
+template <class FWD, class INV_>
+struct CtPlan {
+    using Fwd = FWD; using Inv = INV_;
+    static constexpr int N = FWD::total();
+    static constexpr int M = INV_::total();
+    static constexpr int NKEEP = N < M ? N + 1 : M;
+    static constexpr int HALF_IN = (N + 1) / 2;
+    static constexpr int tw_entries(int radix, int m) { return tw_table_mode(radix) ? m * (radix - 1) : m; }
+    static constexpr int fwd_span(int t) { return N / FWD::prod_upto(t); }
+    static constexpr int fwd_twoff(int t) {
+        if (t + 1 >= FWD::count) return -1;
+        int off = 0;
+        for (int u = 0; u < t; ++u) off += tw_entries(FWD::at(u), fwd_span(u) / FWD::at(u));
+        return off;
+    }
+    static constexpr int inv_span(int t) { return INV_::prod_upto(t + 1); }
+    static constexpr int inv_twoff(int t) {
+        if (t == 0) return -1;
+        int off = 0;
+        for (int u = 1; u < t; ++u) off += tw_entries(INV_::at(u), INV_::prod_upto(u));
+        return off;
+    }
+    template <int T> using FwdStage = CtStage<FWD::at(T), fwd_span(T), N, fwd_twoff(T)>;
+    template <int T> using InvStage = CtStage<INV_::at(T), inv_span(T), M, inv_twoff(T)>;
+    static_assert(INV_::at(INV_::count - 1) % 2 == 0, "last inverse radix must be even");
+};
+
+template <class PL, class Exec, int T> struct CtFwdRest {
+    static BB_HD void run(const Exec& ex, float2* A, const float2* twf) {
+        if constexpr (T < PL::Fwd::count) {
+            using S = typename PL::template FwdStage<T>;
+            ex.each([&](int lane, int nl) { dif_stage<S::radix>(A, twf, S{}, lane, nl); });
+            CtFwdRest<PL, Exec, T + 1>::run(ex, A, twf);
+        }
+    }
+};
+template <class PL, class Exec, int T> struct CtInvMid {
+    static BB_HD void run(const Exec& ex, float2* B, const float2* twi) {
+        if constexpr (T + 1 < PL::Inv::count) {
+            using S = typename PL::template InvStage<T>;
+            ex.each([&](int lane, int nl) { dit_stage<S::radix>(B, twi, S{}, lane, nl); });
+            CtInvMid<PL, Exec, T + 1>::run(ex, B, twi);
+        }
+    }
+};
+
+template <class PL, class Exec, class Loader, class Sink, class AfterSplit>
+BB_HD void process_block_ct(const Exec& ex, const Tables& T, float2* A, float2* B, float2* carry,
+                            const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
+    using S0 = typename PL::template FwdStage<0>;
+    ex.each([&](int lane, int nl) { dif_first<S0::radix>(A, T.twf, S0{}, PL::HALF_IN, ld, lane, nl); });
+    CtFwdRest<PL, Exec, 1>::run(ex, A, T.twf);
+    ex.each([&](int lane, int nl) { split_pass(A, B, T.pos_f, T.pos_i, T.Pt, T.Qt, T.WI, PL::N, PL::M, PL::NKEEP, lane, nl); });
+    after_split();
+    CtInvMid<PL, Exec, 0>::run(ex, B, T.twi);
+    using SL = typename PL::template InvStage<PL::Inv::count - 1>;
+    ex.each([&](int lane, int nl) { dit_last<SL::radix>(B, T.twi, SL{}, carry, sink, lane, nl); });
+}
+
+// X(NAME, N_IN, N_OUT, CtPlan<RSeq<forward DIF radices>, RSeq<inverse DIT radices, last one even>>)
+#define BB_K2_CT_PLANS(X)                                                                                        \
+    X(p1029_1120, 1029, 1120, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 7, 3>, bb::k2w::RSeq<7, 5, 4, 8>>)  /* 44.1k -> 48k */ \
+    X(p1026_684, 1026, 684, bb::k2w::CtPlan<bb::k2w::RSeq<6, 19, 9>, bb::k2w::RSeq<19, 9, 4>>)        /* 48k -> 32k */   \
+    X(p1029_2240, 1029, 2240, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 7, 3>, bb::k2w::RSeq<7, 5, 8, 8>>)  /* 22.05k -> 48k */ \
+    X(p1024_512, 1024, 512, bb::k2w::CtPlan<bb::k2w::RSeq<16, 8, 8>, bb::k2w::RSeq<8, 8, 8>>)         /* 96k -> 48k */   \
+    X(p1024_1536, 1024, 1536, bb::k2w::CtPlan<bb::k2w::RSeq<16, 8, 8>, bb::k2w::RSeq<3, 8, 8, 8>>)    /* 32k -> 48k */   \
+    X(p1323_960, 1323, 960, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 9, 3>, bb::k2w::RSeq<5, 3, 8, 8>>)    /* 44.1k -> 32k */
+
 // ------------------------------------------------------------------ host-side plan construction
 inline bool radix_supported(int r) {
     switch (r) { case 2: case 3: case 4: case 5: case 6: case 7: case 8: case 9: case 11: case 13: case 16: case 19: return true; default: return false; }
@@ -276,9 +369,17 @@ inline bool choose_radices(int n, bool inverse, std::vector<int>* out) {
     return true;
 }
 
+inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const std::vector<int>* fwd, const std::vector<int>* inv);
+
 inline bool build_plan(int N, int M, int nkeep, RtPlan* P, std::vector<int>* fwd, std::vector<int>* inv) {
     if (M % 2 != 0 || N >= 65536 || M >= 65536) return false;
     if (!choose_radices(N, false, fwd) || !choose_radices(M, true, inv)) return false;
+    return build_plan_from_radices(N, M, nkeep, P, fwd, inv);
+}
+
+inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const std::vector<int>* fwd, const std::vector<int>* inv) {
+    if (M % 2 != 0 || N >= 65536 || M >= 65536) return false;
+    if ((int)fwd->size() > kMaxStages || (int)inv->size() > kMaxStages || inv->empty() || inv->back() % 2) return false;
     P->N = N; P->M = M; P->nkeep = nkeep; P->half_in = (N + 1) / 2;
     P->nf = (int)fwd->size(); P->ni = (int)inv->size();
     int span = N, off = 0;

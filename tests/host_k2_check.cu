@@ -6,6 +6,7 @@
 #include <vector>
 #include <complex>
 #include <cmath>
+#include <type_traits>
 #include "../birda_b200/csrc/k2_warp.cuh"
 
 using namespace bb;
@@ -17,11 +18,17 @@ struct HostExec {
     template <class F> void each(F&& f) const { for (int l = 0; l < nl; ++l) f(l, nl); }
 };
 
-static int check(int N, int M, int nl) {
+template <class CT>
+static int check_impl(int N, int M, int nl) {
     const double pi = 3.14159265358979323846;
     const int NKEEP = N < M ? N + 1 : M;
     RtPlan P; std::vector<int> fwd, inv;
-    if (!build_plan(N, M, NKEEP, &P, &fwd, &inv)) { printf("N=%d M=%d: no plan (generic kernel)\n", N, M); return 0; }
+    constexpr bool kCt = !std::is_same<CT, void>::value;
+    if constexpr (kCt) {
+        for (int i = 0; i < CT::Fwd::count; ++i) fwd.push_back(CT::Fwd::at(i));
+        for (int i = 0; i < CT::Inv::count; ++i) inv.push_back(CT::Inv::at(i));
+        if (!build_plan_from_radices(N, M, NKEEP, &P, &fwd, &inv)) { printf("bad ct plan\n"); return 1; }
+    } else if (!build_plan(N, M, NKEEP, &P, &fwd, &inv)) { printf("N=%d M=%d: no plan (generic kernel)\n", N, M); return 0; }
     std::vector<uint16_t> pos_f(N), pos_i(M);
     build_pos_tables(fwd, inv, N, M, pos_f.data(), pos_i.data());
     srand(1234 + N);
@@ -49,7 +56,8 @@ static int check(int N, int M, int nl) {
             return make_float2(re, im);
         };
         auto sink = [&](int n, float2 y) { out[b * M + 2 * n] = y.x; out[b * M + 2 * n + 1] = y.y; };
-        process_block(HostExec{nl}, P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
+        if constexpr (kCt) process_block_ct<CT>(HostExec{nl}, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
+        else process_block(HostExec{nl}, P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
     }
     std::vector<double> ref(NB * M + M, 0.0);
     for (int b = 0; b < NB; ++b) {
@@ -66,7 +74,7 @@ static int check(int N, int M, int nl) {
     double maxerr = 0, rms = 0;
     for (int i = 0; i < NB * M; ++i) { maxerr = fmax(maxerr, fabs(out[i] - ref[i])); rms += ref[i] * ref[i]; }
     rms = sqrt(rms / (NB * M));
-    printf("N=%4d M=%4d fwd[", N, M);
+    printf("%s N=%4d M=%4d fwd[", kCt ? "ct" : "rt", N, M);
     for (int r : fwd) printf(" %d", r);
     printf(" ] inv[");
     for (int r : inv) printf(" %d", r);
@@ -78,7 +86,10 @@ int main() {
     int bad = 0;
     const int cases[][2] = {{1029, 1120}, {1029, 2240}, {1026, 684}, {1024, 512}, {1024, 1536}, {1024, 3072},
                             {1323, 960}, {1323, 1920}, {1024, 2048}, {1026, 342}, {1029, 560}, {1125, 216}, {1024, 256}};
-    for (auto& c : cases) for (int nl : {32, 64}) bad += check(c[0], c[1], nl);
+    for (auto& c : cases) for (int nl : {32, 64}) bad += check_impl<void>(c[0], c[1], nl);
+#define BB_CT(NAME, NI, NO, ...) for (int nl : {32, 64}) bad += check_impl<__VA_ARGS__>(NI, NO, nl);
+    BB_K2_CT_PLANS(BB_CT)
+#undef BB_CT
     printf(bad ? "FAILED\n" : "all plans ok\n");
     return bad;
 }
