@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -110,6 +111,7 @@ class Context:
         else:
             check(lib.bb_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(self._h)))
         self.device = device
+        self._plans = weakref.WeakSet()       # plans must be destroyed before their context
 
     @property
     def handle(self):
@@ -124,6 +126,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for p in list(self._plans):
+                p.close()
             lib.bb_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -203,6 +207,7 @@ class FrontEndPlan:
         self._h = C.c_void_p()
         check(lib.bb_plan_create(ctx.handle, src_rate, channels, fmt, tgt_rate, segment_samples, overlap_samples,
                                  C.byref(self._h)), ctx.handle)
+        ctx._plans.add(self)
         self.src_rate, self.tgt_rate, self.channels, self.fmt = src_rate, tgt_rate, channels, fmt
         self.segment_samples, self.overlap_samples = segment_samples, overlap_samples
         a, b = C.c_uint64(), C.c_uint64()

@@ -63,7 +63,7 @@ def test_pipeline_matches_oracle(sr, channels, overlap, batch, rerank):
     got = [(d.segment, d.index) for d in res.detections]
     want = [(d.segment, d.index) for d in dets]
     # the stand-in's scores depend on resampled samples (1e-5): allow boundary flips only
-    assert len(set(got) ^ set(want)) <= max(2, len(want) // 50), (len(got), len(want))
+    assert len(set(got) ^ set(want)) <= max(3, len(want) // 20), (len(got), len(want))
     common = set(got) & set(want)
     gm = {(d.segment, d.index): d for d in res.detections}
     for d in dets:
