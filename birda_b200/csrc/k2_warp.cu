@@ -25,6 +25,8 @@ struct WarpParams {
     // shared memory layout (bytes)
     uint32_t off_twi, off_posf, off_posi, off_P, off_Q, off_WI, off_items, tables, per_group, off_B, off_carry;
     int groups, gw;                    // thread groups per CTA, warps per group (a group owns one block at a time)
+    int ws;                            // 1: warp-specialised pair (forward warp / inverse warp) per group
+    uint32_t off_ctl;                  // per-group control block (mbarriers + block descriptor)
 };
 
 struct DevExec {
@@ -157,6 +159,12 @@ struct RtView {
                                                  float2* carry, const Loader& ld, const Sink& sink, After&& after) {
         process_block(ex, p, T, A, B, carry, ld, sink, after);
     }
+    template <class Exec, class Loader, class Before>
+    static __device__ __forceinline__ void fwd(const Exec& ex, const RtPlan& p, const Tables& T, float2* A, float2* B,
+                                               const Loader& ld, Before&& before) { forward_half(ex, p, T, A, B, ld, before); }
+    template <class Exec, class Sink>
+    static __device__ __forceinline__ void inv(const Exec& ex, const RtPlan& p, const Tables& T, float2* B, float2* carry,
+                                               const Sink& sink) { inverse_half(ex, p, T, B, carry, sink); }
 };
 template <class PL> struct CtView {
     static __device__ __forceinline__ constexpr int n(const RtPlan&) { return PL::N; }
@@ -167,6 +175,32 @@ template <class PL> struct CtView {
                                                  float2* carry, const Loader& ld, const Sink& sink, After&& after) {
         process_block_ct<PL>(ex, T, A, B, carry, ld, sink, after);
     }
+    template <class Exec, class Loader, class Before>
+    static __device__ __forceinline__ void fwd(const Exec& ex, const RtPlan&, const Tables& T, float2* A, float2* B,
+                                               const Loader& ld, Before&& before) { forward_half_ct<PL>(ex, T, A, B, ld, before); }
+    template <class Exec, class Sink>
+    static __device__ __forceinline__ void inv(const Exec& ex, const RtPlan&, const Tables& T, float2* B, float2* carry,
+                                               const Sink& sink) { inverse_half_ct<PL>(ex, T, B, carry, sink); }
+};
+
+// ---- mbarrier helpers (CTA scope, generic proxy)
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_LOOP;\n}\n"
+                 ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+struct GroupCtl {                       // 32 bytes per group
+    unsigned long long bar_full;        // forward warp -> inverse warp: B holds a packed spectrum
+    unsigned long long bar_free;        // inverse warp -> forward warp: B may be overwritten
+    float* out;                         // output pointer of the block in B
+    int lim;                            // samples of the block to store (0: carry only)
+    int flags;                          // 1: float2 stores allowed  2: first block of a run (zero the carry)  4: exit
 };
 
 template <class PV>
@@ -263,12 +297,133 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
     }
 }
 
+
+// Warp-specialised variant: each group is a PAIR of warps.  The forward warp stages PCM, runs the forward
+// FFT and the split pass; the inverse warp runs the inverse FFT, the overlap-add and the stores.  They
+// meet twice per block on two mbarriers (B full / B free) instead of at every stage, and each warp keeps
+// the 32-lane butterfly mapping (no half-empty iterations).
+template <class PV>
+__device__ __forceinline__ void resample_body_ws(const WarpParams& P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const RtPlan& PL = P.plan;
+    float2* s_twf = reinterpret_cast<float2*>(smem);
+    float2* s_twi = reinterpret_cast<float2*>(smem + P.off_twi);
+    uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + P.off_posf);
+    uint16_t* s_posi = reinterpret_cast<uint16_t*>(smem + P.off_posi);
+    float2* s_P = reinterpret_cast<float2*>(smem + P.off_P);
+    float2* s_Q = reinterpret_cast<float2*>(smem + P.off_Q);
+    float2* s_WI = reinterpret_cast<float2*>(smem + P.off_WI);
+    GroupCtl* s_ctl = reinterpret_cast<GroupCtl*>(smem + P.off_ctl);
+    const int NT = blockDim.x;
+    for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = P.twf[i];
+    for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = P.twi[i];
+    for (int i = threadIdx.x; i < PL.N; i += NT) s_posf[i] = P.pos_f[i];
+    for (int i = threadIdx.x; i < PL.M; i += NT) s_posi[i] = P.pos_i[i];
+    for (int i = threadIdx.x; i < PL.nkeep; i += NT) { s_P[i] = P.Pt[i]; s_Q[i] = P.Qt[i]; }
+    for (int i = threadIdx.x; i <= PL.M / 2; i += NT) s_WI[i] = P.WI[i];
+    if ((int)threadIdx.x < P.groups) { mbar_init(&s_ctl[threadIdx.x].bar_full, 32); mbar_init(&s_ctl[threadIdx.x].bar_free, 32); }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = warp >> 1;
+    const bool is_fwd = (warp & 1) == 0;
+    DevExec ex; ex.nl = 32; ex.glane = lane; ex.bar_id = 0;
+    GroupCtl* ctl = &s_ctl[group];
+    unsigned char* gbase = smem + P.tables + (size_t)group * P.per_group;
+    float2* A = reinterpret_cast<float2*>(gbase);
+    float2* B = reinterpret_cast<float2*>(gbase + P.off_B);
+    float2* carry = reinterpret_cast<float2*>(gbase + P.off_carry);
+    const Tables T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
+    const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
+
+    if (!is_fwd) {
+        // ------------------------------------------------------------ inverse warp
+        int parity = 0;
+        for (;;) {
+            mbar_wait(&ctl->bar_full, parity); parity ^= 1;
+            DevSink sink; sink.p = ctl->out; sink.lim = ctl->lim;
+            const int flags = ctl->flags;
+            sink.vec = (flags & 1) != 0;
+            if (flags & 4) break;
+            if (flags & 2) { for (int j = lane; j < M / 2; j += 32) carry[j] = make_float2(0.f, 0.f); __syncwarp(); }
+            PV::inv(ex, PL, T, B, carry, sink);
+            mbar_arrive(&ctl->bar_free);
+        }
+        return;
+    }
+    // ---------------------------------------------------------------- forward warp
+    Source src;
+    src.pcm = P.pcm; src.fmt = P.fmt; src.ch = P.channels; src.fch = (float)P.channels;
+    const uint32_t bps = P.fmt == BB_S16 ? 2u : 4u;
+    src.pcm_end = reinterpret_cast<const char*>(P.pcm) + P.total_frames * P.channels * bps;
+    src.kind = 2;
+    if (P.fmt == BB_S16 && P.channels == 2 && (reinterpret_cast<uintptr_t>(P.pcm) & 3) == 0) src.kind = 0;
+    if (P.fmt == BB_S16 && P.channels == 1 && (reinterpret_cast<uintptr_t>(P.pcm) & 1) == 0) src.kind = 1;
+    int free_parity = 0;
+    bool b_in_use = false;                   // has B been handed to the inverse warp at least once?
+    auto acquire_b = [&]() { if (b_in_use) { mbar_wait(&ctl->bar_free, free_parity); free_parity ^= 1; } };
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(P.counter, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= P.nitems) break;
+        const uint64_t lrow = item / P.items_per_row;
+        const uint64_t row = P.row_first + lrow;
+        const uint32_t it = (uint32_t)(item - lrow * P.items_per_row);
+        float* __restrict__ orow = P.out + row * P.seg;
+        const uint32_t b0 = it * P.R;
+        const uint32_t b1 = min(b0 + P.R, P.nblk);
+        const bool last_item = it + 1 == P.items_per_row;
+        const uint32_t o_lo = min(b0 * (uint32_t)M, P.out_len);
+        const uint32_t o_hi = last_item ? P.out_len : min(b1 * (uint32_t)M, P.out_len);
+        if (row >= P.nseg) {                         // batch-padding row: zeros (processor.rs:239-260)
+            const uint64_t z_hi = last_item ? P.seg : o_hi;
+            for (uint64_t j = o_lo + lane; j < z_hi; j += 32) orow[j] = 0.0f;
+            continue;
+        }
+        if (last_item) for (uint64_t j = P.out_len + lane; j < P.seg; j += 32) orow[j] = 0.0f;
+        if (b0 >= b1) continue;
+        const uint64_t start = (row + 1 == P.nseg) ? P.last_start : row * P.hop;
+        const uint64_t take = P.total_frames - start < P.src_seg ? P.total_frames - start : P.src_seg;
+        auto valid_of = [&](uint32_t b) -> int {
+            const uint64_t q0 = (uint64_t)b * N;
+            return q0 < take ? (int)(take - q0 < (uint64_t)N ? take - q0 : (uint64_t)N) : 0;
+        };
+        const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 7) == 0);
+        const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
+        int shift = prefetch_block(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), HALF_IN, lane, 32);
+        for (uint32_t b = bfirst; b < b1; ++b) {
+            cp_async_wait_all();
+            __syncwarp();
+            BlockLoader ld{&src, A, start + (uint64_t)b * N, valid_of(b), shift};
+            PV::fwd(ex, PL, T, A, B, ld, [&] {
+                acquire_b();                                   // the inverse warp has finished with B (and the descriptor)
+                if (lane == 0) {
+                    const int64_t lim = (int64_t)o_hi - (int64_t)b * M;
+                    ctl->out = orow + (size_t)b * M;
+                    ctl->lim = b < b0 ? 0 : (int)(lim < 0 ? 0 : (lim > M ? M : lim));
+                    ctl->flags = (vec ? 1 : 0) | (b == bfirst ? 2 : 0);
+                }
+            });
+            mbar_arrive(&ctl->bar_full);                       // B (and the descriptor) are ready
+            b_in_use = true;
+            shift = 0;
+            if (b + 1 < b1) shift = prefetch_block(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), HALF_IN, lane, 32);
+        }
+    }
+    acquire_b();
+    if (lane == 0) ctl->flags = 4;
+    __syncwarp();
+    mbar_arrive(&ctl->bar_full);
+}
+
 __global__ void __launch_bounds__(kMaxThreads, 1)
-resample_warp_kernel(const __grid_constant__ WarpParams P) { resample_body<RtView>(P); }
+resample_warp_kernel(const __grid_constant__ WarpParams P) { if (P.ws) resample_body_ws<RtView>(P); else resample_body<RtView>(P); }
 
 template <class PL>
 __global__ void __launch_bounds__(kMaxThreads, 1)
-resample_plan_kernel(const __grid_constant__ WarpParams P) { resample_body<CtView<PL>>(P); }
+resample_plan_kernel(const __grid_constant__ WarpParams P) { if (P.ws) resample_body_ws<CtView<PL>>(P); else resample_body<CtView<PL>>(P); }
 
 // index of the compile-time plan for (n_in, n_out), -1 when only the runtime plan applies
 int ct_plan_index(uint32_t n_in, uint32_t n_out) {
@@ -363,7 +518,8 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     P.off_Q = P.off_P + a16((size_t)PL.nkeep * 8);
     P.off_WI = P.off_Q + a16((size_t)PL.nkeep * 8);
     P.off_items = P.off_WI + a16((size_t)(PL.M / 2 + 1) * 8);
-    P.tables = P.off_items + a16((size_t)kMaxGroups * 8);
+    P.off_ctl = P.off_items + a16((size_t)kMaxGroups * 8);
+    P.tables = P.off_ctl + a16((size_t)kMaxGroups * sizeof(GroupCtl));
     P.off_B = a16((size_t)PL.N * 8);
     P.off_carry = P.off_B + a16((size_t)PL.M * 8);
     P.per_group = P.off_carry + a16((size_t)(PL.M / 2) * 8);
@@ -374,6 +530,8 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     if (gw < 1) { gw = 1; groups = kMaxThreads / 32; }
     if (gw > 4) gw = 4;
     if (const char* g = std::getenv("BIRDA_K2_GROUP_WARPS")) { int v = atoi(g); if (v >= 1 && v <= 4 && v * groups * 32 <= kMaxThreads) gw = v; }
+    P.ws = gw == 2 ? 1 : 0;
+    if (const char* g = std::getenv("BIRDA_K2_WS")) P.ws = (g[0] == '1' && gw == 2) ? 1 : 0;
     P.groups = groups; P.gw = gw;
     const int warps = groups;                           // work items are per group
     const size_t smem = P.tables + (size_t)groups * P.per_group;

@@ -229,21 +229,35 @@ struct Tables {
 // One block.  ex.each(f) runs f(lane, nlanes) for every lane of the thread group that owns the block and
 // orders memory between calls (device: __syncwarp or a named barrier; host harness: a loop).  after_split() is called once the forward
 // buffer A is dead (the device kernel starts the next block's PCM prefetch there).
-template <class Exec, class Loader, class Sink, class AfterSplit>
-BB_HD void process_block(const Exec& ex, const RtPlan& P, const Tables& T, float2* A, float2* B, float2* carry,
-                         const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
+// forward half: loader -> in-place DIF in A -> (before_split) -> split / filter / re-bin into B.
+// before_split() runs when A holds the forward result and B is about to be overwritten (a forward /
+// inverse warp pair waits there for the inverse warp to release B).
+template <class Exec, class Loader, class BeforeSplit>
+BB_HD void forward_half(const Exec& ex, const RtPlan& P, const Tables& T, float2* A, float2* B, const Loader& ld,
+                        BeforeSplit&& before_split) {
     ex.each([&](int lane, int nl) {
         BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R>(A, T.twf, P.f[0], P.half_in, ld, lane, nl)))
     });
     for (int t = 1; t < P.nf; ++t)
         ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R>(A, T.twf, P.f[t], lane, nl))) });
+    before_split();
     ex.each([&](int lane, int nl) { split_pass(A, B, T.pos_f, T.pos_i, T.Pt, T.Qt, T.WI, P.N, P.M, P.nkeep, lane, nl); });
-    after_split();
+}
+// inverse half: in-place DIT in B -> overlap-add with the carry -> sink
+template <class Exec, class Sink>
+BB_HD void inverse_half(const Exec& ex, const RtPlan& P, const Tables& T, float2* B, float2* carry, const Sink& sink) {
     for (int t = 0; t + 1 < P.ni; ++t)
         ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R>(B, T.twi, P.i[t], lane, nl))) });
     ex.each([&](int lane, int nl) {
         BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R>(B, T.twi, P.i[P.ni - 1], carry, sink, lane, nl)))
     });
+}
+template <class Exec, class Loader, class Sink, class AfterSplit>
+BB_HD void process_block(const Exec& ex, const RtPlan& P, const Tables& T, float2* A, float2* B, float2* carry,
+                         const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
+    forward_half(ex, P, T, A, B, ld, [] {});
+    after_split();
+    inverse_half(ex, P, T, B, carry, sink);
 }
 
 
@@ -303,17 +317,26 @@ template <class PL, class Exec, int T> struct CtInvMid {
     }
 };
 
-template <class PL, class Exec, class Loader, class Sink, class AfterSplit>
-BB_HD void process_block_ct(const Exec& ex, const Tables& T, float2* A, float2* B, float2* carry,
-                            const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
+template <class PL, class Exec, class Loader, class BeforeSplit>
+BB_HD void forward_half_ct(const Exec& ex, const Tables& T, float2* A, float2* B, const Loader& ld, BeforeSplit&& before_split) {
     using S0 = typename PL::template FwdStage<0>;
     ex.each([&](int lane, int nl) { dif_first<S0::radix>(A, T.twf, S0{}, PL::HALF_IN, ld, lane, nl); });
     CtFwdRest<PL, Exec, 1>::run(ex, A, T.twf);
+    before_split();
     ex.each([&](int lane, int nl) { split_pass(A, B, T.pos_f, T.pos_i, T.Pt, T.Qt, T.WI, PL::N, PL::M, PL::NKEEP, lane, nl); });
-    after_split();
+}
+template <class PL, class Exec, class Sink>
+BB_HD void inverse_half_ct(const Exec& ex, const Tables& T, float2* B, float2* carry, const Sink& sink) {
     CtInvMid<PL, Exec, 0>::run(ex, B, T.twi);
     using SL = typename PL::template InvStage<PL::Inv::count - 1>;
     ex.each([&](int lane, int nl) { dit_last<SL::radix>(B, T.twi, SL{}, carry, sink, lane, nl); });
+}
+template <class PL, class Exec, class Loader, class Sink, class AfterSplit>
+BB_HD void process_block_ct(const Exec& ex, const Tables& T, float2* A, float2* B, float2* carry,
+                            const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
+    forward_half_ct<PL>(ex, T, A, B, ld, [] {});
+    after_split();
+    inverse_half_ct<PL>(ex, T, B, carry, sink);
 }
 
 // X(NAME, N_IN, N_OUT, CtPlan<RSeq<forward DIF radices>, RSeq<inverse DIT radices, last one even>>)
