@@ -25,8 +25,7 @@ struct WarpParams {
     // shared memory layout (bytes)
     uint32_t off_twi, off_posf, off_posi, off_P, off_Q, off_WI, off_items, tables, per_group, off_B, off_carry;
     int groups, gw;                    // thread groups per CTA, warps per group (a group owns one block at a time)
-    int ws;                            // 1: warp-specialised pair (forward warp / inverse warp) per group
-    uint32_t off_ctl;                  // per-group control block (mbarriers + block descriptor)
+    int dual;                          // 1: two rows per group in lockstep (packed f32x2 math), tables are float4
 };
 
 struct DevExec {
@@ -154,53 +153,23 @@ struct RtView {
     static __device__ __forceinline__ int n(const RtPlan& p) { return p.N; }
     static __device__ __forceinline__ int m(const RtPlan& p) { return p.M; }
     static __device__ __forceinline__ int half_in(const RtPlan& p) { return p.half_in; }
-    template <class Exec, class Loader, class Sink, class After>
-    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const Tables& T, float2* A, float2* B,
-                                                 float2* carry, const Loader& ld, const Sink& sink, After&& after) {
-        process_block(ex, p, T, A, B, carry, ld, sink, after);
+    template <class C, class Exec, class Loader, class Sink, class After>
+    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const Tables<C>& T, typename Mem<C>::T* A,
+                                                 typename Mem<C>::T* B, typename Mem<C>::T* carry, const Loader& ld,
+                                                 const Sink& sink, After&& after) {
+        process_block<C>(ex, p, T, A, B, carry, ld, sink, after);
     }
-    template <class Exec, class Loader, class Before>
-    static __device__ __forceinline__ void fwd(const Exec& ex, const RtPlan& p, const Tables& T, float2* A, float2* B,
-                                               const Loader& ld, Before&& before) { forward_half(ex, p, T, A, B, ld, before); }
-    template <class Exec, class Sink>
-    static __device__ __forceinline__ void inv(const Exec& ex, const RtPlan& p, const Tables& T, float2* B, float2* carry,
-                                               const Sink& sink) { inverse_half(ex, p, T, B, carry, sink); }
 };
 template <class PL> struct CtView {
     static __device__ __forceinline__ constexpr int n(const RtPlan&) { return PL::N; }
     static __device__ __forceinline__ constexpr int m(const RtPlan&) { return PL::M; }
     static __device__ __forceinline__ constexpr int half_in(const RtPlan&) { return PL::HALF_IN; }
-    template <class Exec, class Loader, class Sink, class After>
-    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan&, const Tables& T, float2* A, float2* B,
-                                                 float2* carry, const Loader& ld, const Sink& sink, After&& after) {
-        process_block_ct<PL>(ex, T, A, B, carry, ld, sink, after);
+    template <class C, class Exec, class Loader, class Sink, class After>
+    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan&, const Tables<C>& T, typename Mem<C>::T* A,
+                                                 typename Mem<C>::T* B, typename Mem<C>::T* carry, const Loader& ld,
+                                                 const Sink& sink, After&& after) {
+        process_block_ct<PL, C>(ex, T, A, B, carry, ld, sink, after);
     }
-    template <class Exec, class Loader, class Before>
-    static __device__ __forceinline__ void fwd(const Exec& ex, const RtPlan&, const Tables& T, float2* A, float2* B,
-                                               const Loader& ld, Before&& before) { forward_half_ct<PL>(ex, T, A, B, ld, before); }
-    template <class Exec, class Sink>
-    static __device__ __forceinline__ void inv(const Exec& ex, const RtPlan&, const Tables& T, float2* B, float2* carry,
-                                               const Sink& sink) { inverse_half_ct<PL>(ex, T, B, carry, sink); }
-};
-
-// ---- mbarrier helpers (CTA scope, generic proxy)
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
-    asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_LOOP;\n}\n"
-                 ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-}
-
-struct GroupCtl {                       // 32 bytes per group
-    unsigned long long bar_full;        // forward warp -> inverse warp: B holds a packed spectrum
-    unsigned long long bar_free;        // inverse warp -> forward warp: B may be overwritten
-    float* out;                         // output pointer of the block in B
-    int lim;                            // samples of the block to store (0: carry only)
-    int flags;                          // 1: float2 stores allowed  2: first block of a run (zero the carry)  4: exit
 };
 
 template <class PV>
@@ -235,7 +204,7 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
     float2* A = reinterpret_cast<float2*>(gbase);
     float2* B = reinterpret_cast<float2*>(gbase + P.off_B);
     float2* carry = reinterpret_cast<float2*>(gbase + P.off_carry);
-    const Tables T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
+    const Tables<float2> T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
     const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
 
     Source src;
@@ -289,7 +258,7 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
             sink.lim = b < b0 ? 0 : (int)(lim < 0 ? 0 : (lim > M ? M : lim));   // recomputed block: carry only
             sink.vec = vec;
             int next_shift = 0;
-            PV::block(ex, PL, T, A, B, carry, ld, sink, [&] {
+            PV::template block<float2>(ex, PL, T, A, B, carry, ld, sink, [&] {
                 if (b + 1 < b1) next_shift = prefetch_block(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), HALF_IN, lane, nl);
             });
             shift = next_shift;
@@ -298,60 +267,128 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
 }
 
 
-// Warp-specialised variant: each group is a PAIR of warps.  The forward warp stages PCM, runs the forward
-// FFT and the split pass; the inverse warp runs the inverse FFT, the overlap-add and the stores.  They
-// meet twice per block on two mbarriers (B full / B free) instead of at every stage, and each warp keeps
-// the 32-lane butterfly mapping (no half-empty iterations).
+
+// ------------------------------------------------------------------------------------------------
+// Two-stream variant: a group runs TWO rows (windows r, r+1; same block range) in lockstep.  Every
+// shared-memory element is a float4 (re0, re1, im0, im1) and every butterfly instruction is a packed
+// f32x2 op, so index math, loads/stores and FP issue slots are shared by the two rows.
+struct DualStream { uint64_t base; int valid; int shift; bool active; };
+
+struct DualLoader {
+    const Source* src; const float4* A; DualStream s0, s1;
+    __device__ __forceinline__ void conv(int kind, int a, int b, int shift, float& re, float& im) const {
+        if (kind == 0) {
+            re = __fmul_rn(__int2float_rn((int)(short)(a & 0xffff) + (a >> 16)), 1.0f / 65536.0f);
+            im = __fmul_rn(__int2float_rn((int)(short)(b & 0xffff) + (b >> 16)), 1.0f / 65536.0f);
+        } else {
+            const int w = __funnelshift_r(a, b, shift);
+            re = __fmul_rn(__int2float_rn((int)(short)(w & 0xffff)), 1.0f / 32768.0f);
+            im = __fmul_rn(__int2float_rn(w >> 16), 1.0f / 32768.0f);
+        }
+    }
+    __device__ __forceinline__ cx2 operator()(int n) const {
+        const int i0 = 2 * n;
+        float r0 = 0.f, m0 = 0.f, r1 = 0.f, m1 = 0.f;
+        if (src->kind != 2) {
+            const int4 v = *reinterpret_cast<const int4*>(A + n);
+            conv(src->kind, v.x, v.y, s0.shift, r0, m0);
+            conv(src->kind, v.z, v.w, s1.shift, r1, m1);
+            if (i0 >= s0.valid) r0 = 0.f;
+            if (i0 + 1 >= s0.valid) m0 = 0.f;
+            if (i0 >= s1.valid) r1 = 0.f;
+            if (i0 + 1 >= s1.valid) m1 = 0.f;
+        } else {
+            if (i0 < s0.valid) r0 = src->direct(s0.base + i0);
+            if (i0 + 1 < s0.valid) m0 = src->direct(s0.base + i0 + 1);
+            if (i0 < s1.valid) r1 = src->direct(s1.base + i0);
+            if (i0 + 1 < s1.valid) m1 = src->direct(s1.base + i0 + 1);
+        }
+        cx2 c; c.re = make_float2(r0, r1); c.im = make_float2(m0, m1);
+        return c;
+    }
+};
+
+// stage one stream's raw PCM of a block into its 8-byte half of the float4 slots
+__device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int half, uint64_t base, int valid, int half_in, int lane, int nl) {
+    int shift = 0;
+    char* dst0 = reinterpret_cast<char*>(A) + half * 8;
+    if (s.kind == 0) {
+        const char* g0 = reinterpret_cast<const char*>(s.pcm) + base * 4;
+        const bool al8 = (reinterpret_cast<uintptr_t>(g0) & 7) == 0;
+        for (int n = lane; n < half_in; n += nl) {
+            if (2 * n >= valid) break;
+            const char* g = g0 + (size_t)n * 8;
+            char* d = dst0 + (size_t)n * 16;
+            const long long room = s.pcm_end - g;
+            if (al8) cp_async8(d, g, room >= 8 ? 8 : (room > 0 ? (int)room : 0));
+            else { cp_async4(d, g, room >= 4 ? 4 : 0); cp_async4(d + 4, g + 4, room >= 8 ? 4 : 0); }
+        }
+    } else if (s.kind == 1) {
+        const char* g0 = reinterpret_cast<const char*>(s.pcm) + base * 2;
+        const bool odd = (reinterpret_cast<uintptr_t>(g0) & 3) != 0;
+        shift = odd ? 16 : 0;
+        g0 -= odd ? 2 : 0;
+        for (int n = lane; n < half_in; n += nl) {
+            if (2 * n >= valid) break;
+            const char* g = g0 + (size_t)n * 4;
+            char* d = dst0 + (size_t)n * 16;
+            const long long room = s.pcm_end - g;
+            cp_async4(d, g, room >= 4 ? 4 : (room > 0 ? (int)room : 0));
+            if (odd) cp_async4(d + 4, g + 4, room >= 8 ? 4 : (room > 4 ? (int)(room - 4) : 0));
+        }
+    }
+    return shift;
+}
+
+struct DualSink {
+    float* p0; float* p1; int lim0, lim1; bool vec0, vec1;
+    __device__ __forceinline__ void put(float* p, int lim, bool vec, int o, float a, float b) const {
+        if (vec && o + 1 < lim) *reinterpret_cast<float2*>(p + o) = make_float2(a, b);
+        else { if (o < lim) p[o] = a; if (o + 1 < lim) p[o + 1] = b; }
+    }
+    __device__ __forceinline__ void operator()(int n, const cx2& y) const {
+        const int o = 2 * n;
+        put(p0, lim0, vec0, o, y.re.x, y.im.x);
+        put(p1, lim1, vec1, o, y.re.y, y.im.y);
+    }
+};
+
 template <class PV>
-__device__ __forceinline__ void resample_body_ws(const WarpParams& P) {
+__device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const RtPlan& PL = P.plan;
-    float2* s_twf = reinterpret_cast<float2*>(smem);
-    float2* s_twi = reinterpret_cast<float2*>(smem + P.off_twi);
+    float4* s_twf = reinterpret_cast<float4*>(smem);
+    float4* s_twi = reinterpret_cast<float4*>(smem + P.off_twi);
     uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + P.off_posf);
     uint16_t* s_posi = reinterpret_cast<uint16_t*>(smem + P.off_posi);
-    float2* s_P = reinterpret_cast<float2*>(smem + P.off_P);
-    float2* s_Q = reinterpret_cast<float2*>(smem + P.off_Q);
-    float2* s_WI = reinterpret_cast<float2*>(smem + P.off_WI);
-    GroupCtl* s_ctl = reinterpret_cast<GroupCtl*>(smem + P.off_ctl);
+    float4* s_P = reinterpret_cast<float4*>(smem + P.off_P);
+    float4* s_Q = reinterpret_cast<float4*>(smem + P.off_Q);
+    float4* s_WI = reinterpret_cast<float4*>(smem + P.off_WI);
     const int NT = blockDim.x;
-    for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = P.twf[i];
-    for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = P.twi[i];
+    auto bc = [](float2 w) { return make_float4(w.x, w.x, w.y, w.y); };
+    for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = bc(P.twf[i]);
+    for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = bc(P.twi[i]);
     for (int i = threadIdx.x; i < PL.N; i += NT) s_posf[i] = P.pos_f[i];
     for (int i = threadIdx.x; i < PL.M; i += NT) s_posi[i] = P.pos_i[i];
-    for (int i = threadIdx.x; i < PL.nkeep; i += NT) { s_P[i] = P.Pt[i]; s_Q[i] = P.Qt[i]; }
-    for (int i = threadIdx.x; i <= PL.M / 2; i += NT) s_WI[i] = P.WI[i];
-    if ((int)threadIdx.x < P.groups) { mbar_init(&s_ctl[threadIdx.x].bar_full, 32); mbar_init(&s_ctl[threadIdx.x].bar_free, 32); }
+    for (int i = threadIdx.x; i < PL.nkeep; i += NT) { s_P[i] = bc(P.Pt[i]); s_Q[i] = bc(P.Qt[i]); }
+    for (int i = threadIdx.x; i <= PL.M / 2; i += NT) s_WI[i] = bc(P.WI[i]);
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int group = warp >> 1;
-    const bool is_fwd = (warp & 1) == 0;
-    DevExec ex; ex.nl = 32; ex.glane = lane; ex.bar_id = 0;
-    GroupCtl* ctl = &s_ctl[group];
+    const int warp = threadIdx.x >> 5;
+    const int group = warp / P.gw;
+    DevExec ex;
+    ex.nl = P.gw * 32;
+    ex.glane = (warp - group * P.gw) * 32 + (int)(threadIdx.x & 31);
+    ex.bar_id = 1 + group;
+    const int lane = ex.glane, nl = ex.nl;
+    unsigned long long* s_items = reinterpret_cast<unsigned long long*>(smem + P.off_items);
     unsigned char* gbase = smem + P.tables + (size_t)group * P.per_group;
-    float2* A = reinterpret_cast<float2*>(gbase);
-    float2* B = reinterpret_cast<float2*>(gbase + P.off_B);
-    float2* carry = reinterpret_cast<float2*>(gbase + P.off_carry);
-    const Tables T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
+    float4* A = reinterpret_cast<float4*>(gbase);
+    float4* B = reinterpret_cast<float4*>(gbase + P.off_B);
+    float4* carry = reinterpret_cast<float4*>(gbase + P.off_carry);
+    const Tables<cx2> T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
     const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
 
-    if (!is_fwd) {
-        // ------------------------------------------------------------ inverse warp
-        int parity = 0;
-        for (;;) {
-            mbar_wait(&ctl->bar_full, parity); parity ^= 1;
-            DevSink sink; sink.p = ctl->out; sink.lim = ctl->lim;
-            const int flags = ctl->flags;
-            sink.vec = (flags & 1) != 0;
-            if (flags & 4) break;
-            if (flags & 2) { for (int j = lane; j < M / 2; j += 32) carry[j] = make_float2(0.f, 0.f); __syncwarp(); }
-            PV::inv(ex, PL, T, B, carry, sink);
-            mbar_arrive(&ctl->bar_free);
-        }
-        return;
-    }
-    // ---------------------------------------------------------------- forward warp
     Source src;
     src.pcm = P.pcm; src.fmt = P.fmt; src.ch = P.channels; src.fch = (float)P.channels;
     const uint32_t bps = P.fmt == BB_S16 ? 2u : 4u;
@@ -359,71 +396,85 @@ __device__ __forceinline__ void resample_body_ws(const WarpParams& P) {
     src.kind = 2;
     if (P.fmt == BB_S16 && P.channels == 2 && (reinterpret_cast<uintptr_t>(P.pcm) & 3) == 0) src.kind = 0;
     if (P.fmt == BB_S16 && P.channels == 1 && (reinterpret_cast<uintptr_t>(P.pcm) & 1) == 0) src.kind = 1;
-    int free_parity = 0;
-    bool b_in_use = false;                   // has B been handed to the inverse warp at least once?
-    auto acquire_b = [&]() { if (b_in_use) { mbar_wait(&ctl->bar_free, free_parity); free_parity ^= 1; } };
+    const uint64_t row_end = P.row_first + P.rows_total;
 
     for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(P.counter, 1ull);
-        item = __shfl_sync(0xffffffffu, item, 0);
+        if (lane == 0) s_items[group] = atomicAdd(P.counter, 1ull);
+        ex.sync();
+        const unsigned long long item = s_items[group];
+        ex.sync();
         if (item >= P.nitems) break;
-        const uint64_t lrow = item / P.items_per_row;
-        const uint64_t row = P.row_first + lrow;
-        const uint32_t it = (uint32_t)(item - lrow * P.items_per_row);
-        float* __restrict__ orow = P.out + row * P.seg;
+        const uint64_t lpair = item / P.items_per_row;
+        const uint32_t it = (uint32_t)(item - lpair * P.items_per_row);
         const uint32_t b0 = it * P.R;
         const uint32_t b1 = min(b0 + P.R, P.nblk);
         const bool last_item = it + 1 == P.items_per_row;
         const uint32_t o_lo = min(b0 * (uint32_t)M, P.out_len);
         const uint32_t o_hi = last_item ? P.out_len : min(b1 * (uint32_t)M, P.out_len);
-        if (row >= P.nseg) {                         // batch-padding row: zeros (processor.rs:239-260)
-            const uint64_t z_hi = last_item ? P.seg : o_hi;
-            for (uint64_t j = o_lo + lane; j < z_hi; j += 32) orow[j] = 0.0f;
-            continue;
+        uint64_t start[2], take[2]; float* orow[2]; bool active[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const uint64_t row = P.row_first + 2 * lpair + s;
+            orow[s] = P.out + row * P.seg;
+            active[s] = row < row_end && row < P.nseg;
+            start[s] = 0; take[s] = 0;
+            if (row < row_end && row >= P.nseg) {            // batch-padding row: zeros (processor.rs:239-260)
+                const uint64_t z_hi = last_item ? P.seg : o_hi;
+                for (uint64_t j = o_lo + lane; j < z_hi; j += nl) orow[s][j] = 0.0f;
+            }
+            if (active[s]) {
+                if (last_item) for (uint64_t j = P.out_len + lane; j < P.seg; j += nl) orow[s][j] = 0.0f;
+                start[s] = (row + 1 == P.nseg) ? P.last_start : row * P.hop;
+                take[s] = P.total_frames - start[s] < P.src_seg ? P.total_frames - start[s] : P.src_seg;
+            }
         }
-        if (last_item) for (uint64_t j = P.out_len + lane; j < P.seg; j += 32) orow[j] = 0.0f;
-        if (b0 >= b1) continue;
-        const uint64_t start = (row + 1 == P.nseg) ? P.last_start : row * P.hop;
-        const uint64_t take = P.total_frames - start < P.src_seg ? P.total_frames - start : P.src_seg;
-        auto valid_of = [&](uint32_t b) -> int {
+        if ((!active[0] && !active[1]) || b0 >= b1) continue;
+        auto stream_of = [&](int s, uint32_t b) -> DualStream {
+            DualStream d; d.active = active[s]; d.shift = 0;
             const uint64_t q0 = (uint64_t)b * N;
-            return q0 < take ? (int)(take - q0 < (uint64_t)N ? take - q0 : (uint64_t)N) : 0;
+            d.valid = (active[s] && q0 < take[s]) ? (int)(take[s] - q0 < (uint64_t)N ? take[s] - q0 : (uint64_t)N) : 0;
+            d.base = start[s] + q0;
+            return d;
         };
-        const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 7) == 0);
+        for (int j = lane; j < M / 2; j += nl) carry[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
-        int shift = prefetch_block(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), HALF_IN, lane, 32);
+        DualStream c0 = stream_of(0, bfirst), c1 = stream_of(1, bfirst);
+        c0.shift = prefetch_half(src, A, 0, c0.base, c0.valid, HALF_IN, lane, nl);
+        c1.shift = prefetch_half(src, A, 1, c1.base, c1.valid, HALF_IN, lane, nl);
         for (uint32_t b = bfirst; b < b1; ++b) {
             cp_async_wait_all();
-            __syncwarp();
-            BlockLoader ld{&src, A, start + (uint64_t)b * N, valid_of(b), shift};
-            PV::fwd(ex, PL, T, A, B, ld, [&] {
-                acquire_b();                                   // the inverse warp has finished with B (and the descriptor)
-                if (lane == 0) {
-                    const int64_t lim = (int64_t)o_hi - (int64_t)b * M;
-                    ctl->out = orow + (size_t)b * M;
-                    ctl->lim = b < b0 ? 0 : (int)(lim < 0 ? 0 : (lim > M ? M : lim));
-                    ctl->flags = (vec ? 1 : 0) | (b == bfirst ? 2 : 0);
+            ex.sync();
+            DualLoader ld{&src, A, c0, c1};
+            DualSink sink;
+            const int64_t lim = (int64_t)o_hi - (int64_t)b * M;
+            const int l = b < b0 ? 0 : (int)(lim < 0 ? 0 : (lim > M ? M : lim));   // recomputed block: carry only
+            sink.p0 = orow[0] + (size_t)b * M; sink.p1 = orow[1] + (size_t)b * M;
+            sink.lim0 = active[0] ? l : 0; sink.lim1 = active[1] ? l : 0;
+            sink.vec0 = (reinterpret_cast<uintptr_t>(orow[0]) & 7) == 0; sink.vec1 = (reinterpret_cast<uintptr_t>(orow[1]) & 7) == 0;
+            DualStream n0 = c0, n1 = c1;
+            PV::template block<cx2>(ex, PL, T, A, B, carry, ld, sink, [&] {
+                if (b + 1 < b1) {
+                    n0 = stream_of(0, b + 1); n1 = stream_of(1, b + 1);
+                    n0.shift = prefetch_half(src, A, 0, n0.base, n0.valid, HALF_IN, lane, nl);
+                    n1.shift = prefetch_half(src, A, 1, n1.base, n1.valid, HALF_IN, lane, nl);
                 }
             });
-            mbar_arrive(&ctl->bar_full);                       // B (and the descriptor) are ready
-            b_in_use = true;
-            shift = 0;
-            if (b + 1 < b1) shift = prefetch_block(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), HALF_IN, lane, 32);
+            c0 = n0; c1 = n1;
         }
     }
-    acquire_b();
-    if (lane == 0) ctl->flags = 4;
-    __syncwarp();
-    mbar_arrive(&ctl->bar_full);
 }
 
 __global__ void __launch_bounds__(kMaxThreads, 1)
-resample_warp_kernel(const __grid_constant__ WarpParams P) { if (P.ws) resample_body_ws<RtView>(P); else resample_body<RtView>(P); }
+resample_warp_kernel(const __grid_constant__ WarpParams P) { resample_body<RtView>(P); }
 
 template <class PL>
 __global__ void __launch_bounds__(kMaxThreads, 1)
-resample_plan_kernel(const __grid_constant__ WarpParams P) { if (P.ws) resample_body_ws<CtView<PL>>(P); else resample_body<CtView<PL>>(P); }
+resample_plan_kernel(const __grid_constant__ WarpParams P) { resample_body<CtView<PL>>(P); }
+
+constexpr int kDualThreads = 384;     // 12 warps: register cap 170 per thread for the two-stream butterflies
+template <class PL>
+__global__ void __launch_bounds__(kDualThreads, 1)
+resample_plan2_kernel(const __grid_constant__ WarpParams P) { resample_body_dual<CtView<PL>>(P); }
 
 // index of the compile-time plan for (n_in, n_out), -1 when only the runtime plan applies
 int ct_plan_index(uint32_t n_in, uint32_t n_out) {
@@ -511,55 +562,73 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     P.nblk = (P.out_len + rs.n_out - 1) / rs.n_out;
     if (P.nblk == 0) P.nblk = 1;
     auto a16 = [](size_t x) { return (uint32_t)((x + 15) & ~(size_t)15); };
-    P.off_twi = a16((size_t)PL.twf_len * 8);
-    P.off_posf = P.off_twi + a16((size_t)PL.twi_len * 8);
+    // two-stream mode: compile-time plans only, at least two rows
+    bool dual = rs.ct_index >= 0 && rows_total >= 2;
+    if (const char* g = std::getenv("BIRDA_K2_DUAL")) if (g[0] == '0') dual = false;
+    const size_t esz = dual ? 16 : 8;                   // bytes per complex element in shared memory
+    const int max_threads = dual ? kDualThreads : kMaxThreads;
+    P.dual = dual ? 1 : 0;
+    P.off_twi = a16((size_t)PL.twf_len * esz);
+    P.off_posf = P.off_twi + a16((size_t)PL.twi_len * esz);
     P.off_posi = P.off_posf + a16((size_t)PL.N * 2);
     P.off_P = P.off_posi + a16((size_t)PL.M * 2);
-    P.off_Q = P.off_P + a16((size_t)PL.nkeep * 8);
-    P.off_WI = P.off_Q + a16((size_t)PL.nkeep * 8);
-    P.off_items = P.off_WI + a16((size_t)(PL.M / 2 + 1) * 8);
-    P.off_ctl = P.off_items + a16((size_t)kMaxGroups * 8);
-    P.tables = P.off_ctl + a16((size_t)kMaxGroups * sizeof(GroupCtl));
-    P.off_B = a16((size_t)PL.N * 8);
-    P.off_carry = P.off_B + a16((size_t)PL.M * 8);
-    P.per_group = P.off_carry + a16((size_t)(PL.M / 2) * 8);
+    P.off_Q = P.off_P + a16((size_t)PL.nkeep * esz);
+    P.off_WI = P.off_Q + a16((size_t)PL.nkeep * esz);
+    P.off_items = P.off_WI + a16((size_t)(PL.M / 2 + 1) * esz);
+    P.tables = P.off_items + a16((size_t)kMaxGroups * 8);
+    P.off_B = a16((size_t)PL.N * esz);
+    P.off_carry = P.off_B + a16((size_t)PL.M * esz);
+    P.per_group = P.off_carry + a16((size_t)(PL.M / 2) * esz);
+    if (P.tables + P.per_group > kSmemMax) {
+        if (!dual) return cudaErrorInvalidConfiguration;
+        // does not fit with two streams: fall back to one stream per group
+        setenv("BIRDA_K2_DUAL", "0", 1);
+        cudaError_t e2 = launch_resample_warp(st, sm_count, rs, d_pcm, fmt, channels, total_frames, src_seg, hop, nseg, last_start,
+                                              row_first, rows_total, seg, resampled_len, d_out, launches);
+        unsetenv("BIRDA_K2_DUAL");
+        return e2;
+    }
     int groups = (int)((kSmemMax - P.tables) / P.per_group);
     if (groups > kMaxGroups) groups = kMaxGroups;
-    if (groups < 1) return cudaErrorInvalidConfiguration;
-    int gw = (kMaxThreads / 32) / groups;               // warps cooperating on one block
-    if (gw < 1) { gw = 1; groups = kMaxThreads / 32; }
+    if (groups > max_threads / 32) groups = max_threads / 32;
+    int gw = (max_threads / 32) / groups;               // warps cooperating on one block (pair)
+    if (gw < 1) gw = 1;
     if (gw > 4) gw = 4;
-    if (const char* g = std::getenv("BIRDA_K2_GROUP_WARPS")) { int v = atoi(g); if (v >= 1 && v <= 4 && v * groups * 32 <= kMaxThreads) gw = v; }
-    P.ws = gw == 2 ? 1 : 0;
-    if (const char* g = std::getenv("BIRDA_K2_WS")) P.ws = (g[0] == '1' && gw == 2) ? 1 : 0;
+    if (const char* g = std::getenv("BIRDA_K2_GROUP_WARPS")) { int v = atoi(g); if (v >= 1 && v <= 4 && v * groups * 32 <= max_threads) gw = v; }
     P.groups = groups; P.gw = gw;
-    const int warps = groups;                           // work items are per group
     const size_t smem = P.tables + (size_t)groups * P.per_group;
-    const uint64_t total_warps = (uint64_t)sm_count * groups;
-    // blocks per work item: aim for >= 8 items per warp, keep the recomputed block a small fraction
+    const uint64_t units = dual ? (rows_total + 1) / 2 : rows_total;      // rows or row pairs
+    const uint64_t total_groups = (uint64_t)sm_count * groups;
+    // blocks per work item: aim for >= 8 items per group, keep the recomputed block a small fraction
     uint32_t R = P.nblk;
-    const uint64_t want_items = total_warps * 8;
-    if (rows_total < want_items) {
-        uint64_t per_row = (want_items + rows_total - 1) / rows_total;
+    const uint64_t want_items = total_groups * 8;
+    if (units < want_items) {
+        uint64_t per_row = (want_items + units - 1) / units;
         R = (uint32_t)((P.nblk + per_row - 1) / per_row);
         if (R < 16) R = 16;
         if (R > P.nblk) R = P.nblk;
     }
     P.R = R;
     P.items_per_row = (P.nblk + R - 1) / R;
-    P.nitems = rows_total * P.items_per_row;
+    P.nitems = units * P.items_per_row;
     cudaError_t e = cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    uint64_t ctas = (P.nitems + warps - 1) / warps;
+    uint64_t ctas = (P.nitems + groups - 1) / groups;
     if (ctas > (uint64_t)sm_count) ctas = sm_count;
     const unsigned threads = (unsigned)(groups * gw * 32);
     bool launched = false;
     int i = 0;
 #define BB_CT(NAME, NI, NO, ...)                                                                                        \
     if (!launched && i == rs.ct_index) {                                                                                 \
-        e = cudaFuncSetAttribute(resample_plan_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                                  \
-        resample_plan_kernel<__VA_ARGS__><<<(unsigned)ctas, threads, smem, st>>>(P);                                     \
+        if (dual) {                                                                                                      \
+            e = cudaFuncSetAttribute(resample_plan2_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                              \
+            resample_plan2_kernel<__VA_ARGS__><<<(unsigned)ctas, threads, smem, st>>>(P);                                \
+        } else {                                                                                                         \
+            e = cudaFuncSetAttribute(resample_plan_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                              \
+            resample_plan_kernel<__VA_ARGS__><<<(unsigned)ctas, threads, smem, st>>>(P);                                 \
+        }                                                                                                                \
         launched = true;                                                                                                 \
     }                                                                                                                    \
     ++i;

@@ -73,14 +73,29 @@ struct RtPlan {
     int twf_len, twi_len;        // compact twiddle table sizes (float2 entries)
 };
 
+// shared-memory storage of one element: float2 for a single stream, float4 (re0, re1, im0, im1) for two
+template <class C> struct Mem;
+template <> struct Mem<float2> {
+    using T = float2;
+    static BB_HD float2 ld(const float2* p) { return *p; }
+    static BB_HD void st(float2* p, float2 v) { *p = v; }
+    static BB_HD float2 bcast(float2 w) { return w; }                      // twiddle / table entry for the stream(s)
+};
+template <> struct Mem<cx2> {
+    using T = float4;
+    static BB_HD cx2 ld(const float4* p) { const float4 v = *p; cx2 c; c.re = make_float2(v.x, v.y); c.im = make_float2(v.z, v.w); return c; }
+    static BB_HD void st(float4* p, const cx2& v) { *p = make_float4(v.re.x, v.re.y, v.im.x, v.im.y); }
+    static BB_HD cx2 bcast(float2 w) { cx2 c; c.re = make_float2(w.x, w.x); c.im = make_float2(w.y, w.y); return c; }
+};
+
 // a[k] *= w_span^(p k), k = 1..R-1.  Table layout: chain mode [p] holds w^p; table mode [(k-1)*m + p]
-template <int R> BB_HD void apply_twiddles(float2 (&a)[R], const float2* __restrict__ tw, int m, int p) {
+template <int R, class C> BB_HD void apply_twiddles(C (&a)[R], const typename Mem<C>::T* __restrict__ tw, int m, int p) {
     if constexpr (tw_table_mode(R)) {
 #pragma unroll
-        for (int k = 1; k < R; ++k) a[k] = cmul(a[k], tw[(k - 1) * m + p]);
+        for (int k = 1; k < R; ++k) a[k] = cmul(a[k], Mem<C>::ld(tw + (k - 1) * m + p));
     } else {
-        float2 pw[R];
-        pw[1] = tw[p];
+        C pw[R];
+        pw[1] = Mem<C>::ld(tw + p);
 #pragma unroll
         for (int k = 2; k < R; ++k) pw[k] = cmul(pw[k / 2], pw[k - k / 2]);
 #pragma unroll
@@ -89,115 +104,123 @@ template <int R> BB_HD void apply_twiddles(float2 (&a)[R], const float2* __restr
 }
 
 // ---- forward DIF stage, in place
-template <int R, class S>
-BB_HD void dif_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const S& s, int lane, int nl) {
+template <int R, class C, class S>
+BB_HD void dif_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl) {
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < s.NBF_(); q += nl) {
         const int sb = s.div(q), p = q - sb * m;
-        float2* __restrict__ e = buf + sb * s.SPAN_() + p;
-        float2 a[R];
+        typename Mem<C>::T* __restrict__ e = buf + sb * s.SPAN_() + p;
+        C a[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) a[j] = e[j * m];
+        for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(e + j * m);
         Dft<R, false>::run(a);
-        if (s.TWOFF_() >= 0) apply_twiddles<R>(a, tw + s.TWOFF_(), m, p);
+        if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, p);
 #pragma unroll
-        for (int k = 0; k < R; ++k) e[k * m] = a[k];
+        for (int k = 0; k < R; ++k) Mem<C>::st(e + k * m, a[k]);
     }
 }
 
 // first forward stage: input z[n] comes from `ld(n)` for n < half_in, zero above
-template <int R, class S, class Loader>
-BB_HD void dif_first(float2* __restrict__ buf, const float2* __restrict__ tw, const S& s, int half_in,
+template <int R, class C, class S, class Loader>
+BB_HD void dif_first(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int half_in,
                      const Loader& ld, int lane, int nl) {
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < m; q += nl) {
-        float2 a[R];
+        C a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int n = q + j * m;
-            a[j] = n < half_in ? ld(n) : make_float2(0.f, 0.f);
+            a[j] = n < half_in ? ld(n) : czero<C>();
         }
         Dft<R, false>::run(a);
-        if (s.TWOFF_() >= 0) apply_twiddles<R>(a, tw + s.TWOFF_(), m, q);
-        float2* __restrict__ e = buf + q;
+        if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, q);
+        typename Mem<C>::T* __restrict__ e = buf + q;
 #pragma unroll
-        for (int k = 0; k < R; ++k) e[k * m] = a[k];
+        for (int k = 0; k < R; ++k) Mem<C>::st(e + k * m, a[k]);
     }
 }
 
 // ---- inverse DIT stage, in place
-template <int R, class S>
-BB_HD void dit_stage(float2* __restrict__ buf, const float2* __restrict__ tw, const S& s, int lane, int nl) {
+template <int R, class C, class S>
+BB_HD void dit_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl) {
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < s.NBF_(); q += nl) {
         const int sb = s.div(q), p = q - sb * m;
-        float2* __restrict__ e = buf + sb * s.SPAN_() + p;
-        float2 a[R];
+        typename Mem<C>::T* __restrict__ e = buf + sb * s.SPAN_() + p;
+        C a[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) a[j] = e[j * m];
-        if (s.TWOFF_() >= 0) apply_twiddles<R>(a, tw + s.TWOFF_(), m, p);
+        for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(e + j * m);
+        if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, p);
         Dft<R, true>::run(a);
 #pragma unroll
-        for (int k = 0; k < R; ++k) e[k * m] = a[k];
+        for (int k = 0; k < R; ++k) Mem<C>::st(e + k * m, a[k]);
     }
 }
 
 // last inverse stage (span == M): output z'[n] = (y[2n], y[2n+1]).  n < M/2: add the carry and emit;
 // n >= M/2: becomes the carry of the next block.  R even, so both halves of one carry slot belong
 // to the same butterfly (no cross-lane hazard).
-template <int R, class S, class Sink>
-BB_HD void dit_last(const float2* __restrict__ buf, const float2* __restrict__ tw, const S& s,
-                    float2* __restrict__ carry, const Sink& sink, int lane, int nl) {
+template <int R, class C, class S, class Sink>
+BB_HD void dit_last(const typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s,
+                    typename Mem<C>::T* __restrict__ carry, const Sink& sink, int lane, int nl) {
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int p = lane; p < m; p += nl) {
-        float2 a[R];
+        C a[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) a[j] = buf[p + j * m];
-        if (s.TWOFF_() >= 0) apply_twiddles<R>(a, tw + s.TWOFF_(), m, p);
+        for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(buf + p + j * m);
+        if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, p);
         Dft<R, true>::run(a);
 #pragma unroll
         for (int k = 0; k < R / 2; ++k) {
             const int n = p + k * m;
-            const float2 c = carry[n];
-            sink(n, make_float2(a[k].x + c.x, a[k].y + c.y));
-            carry[n] = a[k + R / 2];
+            sink(n, cadd(a[k], Mem<C>::ld(carry + n)));
+            Mem<C>::st(carry + n, a[k + R / 2]);
         }
     }
 }
 
+template <class C> struct Tables {
+    using T = typename Mem<C>::T;
+    const T* twf; const T* twi; const uint16_t* pos_f; const uint16_t* pos_i;
+    const T* Pt; const T* Qt; const T* WI;
+};
+
 // ---- fused split / filter / re-bin / inverse pack:  A (digit-reversed forward result) -> B
 //   Y(k)  = P[k] Z[k] + Q[k] conj(Z[N-k])                       (k < nkeep, else 0)
 //   Z'(k) = Y(k) + conj(Y(M-k)) + i wi[k] (Y(k) - conj(Y(M-k)))
-BB_HD void split_pass(const float2* __restrict__ A, float2* __restrict__ B, const uint16_t* __restrict__ pos_f,
-                      const uint16_t* __restrict__ pos_i, const float2* __restrict__ Pt, const float2* __restrict__ Qt,
-                      const float2* __restrict__ WI, int N, int M, int nkeep, int lane, int nl) {
+template <class C>
+BB_HD void split_pass(const typename Mem<C>::T* __restrict__ A, typename Mem<C>::T* __restrict__ B, const Tables<C>& T,
+                      int N, int M, int nkeep, int lane, int nl) {
     const int half = M / 2;
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int k = lane; k <= half; k += nl) {
         const int k2 = M - k;
-        float2 yk = make_float2(0.f, 0.f), yk2 = make_float2(0.f, 0.f);
+        C yk = czero<C>(), yk2 = czero<C>();
         if (k < nkeep) {
-            const float2 zk = A[pos_f[k == N ? 0 : k]], zn = cconj(A[pos_f[k == 0 ? 0 : N - k]]);
-            yk = cadd(cmul(Pt[k], zk), cmul(Qt[k], zn));
+            const C zk = Mem<C>::ld(A + T.pos_f[k == N ? 0 : k]), zn = cconj(Mem<C>::ld(A + T.pos_f[k == 0 ? 0 : N - k]));
+            yk = cadd(cmul(Mem<C>::ld(T.Pt + k), zk), cmul(Mem<C>::ld(T.Qt + k), zn));
         }
         if (k2 < nkeep) {
-            const float2 zk = A[pos_f[k2 == N ? 0 : k2]], zn = cconj(A[pos_f[N - k2]]);
-            yk2 = cadd(cmul(Pt[k2], zk), cmul(Qt[k2], zn));
+            const C zk = Mem<C>::ld(A + T.pos_f[k2 == N ? 0 : k2]), zn = cconj(Mem<C>::ld(A + T.pos_f[N - k2]));
+            yk2 = cadd(cmul(Mem<C>::ld(T.Pt + k2), zk), cmul(Mem<C>::ld(T.Qt + k2), zn));
         }
-        if (k == 0) { yk.y = 0.f; yk2.y = 0.f; }           // DC / Nyquist are real (realfft ignores their imag)
-        const float2 wi = WI[k];
+        if (k == 0) {                                   // DC / Nyquist are real (realfft ignores their imag)
+            yk = Cx<C>::make(Cx<C>::re(yk), kzero(typename Cx<C>::K()));
+            yk2 = Cx<C>::make(Cx<C>::re(yk2), kzero(typename Cx<C>::K()));
+        }
+        const C wi = Mem<C>::ld(T.WI + k);
         {
-            const float2 e = cadd(yk, cconj(yk2)), o = cmul(wi, csub(yk, cconj(yk2)));
-            B[pos_i[k]] = make_float2(e.x - o.y, e.y + o.x);
+            const C e = cadd(yk, cconj(yk2)), o = cmul(wi, csub(yk, cconj(yk2)));
+            Mem<C>::st(B + T.pos_i[k], Cx<C>::make(ksub(Cx<C>::re(e), Cx<C>::im(o)), kadd(Cx<C>::im(e), Cx<C>::re(o))));
         }
         if (k != 0 && k2 != k) {
-            const float2 wi2 = make_float2(-wi.x, wi.y);    // exp(i pi (M-k)/M) = -conj(wi)
-            const float2 e = cadd(yk2, cconj(yk)), o = cmul(wi2, csub(yk2, cconj(yk)));
-            B[pos_i[k2]] = make_float2(e.x - o.y, e.y + o.x);
+            const C wi2 = Cx<C>::make(kneg(Cx<C>::re(wi)), Cx<C>::im(wi));    // exp(i pi (M-k)/M) = -conj(wi)
+            const C e = cadd(yk2, cconj(yk)), o = cmul(wi2, csub(yk2, cconj(yk)));
+            Mem<C>::st(B + T.pos_i[k2], Cx<C>::make(ksub(Cx<C>::re(e), Cx<C>::im(o)), kadd(Cx<C>::im(e), Cx<C>::re(o))));
         }
     }
 }
@@ -221,43 +244,36 @@ BB_UNROLL_N(BB_K2W_UNROLL)
         default: break;                                                                         \
     }
 
-struct Tables {
-    const float2* twf; const float2* twi; const uint16_t* pos_f; const uint16_t* pos_i;
-    const float2* Pt; const float2* Qt; const float2* WI;
-};
-
-// One block.  ex.each(f) runs f(lane, nlanes) for every lane of the thread group that owns the block and
-// orders memory between calls (device: __syncwarp or a named barrier; host harness: a loop).  after_split() is called once the forward
-// buffer A is dead (the device kernel starts the next block's PCM prefetch there).
-// forward half: loader -> in-place DIF in A -> (before_split) -> split / filter / re-bin into B.
-// before_split() runs when A holds the forward result and B is about to be overwritten (a forward /
-// inverse warp pair waits there for the inverse warp to release B).
-template <class Exec, class Loader, class BeforeSplit>
-BB_HD void forward_half(const Exec& ex, const RtPlan& P, const Tables& T, float2* A, float2* B, const Loader& ld,
-                        BeforeSplit&& before_split) {
+// One block, in two halves.  ex.each(f) runs f(lane, nlanes) for every lane of the thread group that owns
+// the block and orders memory between calls (device: __syncwarp or a named barrier; host harness: a loop).
+// forward half: loader -> in-place DIF in A -> (before_split) -> split / filter / re-bin into B
+template <class C, class Exec, class Loader, class BeforeSplit>
+BB_HD void forward_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
+                        const Loader& ld, BeforeSplit&& before_split) {
     ex.each([&](int lane, int nl) {
-        BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R>(A, T.twf, P.f[0], P.half_in, ld, lane, nl)))
+        BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R, C>(A, T.twf, P.f[0], P.half_in, ld, lane, nl)))
     });
     for (int t = 1; t < P.nf; ++t)
-        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R>(A, T.twf, P.f[t], lane, nl))) });
+        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R, C>(A, T.twf, P.f[t], lane, nl))) });
     before_split();
-    ex.each([&](int lane, int nl) { split_pass(A, B, T.pos_f, T.pos_i, T.Pt, T.Qt, T.WI, P.N, P.M, P.nkeep, lane, nl); });
+    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.N, P.M, P.nkeep, lane, nl); });
 }
 // inverse half: in-place DIT in B -> overlap-add with the carry -> sink
-template <class Exec, class Sink>
-BB_HD void inverse_half(const Exec& ex, const RtPlan& P, const Tables& T, float2* B, float2* carry, const Sink& sink) {
+template <class C, class Exec, class Sink>
+BB_HD void inverse_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry,
+                        const Sink& sink) {
     for (int t = 0; t + 1 < P.ni; ++t)
-        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R>(B, T.twi, P.i[t], lane, nl))) });
+        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R, C>(B, T.twi, P.i[t], lane, nl))) });
     ex.each([&](int lane, int nl) {
-        BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R>(B, T.twi, P.i[P.ni - 1], carry, sink, lane, nl)))
+        BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R, C>(B, T.twi, P.i[P.ni - 1], carry, sink, lane, nl)))
     });
 }
-template <class Exec, class Loader, class Sink, class AfterSplit>
-BB_HD void process_block(const Exec& ex, const RtPlan& P, const Tables& T, float2* A, float2* B, float2* carry,
-                         const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
-    forward_half(ex, P, T, A, B, ld, [] {});
+template <class C, class Exec, class Loader, class Sink, class AfterSplit>
+BB_HD void process_block(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
+                         typename Mem<C>::T* carry, const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
+    forward_half<C>(ex, P, T, A, B, ld, [] {});
     after_split();
-    inverse_half(ex, P, T, B, carry, sink);
+    inverse_half<C>(ex, P, T, B, carry, sink);
 }
 
 
@@ -298,45 +314,46 @@ struct CtPlan {
     static_assert(INV_::at(INV_::count - 1) % 2 == 0, "last inverse radix must be even");
 };
 
-template <class PL, class Exec, int T> struct CtFwdRest {
-    static BB_HD void run(const Exec& ex, float2* A, const float2* twf) {
+template <class PL, class C, class Exec, int T> struct CtFwdRest {
+    static BB_HD void run(const Exec& ex, typename Mem<C>::T* A, const typename Mem<C>::T* twf) {
         if constexpr (T < PL::Fwd::count) {
             using S = typename PL::template FwdStage<T>;
-            ex.each([&](int lane, int nl) { dif_stage<S::radix>(A, twf, S{}, lane, nl); });
-            CtFwdRest<PL, Exec, T + 1>::run(ex, A, twf);
+            ex.each([&](int lane, int nl) { dif_stage<S::radix, C>(A, twf, S{}, lane, nl); });
+            CtFwdRest<PL, C, Exec, T + 1>::run(ex, A, twf);
         }
     }
 };
-template <class PL, class Exec, int T> struct CtInvMid {
-    static BB_HD void run(const Exec& ex, float2* B, const float2* twi) {
+template <class PL, class C, class Exec, int T> struct CtInvMid {
+    static BB_HD void run(const Exec& ex, typename Mem<C>::T* B, const typename Mem<C>::T* twi) {
         if constexpr (T + 1 < PL::Inv::count) {
             using S = typename PL::template InvStage<T>;
-            ex.each([&](int lane, int nl) { dit_stage<S::radix>(B, twi, S{}, lane, nl); });
-            CtInvMid<PL, Exec, T + 1>::run(ex, B, twi);
+            ex.each([&](int lane, int nl) { dit_stage<S::radix, C>(B, twi, S{}, lane, nl); });
+            CtInvMid<PL, C, Exec, T + 1>::run(ex, B, twi);
         }
     }
 };
 
-template <class PL, class Exec, class Loader, class BeforeSplit>
-BB_HD void forward_half_ct(const Exec& ex, const Tables& T, float2* A, float2* B, const Loader& ld, BeforeSplit&& before_split) {
+template <class PL, class C, class Exec, class Loader, class BeforeSplit>
+BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B, const Loader& ld,
+                           BeforeSplit&& before_split) {
     using S0 = typename PL::template FwdStage<0>;
-    ex.each([&](int lane, int nl) { dif_first<S0::radix>(A, T.twf, S0{}, PL::HALF_IN, ld, lane, nl); });
-    CtFwdRest<PL, Exec, 1>::run(ex, A, T.twf);
+    ex.each([&](int lane, int nl) { dif_first<S0::radix, C>(A, T.twf, S0{}, PL::HALF_IN, ld, lane, nl); });
+    CtFwdRest<PL, C, Exec, 1>::run(ex, A, T.twf);
     before_split();
-    ex.each([&](int lane, int nl) { split_pass(A, B, T.pos_f, T.pos_i, T.Pt, T.Qt, T.WI, PL::N, PL::M, PL::NKEEP, lane, nl); });
+    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::N, PL::M, PL::NKEEP, lane, nl); });
 }
-template <class PL, class Exec, class Sink>
-BB_HD void inverse_half_ct(const Exec& ex, const Tables& T, float2* B, float2* carry, const Sink& sink) {
-    CtInvMid<PL, Exec, 0>::run(ex, B, T.twi);
+template <class PL, class C, class Exec, class Sink>
+BB_HD void inverse_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry, const Sink& sink) {
+    CtInvMid<PL, C, Exec, 0>::run(ex, B, T.twi);
     using SL = typename PL::template InvStage<PL::Inv::count - 1>;
-    ex.each([&](int lane, int nl) { dit_last<SL::radix>(B, T.twi, SL{}, carry, sink, lane, nl); });
+    ex.each([&](int lane, int nl) { dit_last<SL::radix, C>(B, T.twi, SL{}, carry, sink, lane, nl); });
 }
-template <class PL, class Exec, class Loader, class Sink, class AfterSplit>
-BB_HD void process_block_ct(const Exec& ex, const Tables& T, float2* A, float2* B, float2* carry,
-                            const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
-    forward_half_ct<PL>(ex, T, A, B, ld, [] {});
+template <class PL, class C, class Exec, class Loader, class Sink, class AfterSplit>
+BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
+                            typename Mem<C>::T* carry, const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
+    forward_half_ct<PL, C>(ex, T, A, B, ld, [] {});
     after_split();
-    inverse_half_ct<PL>(ex, T, B, carry, sink);
+    inverse_half_ct<PL, C>(ex, T, B, carry, sink);
 }
 
 // X(NAME, N_IN, N_OUT, CtPlan<RSeq<forward DIF radices>, RSeq<inverse DIT radices, last one even>>)
@@ -477,6 +494,15 @@ inline void build_split_tables(int N, int M, int nkeep, const float* filt_re, co
         Qt[k] = make_float2((float)(ar - br), (float)(ai - bi));
     }
     for (int k = 0; k <= M / 2; ++k) WI[k] = make_float2((float)cos(pi * k / M), (float)sin(pi * k / M));
+}
+
+// expand a float2 table into the storage type of the element (float2 as is; two streams: (x, x, y, y))
+template <class C> inline std::vector<typename Mem<C>::T> expand_table(const std::vector<float2>& t);
+template <> inline std::vector<float2> expand_table<float2>(const std::vector<float2>& t) { return t; }
+template <> inline std::vector<float4> expand_table<cx2>(const std::vector<float2>& t) {
+    std::vector<float4> o(t.size());
+    for (size_t i = 0; i < t.size(); ++i) o[i] = make_float4(t[i].x, t[i].x, t[i].y, t[i].y);
+    return o;
 }
 
 }  // namespace k2w

@@ -6,6 +6,7 @@
 #include <vector>
 #include <complex>
 #include <cmath>
+#include <cstring>
 #include <type_traits>
 #include "../birda_b200/csrc/k2_warp.cuh"
 
@@ -18,8 +19,10 @@ struct HostExec {
     template <class F> void each(F&& f) const { for (int l = 0; l < nl; ++l) f(l, nl); }
 };
 
-template <class CT>
+template <class CT, class C>
 static int check_impl(int N, int M, int nl) {
+    using MT = typename Mem<C>::T;
+    constexpr int NS = std::is_same<C, cx2>::value ? 2 : 1;      // streams
     const double pi = 3.14159265358979323846;
     const int NKEEP = N < M ? N + 1 : M;
     RtPlan P; std::vector<int> fwd, inv;
@@ -41,29 +44,40 @@ static int check_impl(int N, int M, int nl) {
     std::vector<float2> Pt(NKEEP), Qt(NKEEP), WI(M / 2 + 1), twf(P.twf_len), twi(P.twi_len);
     build_split_tables(N, M, NKEEP, fre.data(), fim.data(), Pt.data(), Qt.data(), WI.data());
     build_twiddles(P, twf.data(), twi.data());
-    Tables T{twf.data(), twi.data(), pos_f.data(), pos_i.data(), Pt.data(), Qt.data(), WI.data()};
+    auto twf_e = expand_table<C>(twf), twi_e = expand_table<C>(twi), Pt_e = expand_table<C>(Pt), Qt_e = expand_table<C>(Qt), WI_e = expand_table<C>(WI);
+    Tables<C> T{twf_e.data(), twi_e.data(), pos_f.data(), pos_i.data(), Pt_e.data(), Qt_e.data(), WI_e.data()};
 
     const int NB = 3;
-    std::vector<float> x(NB * N);
+    std::vector<float> x(NB * N), x2(NB * N);
     for (auto& v : x) v = (float)(rand() / (double)RAND_MAX - 0.5);
+    for (auto& v : x2) v = (float)(rand() / (double)RAND_MAX - 0.5);
     const int valid_last = N - 77;                 // last block partially valid
-    std::vector<float2> A(N), B(M), carry(M / 2, make_float2(0.f, 0.f));
-    std::vector<float> out(NB * M, 0.f);
+    std::vector<MT> A(N), B(M), carry(M / 2);
+    memset(carry.data(), 0, sizeof(MT) * carry.size());
+    std::vector<float> out(NB * M, 0.f), out2(NB * M, 0.f);
     for (int b = 0; b < NB; ++b) {
         const int valid = b + 1 == NB ? valid_last : N;
+        auto smp = [&](const std::vector<float>& v, int i) { return i < valid ? v[b * N + i] : 0.f; };
         auto loader = [&](int n) {
-            float re = 2 * n < valid ? x[b * N + 2 * n] : 0.f, im = 2 * n + 1 < valid ? x[b * N + 2 * n + 1] : 0.f;
-            return make_float2(re, im);
+            if constexpr (NS == 1) return make_float2(smp(x, 2 * n), smp(x, 2 * n + 1));
+            else { cx2 c; c.re = make_float2(smp(x, 2 * n), smp(x2, 2 * n)); c.im = make_float2(smp(x, 2 * n + 1), smp(x2, 2 * n + 1)); return c; }
         };
-        auto sink = [&](int n, float2 y) { out[b * M + 2 * n] = y.x; out[b * M + 2 * n + 1] = y.y; };
-        if constexpr (kCt) process_block_ct<CT>(HostExec{nl}, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
-        else process_block(HostExec{nl}, P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
+        auto sink = [&](int n, C y) {
+            if constexpr (NS == 1) { out[b * M + 2 * n] = y.x; out[b * M + 2 * n + 1] = y.y; }
+            else { out[b * M + 2 * n] = y.re.x; out[b * M + 2 * n + 1] = y.im.x; out2[b * M + 2 * n] = y.re.y; out2[b * M + 2 * n + 1] = y.im.y; }
+        };
+        if constexpr (kCt) process_block_ct<CT, C>(HostExec{nl}, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
+        else process_block<C>(HostExec{nl}, P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
     }
+    double worst = 0;
+    for (int stream = 0; stream < NS; ++stream) {
+    const std::vector<float>& xs = stream ? x2 : x;
+    const std::vector<float>& outs = stream ? out2 : out;
     std::vector<double> ref(NB * M + M, 0.0);
     for (int b = 0; b < NB; ++b) {
         const int valid = b + 1 == NB ? valid_last : N;
         std::vector<cd> X(N + 1), Y(M + 1, cd(0, 0));
-        for (int k = 0; k <= N; ++k) { cd s = 0; for (int n = 0; n < valid; ++n) s += (double)x[b * N + n] * std::polar(1.0, -pi * k * n / N); X[k] = s; }
+        for (int k = 0; k <= N; ++k) { cd s = 0; for (int n = 0; n < valid; ++n) s += (double)xs[b * N + n] * std::polar(1.0, -pi * k * n / N); X[k] = s; }
         for (int k = 0; k < NKEEP; ++k) Y[k] = X[k] * cd(fre[k], fim[k]);
         for (int n = 0; n < 2 * M; ++n) {
             double s = Y[0].real() + Y[M].real() * ((n & 1) ? -1.0 : 1.0);
@@ -72,22 +86,25 @@ static int check_impl(int N, int M, int nl) {
         }
     }
     double maxerr = 0, rms = 0;
-    for (int i = 0; i < NB * M; ++i) { maxerr = fmax(maxerr, fabs(out[i] - ref[i])); rms += ref[i] * ref[i]; }
+    for (int i = 0; i < NB * M; ++i) { maxerr = fmax(maxerr, fabs(outs[i] - ref[i])); rms += ref[i] * ref[i]; }
     rms = sqrt(rms / (NB * M));
-    printf("%s N=%4d M=%4d fwd[", kCt ? "ct" : "rt", N, M);
+    worst = fmax(worst, maxerr / rms);
+    }
+    printf("%s x%d N=%4d M=%4d fwd[", kCt ? "ct" : "rt", NS, N, M);
     for (int r : fwd) printf(" %d", r);
     printf(" ] inv[");
     for (int r : inv) printf(" %d", r);
-    printf(" ]  rel err %.3e\n", maxerr / rms);
-    return maxerr / rms < 5e-6 ? 0 : 1;
+    printf(" ]  rel err %.3e\n", worst);
+    return worst < 5e-6 ? 0 : 1;
 }
 
 int main() {
     int bad = 0;
     const int cases[][2] = {{1029, 1120}, {1029, 2240}, {1026, 684}, {1024, 512}, {1024, 1536}, {1024, 3072},
                             {1323, 960}, {1323, 1920}, {1024, 2048}, {1026, 342}, {1029, 560}, {1125, 216}, {1024, 256}};
-    for (auto& c : cases) for (int nl : {32, 64}) bad += check_impl<void>(c[0], c[1], nl);
-#define BB_CT(NAME, NI, NO, ...) for (int nl : {32, 64}) bad += check_impl<__VA_ARGS__>(NI, NO, nl);
+    for (auto& c : cases) for (int nl : {32, 64}) bad += check_impl<void, float2>(c[0], c[1], nl);
+    for (auto& c : cases) bad += check_impl<void, cx2>(c[0], c[1], 96);
+#define BB_CT(NAME, NI, NO, ...) bad += check_impl<__VA_ARGS__, float2>(NI, NO, 64); bad += check_impl<__VA_ARGS__, cx2>(NI, NO, 96);
     BB_K2_CT_PLANS(BB_CT)
 #undef BB_CT
     printf(bad ? "FAILED\n" : "all plans ok\n");
