@@ -42,6 +42,9 @@ struct RtStage {
     int nbf;        // butterflies in the stage = total / radix
     int tw_off;     // offset of this stage's compact twiddle table (entries p in [0, m)); -1 = none
     uint32_t magic; // ceil(2^32 / m) for q / m  (0 when m == 1)
+    int nsb;        // sub-transforms in the stage = nbf / m
+    uint32_t magic_nsb;
+    int sbfast;     // 1: consecutive lanes walk sub-transforms (stride = span, odd) instead of p (see decompose)
     BB_HD int M_() const { return m; }
     BB_HD int SPAN_() const { return span; }
     BB_HD int NBF_() const { return nbf; }
@@ -52,6 +55,19 @@ struct RtStage {
 #else
         return q / m;
 #endif
+    }
+    // butterfly index q -> (sub-transform sb, position p).  Short sub-transforms (m < 32) with an odd span are
+    // walked sub-transform-first: the lanes of a warp then hit addresses `span` apart (odd stride in 8-byte
+    // units: bank-conflict free) instead of several short runs that collide.
+    BB_HD void decompose(int q, int& sb, int& p) const {
+        if (sbfast) {
+#ifdef __CUDA_ARCH__
+            p = nsb == 1 ? q : (int)__umulhi((unsigned)q, magic_nsb);
+#else
+            p = q / nsb;
+#endif
+            sb = q - p * nsb;
+        } else { sb = div(q); p = q - sb * m; }
     }
 };
 
@@ -64,6 +80,12 @@ struct CtStage {
     static BB_HD constexpr int NBF_() { return NTOT / RADIX; }
     static BB_HD constexpr int TWOFF_() { return TWOFF; }
     static BB_HD constexpr int div(int q) { return q / (SPAN / RADIX); }
+    static constexpr int NSB = NTOT / SPAN;
+    static constexpr bool SBFAST = (SPAN / RADIX) < 32 && (SPAN % 2) == 1 && NSB > 1;
+    static BB_HD void decompose(int q, int& sb, int& p) {
+        if (SBFAST) { p = q / NSB; sb = q - p * NSB; }
+        else { sb = q / (SPAN / RADIX); p = q - sb * (SPAN / RADIX); }
+    }
 };
 
 struct RtPlan {
@@ -109,7 +131,8 @@ BB_HD void dif_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < s.NBF_(); q += nl) {
-        const int sb = s.div(q), p = q - sb * m;
+        int sb, p;
+        s.decompose(q, sb, p);
         typename Mem<C>::T* __restrict__ e = buf + sb * s.SPAN_() + p;
         C a[R];
 #pragma unroll
@@ -148,7 +171,8 @@ BB_HD void dit_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < s.NBF_(); q += nl) {
-        const int sb = s.div(q), p = q - sb * m;
+        int sb, p;
+        s.decompose(q, sb, p);
         typename Mem<C>::T* __restrict__ e = buf + sb * s.SPAN_() + p;
         C a[R];
 #pragma unroll
@@ -429,6 +453,8 @@ inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const st
         s.tw_off = (t + 1 < P->nf) ? off : -1;
         if (s.tw_off >= 0) off += tw_table_mode(s.radix) ? s.m * (s.radix - 1) : s.m;
         s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
+        s.nsb = N / s.span; s.magic_nsb = s.nsb <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.nsb - 1) / s.nsb);
+        s.sbfast = (s.m < 32 && (s.span % 2) == 1 && s.nsb > 1) ? 1 : 0;
         span = s.m;
     }
     P->twf_len = off > 0 ? off : 1;
@@ -439,6 +465,8 @@ inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const st
         s.tw_off = t > 0 ? off : -1;
         if (s.tw_off >= 0) off += tw_table_mode(s.radix) ? s.m * (s.radix - 1) : s.m;
         s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
+        s.nsb = M / s.span; s.magic_nsb = s.nsb <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.nsb - 1) / s.nsb);
+        s.sbfast = (s.m < 32 && (s.span % 2) == 1 && s.nsb > 1) ? 1 : 0;
         prev = s.span;
     }
     P->twi_len = off > 0 ? off : 1;
