@@ -165,10 +165,10 @@ template <class PL> struct CtView {
     static __device__ __forceinline__ constexpr int m(const RtPlan&) { return PL::M; }
     static __device__ __forceinline__ constexpr int half_in(const RtPlan&) { return PL::HALF_IN; }
     template <class C, class Exec, class Loader, class Sink, class After>
-    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan&, const Tables<C>& T, typename Mem<C>::T* A,
+    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const Tables<C>& T, typename Mem<C>::T* A,
                                                  typename Mem<C>::T* B, typename Mem<C>::T* carry, const Loader& ld,
                                                  const Sink& sink, After&& after) {
-        process_block_ct<PL, C>(ex, T, A, B, carry, ld, sink, after);
+        process_block_ct<PL, C>(ex, T, p.split_c, A, B, carry, ld, sink, after);
     }
 };
 
@@ -514,6 +514,7 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     } else if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
     std::vector<uint16_t> pf(P.N), pi_(P.M);
     build_pos_tables(fwd, inv, P.N, P.M, pf.data(), pi_.data());
+    P.split_c = choose_split_stride(P.N, P.M, P.nkeep, pf.data(), pi_.data());
     std::vector<float2> Pt(P.nkeep), Qt(P.nkeep), WI(P.M / 2 + 1), twf(P.twf_len), twi(P.twi_len);
     build_split_tables(P.N, P.M, P.nkeep, spec.filt_re.data(), spec.filt_im.data(), Pt.data(), Qt.data(), WI.data());
     build_twiddles(P, twf.data(), twi.data());

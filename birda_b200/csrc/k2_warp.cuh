@@ -81,7 +81,7 @@ struct CtStage {
     static BB_HD constexpr int TWOFF_() { return TWOFF; }
     static BB_HD constexpr int div(int q) { return q / (SPAN / RADIX); }
     static constexpr int NSB = NTOT / SPAN;
-    static constexpr bool SBFAST = (SPAN / RADIX) < 32 && (SPAN % 2) == 1 && NSB > 1;
+    static constexpr bool SBFAST = (SPAN / RADIX) < 16 && (SPAN % 2) == 1 && NSB >= 8;
     static BB_HD void decompose(int q, int& sb, int& p) {
         if (SBFAST) { p = q / NSB; sb = q - p * NSB; }
         else { sb = q / (SPAN / RADIX); p = q - sb * (SPAN / RADIX); }
@@ -93,6 +93,7 @@ struct RtPlan {
     int nf, ni;
     RtStage f[kMaxStages], i[kMaxStages];
     int twf_len, twi_len;        // compact twiddle table sizes (float2 entries)
+    int split_c;                 // the split pass visits k = (idx * split_c) mod (M/2+1): spreads its scattered accesses over the banks
 };
 
 // shared-memory storage of one element: float2 for a single stream, float4 (re0, re1, im0, im1) for two
@@ -218,10 +219,12 @@ template <class C> struct Tables {
 //   Z'(k) = Y(k) + conj(Y(M-k)) + i wi[k] (Y(k) - conj(Y(M-k)))
 template <class C>
 BB_HD void split_pass(const typename Mem<C>::T* __restrict__ A, typename Mem<C>::T* __restrict__ B, const Tables<C>& T,
-                      int N, int M, int nkeep, int lane, int nl) {
-    const int half = M / 2;
+                      int N, int M, int nkeep, int split_c, int lane, int nl) {
+    const int half = M / 2, L = half + 1;
+    int k = (int)(((long long)lane * split_c) % L);
+    const int step = (int)(((long long)nl * split_c) % L);
 BB_UNROLL_N(BB_K2W_UNROLL)
-    for (int k = lane; k <= half; k += nl) {
+    for (int idx = lane; idx <= half; idx += nl, k = (k + step >= L) ? k + step - L : k + step) {
         const int k2 = M - k;
         C yk = czero<C>(), yk2 = czero<C>();
         if (k < nkeep) {
@@ -280,7 +283,7 @@ BB_HD void forward_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typ
     for (int t = 1; t < P.nf; ++t)
         ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R, C>(A, T.twf, P.f[t], lane, nl))) });
     before_split();
-    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.N, P.M, P.nkeep, lane, nl); });
+    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.N, P.M, P.nkeep, P.split_c, lane, nl); });
 }
 // inverse half: in-place DIT in B -> overlap-add with the carry -> sink
 template <class C, class Exec, class Sink>
@@ -358,13 +361,13 @@ template <class PL, class C, class Exec, int T> struct CtInvMid {
 };
 
 template <class PL, class C, class Exec, class Loader, class BeforeSplit>
-BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B, const Loader& ld,
+BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, int split_c, typename Mem<C>::T* A, typename Mem<C>::T* B, const Loader& ld,
                            BeforeSplit&& before_split) {
     using S0 = typename PL::template FwdStage<0>;
     ex.each([&](int lane, int nl) { dif_first<S0::radix, C>(A, T.twf, S0{}, PL::HALF_IN, ld, lane, nl); });
     CtFwdRest<PL, C, Exec, 1>::run(ex, A, T.twf);
     before_split();
-    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::N, PL::M, PL::NKEEP, lane, nl); });
+    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::N, PL::M, PL::NKEEP, split_c, lane, nl); });
 }
 template <class PL, class C, class Exec, class Sink>
 BB_HD void inverse_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry, const Sink& sink) {
@@ -373,9 +376,9 @@ BB_HD void inverse_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::
     ex.each([&](int lane, int nl) { dit_last<SL::radix, C>(B, T.twi, SL{}, carry, sink, lane, nl); });
 }
 template <class PL, class C, class Exec, class Loader, class Sink, class AfterSplit>
-BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
+BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, int split_c, typename Mem<C>::T* A, typename Mem<C>::T* B,
                             typename Mem<C>::T* carry, const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
-    forward_half_ct<PL, C>(ex, T, A, B, ld, [] {});
+    forward_half_ct<PL, C>(ex, T, split_c, A, B, ld, [] {});
     after_split();
     inverse_half_ct<PL, C>(ex, T, B, carry, sink);
 }
@@ -454,7 +457,7 @@ inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const st
         if (s.tw_off >= 0) off += tw_table_mode(s.radix) ? s.m * (s.radix - 1) : s.m;
         s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
         s.nsb = N / s.span; s.magic_nsb = s.nsb <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.nsb - 1) / s.nsb);
-        s.sbfast = (s.m < 32 && (s.span % 2) == 1 && s.nsb > 1) ? 1 : 0;
+        s.sbfast = (s.m < 16 && (s.span % 2) == 1 && s.nsb >= 8) ? 1 : 0;
         span = s.m;
     }
     P->twf_len = off > 0 ? off : 1;
@@ -466,7 +469,7 @@ inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const st
         if (s.tw_off >= 0) off += tw_table_mode(s.radix) ? s.m * (s.radix - 1) : s.m;
         s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
         s.nsb = M / s.span; s.magic_nsb = s.nsb <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.nsb - 1) / s.nsb);
-        s.sbfast = (s.m < 32 && (s.span % 2) == 1 && s.nsb > 1) ? 1 : 0;
+        s.sbfast = (s.m < 16 && (s.span % 2) == 1 && s.nsb >= 8) ? 1 : 0;
         prev = s.span;
     }
     P->twi_len = off > 0 ? off : 1;
@@ -506,6 +509,31 @@ inline void build_pos_tables(const std::vector<int>& fwd, const std::vector<int>
         }
         pos_i[n] = (uint16_t)pos;
     }
+}
+
+// Pick the split-pass stride: odd, coprime with L = M/2+1, minimising 16-byte bank-quad collisions of the
+// six scattered accesses (4 reads of A through pos_f, 2 writes of B through pos_i) per quarter-warp.
+inline int choose_split_stride(int N, int M, int nkeep, const uint16_t* pos_f, const uint16_t* pos_i) {
+    const int L = M / 2 + 1;
+    auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+    long best_cost = -1; int best_c = 1;
+    for (int c = 1; c < 128 && c < L; c += 2) {
+        if (gcd(c, L) != 1) continue;
+        long cost = 0;
+        for (int i0 = 0; i0 < L; i0 += 8) {
+            int cnt[6][8] = {{0}};
+            for (int i = i0; i < i0 + 8 && i < L; ++i) {
+                const int k = (int)(((long long)i * c) % L), k2 = M - k;
+                if (k < nkeep) { cnt[0][pos_f[k == N ? 0 : k] & 7]++; cnt[1][pos_f[k == 0 ? 0 : N - k] & 7]++; }
+                if (k2 < nkeep) { cnt[2][pos_f[k2 == N ? 0 : k2] & 7]++; cnt[3][pos_f[N - k2] & 7]++; }
+                cnt[4][pos_i[k] & 7]++;
+                if (k != 0 && k2 != k) cnt[5][pos_i[k2 % M] & 7]++;
+            }
+            for (auto& a : cnt) { int mx = 0; for (int v : a) mx = v > mx ? v : mx; cost += mx; }
+        }
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+    }
+    return best_c;
 }
 
 // P = A + B, Q = A - B with A = 0.5 Hf, B = -0.5 i exp(-i pi k / N) Hf;  WI[k] = exp(+i pi k / M)

@@ -34,6 +34,7 @@ static int check_impl(int N, int M, int nl) {
     } else if (!build_plan(N, M, NKEEP, &P, &fwd, &inv)) { printf("N=%d M=%d: no plan (generic kernel)\n", N, M); return 0; }
     std::vector<uint16_t> pos_f(N), pos_i(M);
     build_pos_tables(fwd, inv, N, M, pos_f.data(), pos_i.data());
+    P.split_c = choose_split_stride(N, M, NKEEP, pos_f.data(), pos_i.data());
     srand(1234 + N);
     std::vector<double> h(N);
     for (int n = 0; n < N; ++n) h[n] = (rand() / (double)RAND_MAX - 0.5) * exp(-0.5 * pow((n - N / 2) / (N / 8.0), 2)) / N;
@@ -66,7 +67,7 @@ static int check_impl(int N, int M, int nl) {
             if constexpr (NS == 1) { out[b * M + 2 * n] = y.x; out[b * M + 2 * n + 1] = y.y; }
             else { out[b * M + 2 * n] = y.re.x; out[b * M + 2 * n + 1] = y.im.x; out2[b * M + 2 * n] = y.re.y; out2[b * M + 2 * n + 1] = y.im.y; }
         };
-        if constexpr (kCt) process_block_ct<CT, C>(HostExec{nl}, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
+        if constexpr (kCt) process_block_ct<CT, C>(HostExec{nl}, T, P.split_c, A.data(), B.data(), carry.data(), loader, sink, [] {});
         else process_block<C>(HostExec{nl}, P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
     }
     double worst = 0;
@@ -94,7 +95,7 @@ static int check_impl(int N, int M, int nl) {
     for (int r : fwd) printf(" %d", r);
     printf(" ] inv[");
     for (int r : inv) printf(" %d", r);
-    printf(" ]  rel err %.3e\n", worst);
+    printf(" ] c=%d  rel err %.3e\n", P.split_c, worst);
     return worst < 5e-6 ? 0 : 1;
 }
 
