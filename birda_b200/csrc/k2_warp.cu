@@ -471,7 +471,10 @@ template <class PL>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 resample_plan_kernel(const __grid_constant__ WarpParams P) { resample_body<CtView<PL>>(P); }
 
-constexpr int kDualThreads = 384;     // 12 warps: register cap 170 per thread for the two-stream butterflies
+#ifndef BB_K2_DUAL_THREADS
+#define BB_K2_DUAL_THREADS 384
+#endif
+constexpr int kDualThreads = BB_K2_DUAL_THREADS;     // 384 = 12 warps: register cap 170 per thread for the two-stream butterflies
 template <class PL>
 __global__ void __launch_bounds__(kDualThreads, 1)
 resample_plan2_kernel(const __grid_constant__ WarpParams P) { resample_body_dual<CtView<PL>>(P); }

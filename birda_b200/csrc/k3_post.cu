@@ -39,6 +39,24 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+constexpr int kCap = 1024;     // candidate list capacity per row (scores that clear the coarse threshold)
+
+// block-wide arg-max under the total order (conf desc, idx asc)
+__device__ __forceinline__ void block_argmax(float& c, uint32_t& ix, float* s_wc, uint32_t* s_wi, int lane, int warp) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float oc = __shfl_xor_sync(0xffffffffu, c, o);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (better(oc, oi, c, ix)) { c = oc; ix = oi; }
+    }
+    if (lane == 0) { s_wc[warp] = c; s_wi[warp] = ix; }
+    __syncthreads();
+    c = s_wc[0]; ix = s_wi[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) if (better(s_wc[w], s_wi[w], c, ix)) { c = s_wc[w]; ix = s_wi[w]; }
+    __syncthreads();
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(kThreads)
 post_kernel(const float* __restrict__ scores, uint32_t C, bb_post_cfg cfg,
@@ -47,15 +65,17 @@ post_kernel(const float* __restrict__ scores, uint32_t C, bb_post_cfg cfg,
     __shared__ float    s_red[kWarps];
     __shared__ float    s_wc[kWarps];
     __shared__ uint32_t s_wi[kWarps];
-    __shared__ float    s_bc;
-    __shared__ uint32_t s_bi;
     __shared__ Cand     s_win[K];
+    __shared__ Cand     s_list[kCap];
+    __shared__ int      s_count;
 
     const uint32_t row = blockIdx.x;
     const float* __restrict__ x = scores + (uint64_t)row * C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t topk = cfg.top_k;
     const float min_conf = cfg.min_confidence;
+    if (tid == 0) s_count = 0;
+    if (tid < K) { s_win[tid].conf = 0.f; s_win[tid].idx = 0xFFFFFFFFu; }
 
     float row_max = 0.f, inv_sum = 1.f;
     if (ACT == BB_ACT_SOFTMAX) {
@@ -78,18 +98,18 @@ post_kernel(const float* __restrict__ scores, uint32_t C, bb_post_cfg cfg,
         for (int w = 0; w < kWarps; ++w) s += s_red[w];
         row_max = m; inv_sum = 1.0f / s;
     }
-    // coarse reject in the score domain (sigmoid only): anything this far below logit(min_conf)
-    // cannot reach min_conf, so its activation is never evaluated.
+    auto act = [&](float xv) -> float {
+        if (ACT == BB_ACT_SIGMOID) return sigmoidf_(xv);
+        if (ACT == BB_ACT_SOFTMAX) return expf(xv - row_max) * inv_sum;
+        return xv;
+    };
+    // coarse threshold in the SCORE domain: anything below cannot reach min_conf (activations are monotone),
+    // so the hot loop is load + compare and only survivors are appended to the candidate list.
     float coarse = -FLT_MAX;
-    if (ACT == BB_ACT_SIGMOID && min_conf > 0.f && min_conf < 1.f)
-        coarse = logf(min_conf / (1.0f - min_conf)) - 0.01f;
-    if (ACT == BB_ACT_NONE) coarse = min_conf;     // conf == score; NaN min_conf rejects all below
-
-    Cand loc[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) { loc[k].conf = -FLT_MAX; loc[k].idx = 0xFFFFFFFFu; }
-    int nloc = 0;
-    float kth = -FLT_MAX;          // confidence of the list's last slot (loc[topk-1]) kept in a register
+    if (ACT == BB_ACT_SIGMOID && min_conf > 0.f && min_conf < 1.f) coarse = logf(min_conf / (1.0f - min_conf)) - 0.01f;
+    if (ACT == BB_ACT_SOFTMAX && min_conf > 0.f) coarse = row_max + logf(min_conf / inv_sum) - 0.01f;
+    if (ACT == BB_ACT_NONE) coarse = min_conf;
+    __syncthreads();
 
     constexpr int U = 8;
     for (uint32_t base = tid; base < C; base += kThreads * U) {
@@ -102,53 +122,46 @@ post_kernel(const float* __restrict__ scores, uint32_t C, bb_post_cfg cfg,
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t i = base + u * kThreads;
-            if (i >= C) continue;
-            const float xv = v[u];
-            if (!(xv >= coarse)) continue;
-            float c;
-            if (ACT == BB_ACT_SIGMOID) c = sigmoidf_(xv);
-            else if (ACT == BB_ACT_SOFTMAX) c = expf(xv - row_max) * inv_sum;
-            else c = xv;
-            if (!(c >= min_conf)) continue;
-            // later index never beats an equal confidence already in the list
-            if (nloc == (int)topk && !(c > kth)) continue;
-            // insert keeping the list sorted descending (stable)
-            Cand cur{c, i};
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if (k < (int)topk && cur.conf > loc[k].conf) { Cand t = loc[k]; loc[k] = cur; cur = t; }
+            if (i < C && v[u] >= coarse) {
+                const int pos = atomicAdd(&s_count, 1);
+                if (pos < kCap) { s_list[pos].conf = v[u]; s_list[pos].idx = i; }
             }
-            if (nloc < (int)topk) ++nloc;
-#pragma unroll
-            for (int k = 0; k < K; ++k) if (k == (int)topk - 1) kth = loc[k].conf;
         }
     }
-
-    // merge: top_k rounds of block-wide arg-max over the list heads
-    int head = 0;
-    for (uint32_t r = 0; r < topk; ++r) {
-        float c = -FLT_MAX; uint32_t ix = 0xFFFFFFFFu;
-#pragma unroll
-        for (int k = 0; k < K; ++k) if (k == head && k < nloc) { c = loc[k].conf; ix = loc[k].idx; }
-        float bc = c; uint32_t bi = ix;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
-            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (better(oc, oi, bc, bi)) { bc = oc; bi = oi; }
-        }
-        if (lane == 0) { s_wc[warp] = bc; s_wi[warp] = bi; }
+    __syncthreads();
+    const int n = s_count;
+    if (n <= kCap) {
+        // activate the survivors, then rank each one against the others (total order: conf desc, idx asc)
+        for (int t = tid; t < n; t += kThreads) s_list[t].conf = act(s_list[t].conf);
         __syncthreads();
-        if (tid == 0) {
-            float gc = s_wc[0]; uint32_t gi = s_wi[0];
-#pragma unroll
-            for (int w = 1; w < kWarps; ++w) if (better(s_wc[w], s_wi[w], gc, gi)) { gc = s_wc[w]; gi = s_wi[w]; }
-            s_bc = gc; s_bi = gi;
-            s_win[r].conf = gc; s_win[r].idx = gi;
+        for (int t = tid; t < n; t += kThreads) {
+            const float c = s_list[t].conf; const uint32_t ix = s_list[t].idx;
+            if (!(c >= min_conf)) continue;
+            uint32_t rank = 0;
+            for (int o = 0; o < n; ++o) rank += better(s_list[o].conf, s_list[o].idx, c, ix) ? 1u : 0u;
+            if (rank < topk) { s_win[rank].conf = c; s_win[rank].idx = ix; }
         }
-        __syncthreads();
-        if (s_bi != 0xFFFFFFFFu && ix == s_bi) ++head;     // the owner pops its head
+    } else {
+        // list overflow (tiny min_conf): top_k rounds of block-wide arg-max over the whole row, each round
+        // restricted to candidates strictly after the previous winner in the total order
+        float pc = FLT_MAX; uint32_t pi = 0;
+        for (uint32_t r = 0; r < topk; ++r) {
+            float bc = -FLT_MAX; uint32_t bi = 0xFFFFFFFFu;
+            for (uint32_t i = tid; i < C; i += kThreads) {
+                const float xv = __ldg(x + i);
+                if (!(xv >= coarse)) continue;
+                const float c = act(xv);
+                if (!(c >= min_conf)) continue;
+                if (r > 0 && !better(pc, pi, c, i)) continue;
+                if (better(c, i, bc, bi)) { bc = c; bi = i; }
+            }
+            block_argmax(bc, bi, s_wc, s_wi, lane, warp);
+            if (bi == 0xFFFFFFFFu) break;
+            if (tid == 0) { s_win[r].conf = bc; s_win[r].idx = bi; }
+            pc = bc; pi = bi;
+        }
     }
+    __syncthreads();
 
     if (tid == 0) {
         Cand out[K];
