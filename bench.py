@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -296,7 +296,7 @@ def run_gpu(args):
             "e2e": {"value": e2e, "unit": "audio-h/s", "h2d_bytes_per_step": int(h_pcm.numel() * 2),
                     "d2h_bytes_per_step": int(rows * 5 * 8 + rows * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "resample_warp_kernel (K2)", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "resample_plan2_kernel (K2, two-stream compile-time plan 1029/1120)", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": k2_traffic_bytes(), "algorithmic_bytes": ALGO_BYTES_FRONT,
                          "peak_source": peak_src,
                          "note": "K2 is FP32/shared-memory bound, not HBM bound (SURVEY 7.3 item 2)",
