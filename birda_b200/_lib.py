@@ -28,6 +28,11 @@ f32p = C.POINTER(C.c_float)
 vp = C.c_void_p
 
 
+class WavInfo(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
+                ("fmt", C.c_int32), ("frames", C.c_uint64), ("data_offset", C.c_uint64)]
+
+
 class PostCfg(C.Structure):
     _fields_ = [("activation", C.c_int32), ("min_confidence", C.c_float), ("top_k", C.c_uint32),
                 ("range_threshold", C.c_float), ("keep_unmatched", C.c_int32), ("rerank", C.c_int32)]
@@ -67,6 +72,8 @@ SIGNATURES = {
                                     C.POINTER(vp), u64p, f32p, f32p, u64p, u64p, u64p]),
     "bb_post_run_device": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostCfg), vp, vp, vp, vp, vp]),
     "bb_post_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostCfg), vp, vp, u32p, f32p, u32p]),
+    "bb_wav_probe": (C.c_int32, [C.c_char_p, C.POINTER(WavInfo)]),
+    "bb_wav_read": (C.c_int32, [C.c_char_p, C.POINTER(WavInfo), C.c_uint64, C.c_uint64, vp]),
     "bb_dev_alloc": (C.c_int32, [vp, C.c_uint64, C.POINTER(vp)]),
     "bb_dev_free": (None, [vp, vp]),
     "bb_memcpy_h2d": (C.c_int32, [vp, vp, vp, C.c_uint64]),

@@ -94,6 +94,22 @@ class rules:
         return a.value, b.value
 
 
+def wav_probe(path: str) -> _lib.WavInfo:
+    """Header of a RIFF/RF64 WAVE file (rate, channels, sample format, frames)."""
+    info = _lib.WavInfo()
+    check(lib.bb_wav_probe(path.encode(), C.byref(info)))
+    return info
+
+
+def wav_read(path: str, info: _lib.WavInfo, first_frame: int = 0, frames: Optional[int] = None) -> np.ndarray:
+    """Interleaved frames [first_frame, first_frame+frames) as int16 / int32 / float32 (no conversion)."""
+    n = info.frames - first_frame if frames is None else frames
+    dt = {FMT_S16: np.int16, FMT_S32: np.int32, FMT_F32: np.float32}[info.fmt]
+    out = np.empty(n * info.channels, dtype=dt)
+    check(lib.bb_wav_read(path.encode(), C.byref(info), first_frame, n, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 def device_count() -> int:
     n = C.c_int32()
     rc = lib.bb_device_count(C.byref(n))

@@ -1,0 +1,105 @@
+// PCM ingest for the front end: RIFF/WAVE and RF64 header parsing + positioned reads into a caller
+// buffer (ideally page-locked, see bb_host_alloc).  SURVEY.md §8f rank 1: at thousands x realtime the
+// reference's symphonia decode thread and its three opens per file (src/lib.rs:726,
+// src/pipeline/processor.rs:457, :59; reader src/audio/decode.rs:54-128) become the wall; WAV PCM is
+// already the interleaved layout K1/K2 consume, so the file is read straight into the staging buffer.
+// Sample formats follow what the reference converts (src/audio/decode.rs:353-411): 16-bit PCM -> S16,
+// 32-bit PCM -> S32, 32-bit float -> F32.  8/24-bit PCM and 64-bit float are reported as unsupported
+// (the reference's append_samples drops U8/S24/F64 buffers silently, decode.rs:407-409).
+#include "../../include/birda_b200.h"
+#include "rules.hpp"
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
+
+namespace bb { void set_tls_error(const std::string& m); }
+
+namespace {
+uint32_t rd32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+uint16_t rd16(const unsigned char* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+uint64_t rd64(const unsigned char* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+int fail(int code, const std::string& m) { bb::set_tls_error(m); return code; }
+}  // namespace
+
+extern "C" {
+
+int32_t bb_wav_probe(const char* path, bb_wav_info* out) {
+    if (!path || !out) return fail(BB_ERR_INVALID_ARG, "null argument");
+    std::memset(out, 0, sizeof(*out));
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return fail(BB_ERR_IO, std::string("cannot open ") + path);
+    struct stat st; ::fstat(fd, &st);
+    const uint64_t file_size = (uint64_t)st.st_size;
+    unsigned char h[12];
+    if (::pread(fd, h, 12, 0) != 12 || std::memcmp(h + 8, "WAVE", 4) != 0 ||
+        (std::memcmp(h, "RIFF", 4) != 0 && std::memcmp(h, "RF64", 4) != 0)) {
+        ::close(fd); return fail(BB_ERR_UNSUPPORTED_FORMAT, std::string(path) + ": not a RIFF/RF64 WAVE file");
+    }
+    const bool rf64 = std::memcmp(h, "RF64", 4) == 0;
+    uint64_t pos = 12, data_size64 = 0; bool have_ds64 = false, have_fmt = false, have_data = false;
+    uint16_t tag = 0, channels = 0, bits = 0, block_align = 0; uint32_t rate = 0;
+    uint64_t data_off = 0, data_size = 0;
+    while (pos + 8 <= file_size) {
+        unsigned char ch[8];
+        if (::pread(fd, ch, 8, (off_t)pos) != 8) break;
+        uint64_t sz = rd32(ch + 4);
+        const uint64_t body = pos + 8;
+        if (std::memcmp(ch, "ds64", 4) == 0 && sz >= 24) {
+            unsigned char d[24];
+            if (::pread(fd, d, 24, (off_t)body) == 24) { data_size64 = rd64(d + 8); have_ds64 = true; }
+        } else if (std::memcmp(ch, "fmt ", 4) == 0 && sz >= 16) {
+            unsigned char f[40]; std::memset(f, 0, sizeof(f));
+            const size_t n = sz < 40 ? (size_t)sz : 40;
+            if (::pread(fd, f, n, (off_t)body) != (ssize_t)n) break;
+            tag = rd16(f); channels = rd16(f + 2); rate = rd32(f + 4); block_align = rd16(f + 12); bits = rd16(f + 14);
+            if (tag == 0xFFFE && sz >= 40) tag = rd16(f + 24);      // WAVE_FORMAT_EXTENSIBLE: sub-format GUID starts with the tag
+            have_fmt = true;
+        } else if (std::memcmp(ch, "data", 4) == 0) {
+            data_off = body;
+            data_size = (sz == 0xFFFFFFFFu && rf64 && have_ds64) ? data_size64 : sz;
+            if (data_off + data_size > file_size) data_size = file_size - data_off;      // truncated file: decode what exists
+            have_data = true;
+            break;
+        }
+        pos = body + sz + (sz & 1);
+    }
+    ::close(fd);
+    if (!have_fmt || !have_data || channels == 0 || rate == 0)
+        return fail(BB_ERR_UNSUPPORTED_FORMAT, std::string(path) + ": missing fmt/data chunk");
+    out->sample_rate = rate; out->channels = channels; out->bits_per_sample = bits;
+    out->data_offset = data_off;
+    const uint32_t bytes = bits / 8;
+    out->fmt = 0;
+    if (tag == 1 && bits == 16) out->fmt = BB_S16;
+    else if (tag == 1 && bits == 32) out->fmt = BB_S32;
+    else if (tag == 3 && bits == 32) out->fmt = BB_F32;
+    const uint32_t frame_bytes = block_align ? block_align : bytes * channels;
+    out->frames = frame_bytes ? data_size / frame_bytes : 0;
+    if (out->fmt == 0)
+        return fail(BB_ERR_UNSUPPORTED_FORMAT, std::string(path) + ": sample format tag " + std::to_string(tag) + " / " +
+                    std::to_string(bits) + " bits is not converted by the reference (decode.rs:353-411)");
+    return BB_OK;
+}
+
+int32_t bb_wav_read(const char* path, const bb_wav_info* info, uint64_t first_frame, uint64_t frames, void* dst) {
+    if (!path || !info || (!dst && frames)) return fail(BB_ERR_INVALID_ARG, "null argument");
+    if (info->fmt == 0) return fail(BB_ERR_UNSUPPORTED_FORMAT, "unsupported sample format");
+    if (first_frame > info->frames || frames > info->frames - first_frame) return fail(BB_ERR_INVALID_ARG, "frame range outside the data chunk");
+    const uint64_t fb = (uint64_t)info->channels * (info->fmt == BB_S16 ? 2 : 4);
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return fail(BB_ERR_IO, std::string("cannot open ") + path);
+    uint64_t off = info->data_offset + first_frame * fb, left = frames * fb;
+    char* p = static_cast<char*>(dst);
+    while (left) {
+        const ssize_t n = ::pread(fd, p, left > (1u << 30) ? (1u << 30) : (size_t)left, (off_t)off);
+        if (n <= 0) { ::close(fd); return fail(BB_ERR_IO, std::string("short read from ") + path); }
+        p += n; off += (uint64_t)n; left -= (uint64_t)n;
+    }
+    ::close(fd);
+    return BB_OK;
+}
+
+}  // extern "C"

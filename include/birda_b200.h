@@ -47,7 +47,8 @@ typedef enum {
     BB_ERR_OOM                = -6,
     BB_ERR_INTERNAL           = -7,  /* -> Error::Internal { message }                        */
     BB_ERR_NO_DEVICE          = -8,
-    BB_ERR_CAPACITY           = -9   /* caller-provided output array too small                */
+    BB_ERR_CAPACITY           = -9,  /* caller-provided output array too small                */
+    BB_ERR_IO                 = -10  /* -> Error::AudioOpen / Error::AudioDecode              */
 } bb_status;
 
 /* interleaved frames, native endian; the formats src/audio/decode.rs:353-411 converts */
@@ -206,6 +207,23 @@ int32_t bb_post_run_device(bb_ctx*, const float* d_scores, uint32_t B, uint32_t 
 int32_t bb_post_run(bb_ctx*, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B,
                     const bb_post_cfg*, const float* d_mask, const uint8_t* d_species_keep,
                     uint32_t* h_index, float* h_conf, uint32_t* h_count);
+
+/* ------------------------------------------------------------------------------------------
+ * PCM ingest: WAV / RF64 files are already the interleaved layout the kernels
+ * consume.  Replaces StreamingDecoder::open + the symphonia packet loop for PCM WAV
+ * (src/audio/decode.rs:54-128, :205-245): probe once, then read frame ranges straight into a staging
+ * buffer (bb_host_alloc) and hand it to bb_frontend_run.  Pure host code.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t sample_rate;
+    uint32_t channels;
+    uint32_t bits_per_sample;
+    int32_t  fmt;            /* bb_sample_fmt, 0 = a format the reference does not convert           */
+    uint64_t frames;
+    uint64_t data_offset;    /* byte offset of the first sample in the file                           */
+} bb_wav_info;
+int32_t bb_wav_probe(const char* path, bb_wav_info* out);
+int32_t bb_wav_read(const char* path, const bb_wav_info* info, uint64_t first_frame, uint64_t frames, void* dst);
 
 /* Device memory helpers for hosts without a CUDA binding of their own (tests, Rust shim) */
 int32_t bb_dev_alloc(bb_ctx*, uint64_t bytes, void** out);
