@@ -3,8 +3,8 @@
 # usage: tools/gpu_profile_round.sh TAG
 TAG=${1:-r01}
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:resample_warp -s 2 -c 1 -f -o gpurun_out/${TAG}_k2_c2_1h python tools/prof_run.py 60 2 c2 > gpurun_out/${TAG}_ncu_k2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:resample_ -s 2 -c 1 -f -o gpurun_out/${TAG}_k2_c2_1h python tools/prof_run.py 60 2 c2 > gpurun_out/${TAG}_ncu_k2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pack_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_k1_c4 python tools/prof_run.py 20 2 c4 > gpurun_out/${TAG}_ncu_k1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:post_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_k3_c2 python tools/prof_run.py 60 2 c2 > gpurun_out/${TAG}_ncu_k3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:post_kernel -s 1 -c 1 -f -o gpurun_out/${TAG}_k3_c2 python tools/prof_run.py 60 2 c2 > gpurun_out/${TAG}_ncu_k3.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"resample|pack_kernel|post_kernel" -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_k2.log gpurun_out/${TAG}_ncu_k1.log gpurun_out/${TAG}_ncu_k3.log
