@@ -1,0 +1,109 @@
+"""Full BASELINE.json sizes on the GPU: spot rows against the oracle plus size-independent properties."""
+import numpy as np
+import pytest
+
+import birda_b200 as b
+from birda_b200.pipeline import FilePipeline, ProcessingConfig
+from birda_b200.shard import shard_files
+from birda_b200.synth import synth_pcm
+from oracle import frontend as ofe
+from oracle import rules as orules
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, ref):
+    rms = np.sqrt(np.mean(ref.astype(np.float64) ** 2, axis=1, keepdims=True))
+    return float((np.abs(got.astype(np.float64) - ref) / np.maximum(np.abs(ref), np.maximum(rms, 1e-30))).max())
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b.Context(0)
+    yield c
+    c.close()
+
+
+def test_c2_full_hour_spot_rows_and_tables(ctx):
+    """C2: 1 h 44.1 kHz stereo, overlap 1.5 s, batch 64 -> 2400 windows (+32 padding rows).  All tables
+    bit-exact; 24 rows spread over the hour (first, last, tail, pair boundaries) within 1e-5."""
+    import torch
+    sec = 3600
+    base = synth_pcm(2, 60.0, 44_100, 2).reshape(-1, 2)
+    pcm = np.tile(base, (sec // 60, 1))
+    pcm[:: 9973, 0] += 17                                    # break the exact periodicity
+    pcm = np.ascontiguousarray(pcm).reshape(-1)
+    plan = b.FrontEndPlan(ctx, 44_100, 2, b.FMT_S16, 48_000, 144_000, 72_000)
+    res = plan.run(pcm, pad_to_batch=64); ctx.sync()
+    assert (res.nseg, res.rows) == (2400, 2432)
+    rows = sorted(set([0, 1, 2, 3, 62, 63, 64, 65, 777, 1200, 1201, 2000, 2396, 2397, 2398, 2399]))
+    ref = ofe.decode_and_stream(pcm, 2, 44_100, 48_000, 144_000, 72_000, precision="f64", only=rows)
+    assert np.array_equal(res.start_sample, ref.start_sample)
+    assert res.start_time.tobytes() == ref.start_time.tobytes() and res.end_time.tobytes() == ref.end_time.tobytes()
+    out = res.torch()
+    got = out[torch.tensor(rows, device=out.device)].cpu().numpy()
+    assert rel_err(got, ref.segments[rows].astype(np.float64)) <= 1e-5
+    assert not bool(out[2400:].any())                        # batch padding is silence
+    tail = out[2399].cpu().numpy()
+    assert not tail[72_000 + 2_000:].any() and tail[:70_000].any()   # half-filled last window, zero padded
+    plan.close()
+
+
+def test_c3_full_hour_perch_spot_rows(ctx):
+    """C3: 1 h 48 kHz mono -> 32 kHz, 5 s windows, batch 128 -> 720 windows."""
+    import torch
+    base = synth_pcm(3, 60.0, 48_000, 1)
+    pcm = np.tile(base, 60); pcm[:: 7919] += 11
+    plan = b.FrontEndPlan(ctx, 48_000, 1, b.FMT_S16, 32_000, 160_000, 0)
+    res = plan.run(pcm, pad_to_batch=128); ctx.sync()
+    assert (res.nseg, res.rows) == (720, 768)
+    rows = [0, 1, 127, 128, 360, 719]
+    ref = ofe.decode_and_stream(pcm, 1, 48_000, 32_000, 160_000, 0, precision="f64", only=rows)
+    assert np.array_equal(res.start_sample, ref.start_sample) and res.end_time.tobytes() == ref.end_time.tobytes()
+    out = res.torch()
+    assert rel_err(out[torch.tensor(rows, device=out.device)].cpu().numpy(), ref.segments[rows].astype(np.float64)) <= 1e-5
+    plan.close()
+
+
+def test_c4_bat_hour_checksum_property(ctx):
+    """C4: 1 h 256 kHz mono bat mode -> 8534 windows of 144000 (overlap 36000), no resampling.  Bit-exact
+    property at full size: every window equals the converted PCM slice, checked through per-row sums of the
+    exact integer samples (an f64 checksum of checksums) and 12 rows compared element-wise."""
+    import torch
+    n = 3600 * 256_000
+    base = synth_pcm(4, 30.0, 256_000, 1, bat=True)
+    pcm = np.tile(base, 120)[:n].copy(); pcm[:: 10007] -= 5
+    seg, ovl = b.rules.segment_samples(0.5625, 0.0, 256_000, bat_mode=True)
+    plan = b.FrontEndPlan(ctx, 256_000, 1, b.FMT_S16, 256_000, seg, ovl)
+    res = plan.run(pcm); ctx.sync()
+    assert res.nseg == 8534
+    out = res.torch()
+    st, tk = b.rules.segment_table(n, seg, ovl)
+    assert np.array_equal(res.start_sample, st)
+    csum = np.concatenate([[0], np.cumsum(pcm.astype(np.int64))])
+    want = (csum[(st + tk).astype(np.int64)] - csum[st.astype(np.int64)]).astype(np.float64) / 32768.0
+    got = out.double().sum(dim=1).cpu().numpy()
+    assert np.array_equal(got, want)                          # sums of exactly representable values are exact in f64
+    for r in (0, 1, 4000, 8532, 8533):
+        ref = np.zeros(seg, np.float32); ref[: int(tk[r])] = pcm[int(st[r]): int(st[r] + tk[r])].astype(np.float32) / np.float32(32768.0)
+        assert np.array_equal(out[r].cpu().numpy(), ref)
+    plan.close()
+
+
+def test_c5_mixed_rate_directory_sharded(ctx):
+    """C5 (scaled down): files at mixed rates / channel counts, BirdNET windows, range mask; shard plan over 8
+    ranks covers every file once; every file's tables match the oracle and a sample row matches to 1e-5."""
+    rates = [16_000, 22_050, 32_000, 44_100, 48_000, 96_000]
+    files = [(1000 + i, rates[i % 6], 1 + (i % 2), 20.0 + 3.0 * (i % 4)) for i in range(12)]
+    shards = shard_files([f[3] for f in files], 8)
+    assert sorted(i for part in shards for i in part) == list(range(12))
+    for seed, sr, ch, dur in files:
+        pcm = synth_pcm(seed, dur, sr, ch)
+        plan = b.FrontEndPlan(ctx, sr, ch, b.FMT_S16, 48_000, 144_000, 0)
+        res = plan.run(pcm, pad_to_batch=8); ctx.sync()
+        row = [res.nseg // 2]
+        ref = ofe.decode_and_stream(pcm, ch, sr, 48_000, 144_000, 0, precision="f64", only=row)
+        assert res.nseg == ref.segments.shape[0] and np.array_equal(res.start_sample, ref.start_sample)
+        assert res.start_time.tobytes() == ref.start_time.tobytes()
+        assert rel_err(res.torch()[row[0]: row[0] + 1].cpu().numpy(), ref.segments[row].astype(np.float64)) <= 1e-5
+        plan.close()

@@ -75,3 +75,22 @@ def test_pipeline_matches_oracle(sr, channels, overlap, batch, rerank):
     st = [d.start_time for d in res.detections]
     assert st == sorted(st) and len(want) > 10
     pipe.close(); ctx.close()
+
+
+def test_pipeline_bat_mode_no_resample():
+    """Bat mode: 256 kHz fed raw, 144000-sample windows with 36000 overlap whatever --overlap says
+    (src/pipeline/processor.rs:461-475, :502-508); the estimate still uses the user's overlap."""
+    import torch
+    ctx = b.Context(0)
+    clf = StandInClassifier(144_000, 300, seed=3)
+    cfg = ProcessingConfig(bat_mode=True, overlap=0.0, batch_size=32, min_confidence=0.05)
+    pipe = FilePipeline(ctx, cfg, clf)
+    pcm = synth_pcm(12, 4.1, 256_000, 1, bat=True)
+    res = pipe.process_pcm(pcm, 1, 256_000, b.FMT_S16)
+    ref = ofe.decode_and_stream(pcm, 1, 256_000, 256_000, 144_000, 36_000)
+    assert res.segments == ref.segments.shape[0]
+    est = orules.estimate_segment_count(pcm.size / 256_000, float(orules.BAT_SEGMENT_DURATION), 0.0)
+    assert res.effective_batch_size == orules.effective_batch_size(32, est)
+    ends = sorted({round(d.end_time - d.start_time, 6) for d in res.detections})
+    assert ends == [0.5625] or not res.detections
+    pipe.close(); ctx.close()
