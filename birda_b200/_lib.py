@@ -38,6 +38,20 @@ class PostCfg(C.Structure):
                 ("range_threshold", C.c_float), ("keep_unmatched", C.c_int32), ("rerank", C.c_int32)]
 
 
+class PipelineCfg(C.Structure):
+    _fields_ = [("target_rate", C.c_uint32), ("segment_duration", C.c_float), ("overlap", C.c_float),
+                ("batch_size", C.c_uint32), ("bat_mode", C.c_int32), ("post", PostCfg),
+                ("d_mask", C.c_void_p), ("d_species_keep", C.c_void_p)]
+
+
+class DetectionC(C.Structure):
+    _fields_ = [("segment", C.c_uint32), ("index", C.c_uint32), ("confidence", C.c_float),
+                ("start_time", C.c_float), ("end_time", C.c_float)]
+
+
+CLASSIFY_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32))
+
+
 # name -> (restype, argtypes).  tests/test_abi.py checks this list against include/birda_b200.h.
 SIGNATURES = {
     "bb_rule_segment_samples": (C.c_int32, [C.c_float, C.c_float, C.c_uint32, C.c_int32, u64p, u64p]),
@@ -74,6 +88,12 @@ SIGNATURES = {
     "bb_post_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostCfg), vp, vp, u32p, f32p, u32p]),
     "bb_wav_probe": (C.c_int32, [C.c_char_p, C.POINTER(WavInfo)]),
     "bb_wav_read": (C.c_int32, [C.c_char_p, C.POINTER(WavInfo), C.c_uint64, C.c_uint64, vp]),
+    "bb_pipeline_create": (C.c_int32, [vp, C.POINTER(PipelineCfg), CLASSIFY_FN, vp, C.POINTER(vp)]),
+    "bb_pipeline_destroy": (None, [vp]),
+    "bb_pipeline_last_error": (C.c_char_p, [vp]),
+    "bb_pipeline_process_pcm": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(DetectionC),
+                                            C.c_uint64, u64p, u64p, u32p]),
+    "bb_pipeline_process_wav": (C.c_int32, [vp, C.c_char_p, C.c_uint64, C.POINTER(DetectionC), C.c_uint64, u64p, u64p, u32p]),
     "bb_dev_alloc": (C.c_int32, [vp, C.c_uint64, C.POINTER(vp)]),
     "bb_dev_free": (None, [vp, vp]),
     "bb_memcpy_h2d": (C.c_int32, [vp, vp, vp, C.c_uint64]),

@@ -1,0 +1,203 @@
+// Host pipeline over the C ABI (product code, C++): the per-file loop of the reference with the front
+// end and the post step on the GPU and the classifier as a callback (ONNX Runtime with IoBinding in
+// birda; any device function in tests).
+//
+// Follows process_file / run_streaming_inference / process_batch
+// (src/pipeline/processor.rs:418-796, :114-190, :220-410):
+//   estimate_segment_count -> effective batch size (:525-545) -> front end over the file in pieces ->
+//   batches of `batch` rows, the last one padded with silence (:239-260) -> classifier -> post step on
+//   the valid rows (:317, :363-385) -> detections sorted by (start_time asc, confidence desc) (:178-187).
+#include "../../include/birda_b200.h"
+#include "rules.hpp"
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace bb { void set_tls_error(const std::string& m); }
+
+struct bb_pipeline {
+    bb_ctx* ctx = nullptr;
+    bb_pipeline_cfg cfg{};
+    bb_classify_fn classify = nullptr;
+    void* user = nullptr;
+    bb_plan* plan = nullptr;
+    uint32_t plan_rate = 0, plan_channels = 0; int plan_fmt = 0;
+    void* pinned = nullptr; uint64_t pinned_bytes = 0;
+    std::vector<uint32_t> h_index; std::vector<float> h_conf; std::vector<uint32_t> h_count;
+    std::vector<float> st, et; std::vector<uint64_t> ss;
+    std::string error;
+};
+
+namespace {
+
+int fail(bb_pipeline* p, int code, const std::string& m) { if (p) p->error = m; bb::set_tls_error(m); return code; }
+
+int ensure_plan(bb_pipeline* p, uint32_t rate, uint32_t channels, int fmt) {
+    if (p->plan && p->plan_rate == rate && p->plan_channels == channels && p->plan_fmt == fmt) return BB_OK;
+    if (p->plan) { bb_plan_destroy(p->plan); p->plan = nullptr; }
+    const uint32_t target = p->cfg.bat_mode ? rate : p->cfg.target_rate;            // processor.rs:464-475
+    uint64_t seg = 0, ovl = 0;
+    bb_rule_segment_samples(p->cfg.segment_duration, p->cfg.overlap, target, p->cfg.bat_mode, &seg, &ovl);
+    int rc = bb_plan_create(p->ctx, rate, channels, (bb_sample_fmt)fmt, target, seg, ovl, &p->plan);
+    if (rc != BB_OK) return fail(p, rc, bb_last_error(p->ctx));
+    p->plan_rate = rate; p->plan_channels = channels; p->plan_fmt = fmt;
+    return BB_OK;
+}
+
+struct Sink { bb_detection* out; uint64_t cap; uint64_t n; bool overflow; };
+
+// one piece of PCM already in host memory -> detections appended to the sink
+int run_piece(bb_pipeline* p, const void* pcm, uint64_t frames, uint64_t first_start, bool eof, uint32_t B,
+              uint64_t seg_base, Sink* sink, uint64_t* nseg_out, uint64_t* consumed) {
+    uint64_t src_seg = 0, src_ovl = 0, nmax = 0;
+    bb_plan_source_window(p->plan, &src_seg, &src_ovl);
+    bb_rule_segment_count(frames, src_seg, src_ovl, &nmax);
+    const uint64_t cap = (nmax / B + 1) * B;
+    p->st.resize(cap); p->et.resize(cap); p->ss.resize(cap);
+    float* d_seg = nullptr; uint64_t nseg = 0, rows = 0;
+    int rc = bb_frontend_run(p->plan, pcm, frames, 0, first_start, eof ? 1 : 0, B, nullptr, cap, &d_seg, p->ss.data(),
+                             p->st.data(), p->et.data(), &nseg, &rows, consumed);
+    if (rc != BB_OK) return fail(p, rc, bb_last_error(p->ctx));
+    *nseg_out = nseg;
+    uint64_t seg_samples = 0, dummy = 0;
+    bb_rule_segment_samples(p->cfg.segment_duration, p->cfg.overlap, p->cfg.bat_mode ? p->plan_rate : p->cfg.target_rate,
+                            p->cfg.bat_mode, &seg_samples, &dummy);
+    const uint32_t K = p->cfg.post.top_k;
+    p->h_index.resize((size_t)B * K); p->h_conf.resize((size_t)B * K); p->h_count.resize(B);
+    for (uint64_t first = 0; first < nseg; first += B) {
+        const uint32_t valid = (uint32_t)std::min<uint64_t>(B, nseg - first);
+        const float* d_scores = nullptr; uint32_t classes = 0;
+        rc = p->classify(p->user, d_seg + first * seg_samples, B, (uint32_t)seg_samples, &d_scores, &classes);
+        if (rc != 0 || !d_scores || classes == 0) return fail(p, BB_ERR_INTERNAL, "classifier callback failed");   // Error::Inference
+        rc = bb_post_run(p->ctx, d_scores, B, classes, valid, &p->cfg.post, p->cfg.d_mask, p->cfg.d_species_keep,
+                         p->h_index.data(), p->h_conf.data(), p->h_count.data());
+        if (rc != BB_OK) return fail(p, rc, bb_last_error(p->ctx));
+        for (uint32_t r = 0; r < valid; ++r)                                       // processor.rs:363-385
+            for (uint32_t j = 0; j < p->h_count[r]; ++j) {
+                const float c = p->h_conf[(size_t)r * K + j];
+                if (!(c >= p->cfg.post.min_confidence)) continue;
+                if (sink->n < sink->cap) {
+                    bb_detection& d = sink->out[sink->n];
+                    d.segment = (uint32_t)(seg_base + first + r); d.index = p->h_index[(size_t)r * K + j]; d.confidence = c;
+                    d.start_time = p->st[first + r]; d.end_time = p->et[first + r];
+                } else sink->overflow = true;
+                ++sink->n;
+            }
+    }
+    return BB_OK;
+}
+
+void sort_detections(bb_detection* d, uint64_t n) {                                 // processor.rs:178-187
+    std::stable_sort(d, d + n, [](const bb_detection& a, const bb_detection& b) {
+        if (a.start_time != b.start_time) return a.start_time < b.start_time;
+        return a.confidence > b.confidence;
+    });
+}
+
+uint32_t effective_batch(const bb_pipeline* p, uint64_t frames, uint32_t rate) {
+    const float seg_dur = p->cfg.bat_mode ? (float)144000 / (float)256000 : p->cfg.segment_duration;   // constants.rs:535
+    int64_t est = -1;
+    bb_rule_estimate_segment_count((double)frames / (double)rate, 1, seg_dur, p->cfg.overlap, &est);
+    uint32_t B = bb_rule_effective_batch_size(p->cfg.batch_size, est);
+    return B ? B : 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t bb_pipeline_create(bb_ctx* ctx, const bb_pipeline_cfg* cfg, bb_classify_fn fn, void* user, bb_pipeline** out) {
+    if (!ctx || !cfg || !fn || !out) return fail(nullptr, BB_ERR_INVALID_ARG, "null argument");
+    if (cfg->batch_size < 1 || cfg->batch_size > 512) return fail(nullptr, BB_ERR_INVALID_ARG, "batch_size must be in [1, 512] (constants.rs:44-55)");
+    if (cfg->post.top_k < 1 || cfg->post.top_k > BB_MAX_TOP_K) return fail(nullptr, BB_ERR_INVALID_ARG, "top_k out of range");
+    bb_pipeline* p = new (std::nothrow) bb_pipeline();
+    if (!p) return fail(nullptr, BB_ERR_OOM, "out of host memory");
+    p->ctx = ctx; p->cfg = *cfg; p->classify = fn; p->user = user;
+    *out = p;
+    return BB_OK;
+}
+
+void bb_pipeline_destroy(bb_pipeline* p) {
+    if (!p) return;
+    if (p->plan) bb_plan_destroy(p->plan);
+    if (p->pinned) bb_host_free(p->pinned);
+    delete p;
+}
+
+const char* bb_pipeline_last_error(const bb_pipeline* p) { return p ? p->error.c_str() : ""; }
+
+int32_t bb_pipeline_process_pcm(bb_pipeline* p, const void* pcm, uint64_t frames, uint32_t src_rate, uint32_t channels,
+                                int32_t fmt, bb_detection* out, uint64_t capacity, uint64_t* n_detections,
+                                uint64_t* n_segments, uint32_t* batch_used) {
+    if (!p || (!pcm && frames) || src_rate == 0) return fail(p, BB_ERR_INVALID_ARG, "bad argument");
+    int rc = ensure_plan(p, src_rate, channels, fmt);
+    if (rc != BB_OK) return rc;
+    const uint32_t B = effective_batch(p, frames, src_rate);
+    if (batch_used) *batch_used = B;
+    Sink sink{out, out ? capacity : 0, 0, false};
+    uint64_t nseg = 0, consumed = 0;
+    rc = run_piece(p, pcm, frames, 0, true, B, 0, &sink, &nseg, &consumed);
+    if (rc != BB_OK) return rc;
+    if (n_segments) *n_segments = nseg;
+    if (n_detections) *n_detections = sink.n;
+    if (sink.overflow) return fail(p, BB_ERR_CAPACITY, "detection capacity too small (" + std::to_string(sink.n) + " needed)");
+    sort_detections(out, sink.n);
+    return BB_OK;
+}
+
+int32_t bb_pipeline_process_wav(bb_pipeline* p, const char* path, uint64_t piece_frames, bb_detection* out, uint64_t capacity,
+                                uint64_t* n_detections, uint64_t* n_segments, uint32_t* batch_used) {
+    if (!p || !path) return fail(p, BB_ERR_INVALID_ARG, "bad argument");
+    bb_wav_info info;
+    int rc = bb_wav_probe(path, &info);
+    if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
+    rc = ensure_plan(p, info.sample_rate, info.channels, info.fmt);
+    if (rc != BB_OK) return rc;
+    const uint32_t B = effective_batch(p, info.frames, info.sample_rate);
+    if (batch_used) *batch_used = B;
+    const uint64_t fb = (uint64_t)info.channels * (info.fmt == BB_S16 ? 2 : 4);
+    uint64_t src_seg = 0, src_ovl = 0;
+    bb_plan_source_window(p->plan, &src_seg, &src_ovl);
+    if (piece_frames == 0) piece_frames = (256ull << 20) / fb;                     // ~256 MB of PCM per piece
+    if (piece_frames < 2 * src_seg) piece_frames = 2 * src_seg;
+    // keep the number of windows per non-final piece a multiple of the batch so only the file's LAST batch is padded
+    const uint64_t hop = src_seg - src_ovl;
+    Sink sink{out, out ? capacity : 0, 0, false};
+    uint64_t pos = 0, seg_base = 0;
+    while (true) {
+        uint64_t want = std::min<uint64_t>(piece_frames, info.frames - pos);
+        bool eof = pos + want >= info.frames;
+        if (!eof) {                                                                // trim to k*B full windows
+            uint64_t nfull = want >= src_seg ? (want - src_seg) / hop + 1 : 0;
+            nfull = nfull / B * B;
+            if (nfull == 0) { want = std::min<uint64_t>(info.frames - pos, src_seg + (uint64_t)B * hop); eof = pos + want >= info.frames; }
+            else want = (nfull - 1) * hop + src_seg;
+        }
+        if (p->pinned_bytes < want * fb) {
+            bb_sync(p->ctx);
+            if (p->pinned) bb_host_free(p->pinned);
+            p->pinned = nullptr; p->pinned_bytes = 0;
+            if (bb_host_alloc(want * fb > 0 ? want * fb : 1, &p->pinned) != BB_OK) return fail(p, BB_ERR_OOM, "pinned staging allocation failed");
+            p->pinned_bytes = want * fb;
+        }
+        bb_sync(p->ctx);                                                            // previous piece's H2D copies are done
+        rc = bb_wav_read(path, &info, pos, want, p->pinned);
+        if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
+        uint64_t nseg = 0, consumed = 0;
+        rc = run_piece(p, p->pinned, want, pos, eof, B, seg_base, &sink, &nseg, &consumed);
+        if (rc != BB_OK) return rc;
+        seg_base += nseg;
+        if (eof) break;
+        if (consumed == 0) return fail(p, BB_ERR_INTERNAL, "streaming made no progress");
+        pos += consumed;
+    }
+    if (n_segments) *n_segments = seg_base;
+    if (n_detections) *n_detections = sink.n;
+    if (sink.overflow) return fail(p, BB_ERR_CAPACITY, "detection capacity too small (" + std::to_string(sink.n) + " needed)");
+    sort_detections(out, sink.n);
+    return BB_OK;
+}
+
+}  // extern "C"

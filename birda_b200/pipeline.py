@@ -125,3 +125,100 @@ class FilePipeline:
 def rules_bat_duration() -> np.float32:
     """bat::SEGMENT_DURATION = 144000 / 256000 as f32 (src/constants.rs:525-535)."""
     return np.float32(144_000) / np.float32(256_000)
+
+
+class _DevView:
+    """__cuda_array_interface__ view of a device pointer (for torch.as_tensor)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+
+class NativePipeline:
+    """The C++ per-file pipeline of the library (csrc/pipeline.cpp: bb_pipeline_*) with a Python classifier
+    callback.  Same contract as FilePipeline; detections come back as Detection objects."""
+
+    def __init__(self, ctx: Context, cfg: ProcessingConfig, classifier: Callable):
+        import ctypes as C
+
+        from . import _lib
+        self.ctx, self.cfg, self.classifier = ctx, cfg, classifier
+        self._scores = None
+        self._error = None
+
+        def _cb(user, d_segments, rows, samples, d_scores, classes):
+            try:
+                import torch
+                x = torch.as_tensor(_DevView(d_segments, (rows, samples)), device=f"cuda:{ctx.device}")
+                s = self.classifier(x).contiguous().float()
+                self._scores = s                       # keep alive until the next call
+                d_scores[0] = s.data_ptr()
+                classes[0] = int(s.shape[1])
+                torch.cuda.current_stream().synchronize() if ctx_stream_differs(ctx) else None
+                return 0
+            except Exception as e:                      # never let an exception cross the C boundary
+                self._error = e
+                return 1
+
+        self._cb = _lib.CLASSIFY_FN(_cb)
+        c = _lib.PipelineCfg(cfg.target_rate, cfg.segment_duration, cfg.overlap, cfg.batch_size, int(cfg.bat_mode),
+                             PostConfig(cfg.activation, cfg.min_confidence, cfg.top_k, cfg.range_threshold,
+                                        cfg.keep_unmatched, cfg.rerank).to_c(), cfg.d_mask, cfg.d_species_keep)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib.bb_pipeline_create(ctx.handle, C.byref(c), self._cb, None, C.byref(self._h)), ctx.handle)
+
+    def _collect(self, call) -> ProcessResult:
+        import ctypes as C
+
+        from . import _lib
+        cap = 1 << 16
+        while True:
+            buf = (_lib.DetectionC * cap)()
+            nd, ns, bu = C.c_uint64(), C.c_uint64(), C.c_uint32()
+            rc = call(buf, cap, C.byref(nd), C.byref(ns), C.byref(bu))
+            if rc == -9 and nd.value > cap:             # BB_ERR_CAPACITY: retry with the reported size
+                cap = int(nd.value)
+                continue
+            if rc != 0:
+                msg = _lib.lib.bb_pipeline_last_error(self._h).decode("utf-8", "replace")
+                if self._error is not None:
+                    raise self._error
+                raise _lib.BirdaError(rc, msg)
+            break
+        res = ProcessResult(segments=int(ns.value), effective_batch_size=int(bu.value))
+        labels = self.cfg.labels
+        for i in range(int(nd.value)):
+            d = buf[i]
+            sci, com = split_label(labels[d.index]) if labels is not None else (str(d.index), str(d.index))
+            res.detections.append(Detection(sci, com, float(d.confidence), float(d.start_time), float(d.end_time), int(d.index), int(d.segment)))
+        res.batches = -(-res.segments // max(res.effective_batch_size, 1))
+        return res
+
+    def process_pcm(self, pcm: np.ndarray, channels: int, source_rate: int, fmt: int) -> ProcessResult:
+        import ctypes as C
+
+        from . import _lib
+        pcm = np.ascontiguousarray(pcm)
+        frames = pcm.size // channels
+        return self._collect(lambda buf, cap, nd, ns, bu: _lib.lib.bb_pipeline_process_pcm(
+            self._h, C.c_void_p(pcm.ctypes.data), frames, source_rate, channels, fmt, buf, cap, nd, ns, bu))
+
+    def process_wav(self, path: str, piece_frames: int = 0) -> ProcessResult:
+        from . import _lib
+        return self._collect(lambda buf, cap, nd, ns, bu: _lib.lib.bb_pipeline_process_wav(
+            self._h, path.encode(), piece_frames, buf, cap, nd, ns, bu))
+
+    def close(self):
+        from . import _lib
+        if self._h:
+            _lib.lib.bb_pipeline_destroy(self._h)
+            self._h = None
+
+
+def ctx_stream_differs(ctx: Context) -> bool:
+    """True when the context runs on its own stream: the classifier's torch work (current stream) must be
+    finished before the library's post kernel reads the scores."""
+    import torch
+
+    from . import _lib
+    return int(_lib.lib.bb_ctx_stream(ctx.handle) or 0) != int(torch.cuda.current_stream().cuda_stream)

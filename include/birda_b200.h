@@ -225,6 +225,46 @@ typedef struct {
 int32_t bb_wav_probe(const char* path, bb_wav_info* out);
 int32_t bb_wav_read(const char* path, const bb_wav_info* info, uint64_t first_frame, uint64_t frames, void* dst);
 
+/* ------------------------------------------------------------------------------------------
+ * Per-file pipeline (C++ host code in the library): the reference's process_file loop
+ * (src/pipeline/processor.rs:418-796) with the front end and the post step on the GPU and the
+ * classifier as a callback.  In birda the callback is BirdClassifier::predict_batch_device (ONNX
+ * Runtime with IoBinding on the ctx stream); it must leave `*d_scores` = device [batch_rows, classes]
+ * f32 valid until the next call.  Return 0 on success (anything else -> BB_ERR_INTERNAL, as
+ * Error::Inference).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bb_pipeline bb_pipeline;
+typedef int32_t (*bb_classify_fn)(void* user, const float* d_segments, uint32_t batch_rows, uint32_t samples,
+                                  const float** d_scores, uint32_t* classes);
+typedef struct {
+    uint32_t    target_rate;        /* classifier.sample_rate()                                       */
+    float       segment_duration;   /* classifier.segment_duration()                                  */
+    float       overlap;            /* --overlap (src/constants.rs:28)                                */
+    uint32_t    batch_size;         /* --batch-size, 1..512 (src/constants.rs:44-55)                  */
+    int32_t     bat_mode;           /* src/pipeline/processor.rs:461-475                              */
+    bb_post_cfg post;
+    const float*   d_mask;          /* device [C] f32 or NULL                                         */
+    const uint8_t* d_species_keep;  /* device [C] u8 or NULL                                          */
+} bb_pipeline_cfg;
+typedef struct {                    /* Detection fields the writers need (src/output/types.rs:8-23)   */
+    uint32_t segment;               /* window index inside the file                                   */
+    uint32_t index;                 /* class index -> label -> Detection::from_label                  */
+    float    confidence;
+    float    start_time;
+    float    end_time;
+} bb_detection;
+int32_t     bb_pipeline_create(bb_ctx*, const bb_pipeline_cfg*, bb_classify_fn, void* user, bb_pipeline** out);
+void        bb_pipeline_destroy(bb_pipeline*);
+const char* bb_pipeline_last_error(const bb_pipeline*);
+/* Whole decoded file in host memory.  Detections come back sorted (start_time asc, confidence desc:
+ * processor.rs:178-187); BB_ERR_CAPACITY reports the needed count in *n_detections. */
+int32_t bb_pipeline_process_pcm(bb_pipeline*, const void* pcm, uint64_t frames, uint32_t src_rate, uint32_t channels,
+                                int32_t fmt, bb_detection* out, uint64_t capacity, uint64_t* n_detections,
+                                uint64_t* n_segments, uint32_t* batch_used);
+/* WAV / RF64 file streamed through a pinned staging buffer in pieces of ~piece_frames (0 = default). */
+int32_t bb_pipeline_process_wav(bb_pipeline*, const char* path, uint64_t piece_frames, bb_detection* out, uint64_t capacity,
+                                uint64_t* n_detections, uint64_t* n_segments, uint32_t* batch_used);
+
 /* Device memory helpers for hosts without a CUDA binding of their own (tests, Rust shim) */
 int32_t bb_dev_alloc(bb_ctx*, uint64_t bytes, void** out);
 void    bb_dev_free(bb_ctx*, void*);
