@@ -597,8 +597,8 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     if (groups > max_threads / 32) groups = max_threads / 32;
     int gw = (max_threads / 32) / groups;               // warps cooperating on one block (pair)
     if (gw < 1) gw = 1;
-    if (gw > 4) gw = 4;
-    if (const char* g = std::getenv("BIRDA_K2_GROUP_WARPS")) { int v = atoi(g); if (v >= 1 && v <= 4 && v * groups * 32 <= max_threads) gw = v; }
+    if (gw > 6) gw = 6;
+    if (const char* g = std::getenv("BIRDA_K2_GROUP_WARPS")) { int v = atoi(g); if (v >= 1 && v <= 6 && v * groups * 32 <= max_threads) gw = v; }
     P.groups = groups; P.gw = gw;
     const size_t smem = P.tables + (size_t)groups * P.per_group;
     const uint64_t units = dual ? (rows_total + 1) / 2 : rows_total;      // rows or row pairs

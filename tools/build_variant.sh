@@ -11,6 +11,8 @@ for f in capi k1_pack k2_resample k2_warp k3_post; do
   fi
 done
 g++ -O2 -std=c++17 -fPIC -fno-fast-math -ffp-contract=off -c rules.cpp -o $D/rules.o
+g++ -O2 -std=c++17 -fPIC -c wav.cpp -o $D/wav.o
+g++ -O2 -std=c++17 -fPIC -fno-fast-math -c pipeline.cpp -o $D/pipeline.o
 wait
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $ROOT/birda_b200/variants/libbirda_b200_$1.so $D/*.o -cudart static
 grep "Used" $D/k2_warp.log | tail -1
