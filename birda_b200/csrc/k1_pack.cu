@@ -16,7 +16,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kUnroll  = 4;                       // float4 stores per thread per tile
-constexpr int kTile    = kThreads * kUnroll * 4;  // output floats per tile
+constexpr int kSub     = kThreads * kUnroll * 4;  // output floats per pass of the general path
+constexpr int kTile    = kSub * 2;                // output floats per tile
 
 template <int FMT> struct SampleT;
 template <> struct SampleT<BB_S16> { using type = int16_t; };
@@ -66,6 +67,19 @@ __device__ __forceinline__ float4 load4_aligned(const S* __restrict__ p) {
     return o;
 }
 
+// 16 bytes of interleaved PCM -> E = 16 / (CH * sizeof(S)) mono samples, reference operation order
+template <typename S, int CH> struct Slot16 {
+    static constexpr int E = 16 / (CH * (int)sizeof(S));
+    static __device__ __forceinline__ void convert(const int4& raw, float (&o)[E]) {
+        const S* s = reinterpret_cast<const S*>(&raw);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (CH == 1) o[e] = conv(s[e]);
+            else o[e] = __fdiv_rn(__fadd_rn(__fadd_rn(0.0f, conv(s[2 * e])), conv(s[2 * e + 1])), 2.0f);
+        }
+    }
+};
+
 // CH_T: 1 or 2 = compile-time channel count with vector loads; 0 = runtime channel count.
 template <int FMT, int CH_T>
 __global__ void __launch_bounds__(kThreads)
@@ -86,6 +100,44 @@ pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_fr
             take  = total_frames - start < seg ? total_frames - start : seg;
         }
         float* __restrict__ orow = out + row * seg;
+        if (CH_T != 0) {
+            // fast path: the whole tile lies inside the window's real samples and the window start is 16-byte
+            // aligned -> all loads of the tile are issued back to back (kUnroll x 16 B in flight per thread),
+            // no per-element control flow between a load and the next one
+            constexpr int ch = CH_T == 0 ? 1 : CH_T;
+            using SL = Slot16<S, ch>;
+            constexpr int E = SL::E;
+            constexpr int kPass = kThreads * kUnroll * E;         // floats per pass: kUnroll x 16 B loads in flight per thread
+            static_assert(kTile % kPass == 0, "tile must be a whole number of passes");
+            const bool aligned16 = ((reinterpret_cast<uintptr_t>(pcm) + start * ch * sizeof(S)) & 15) == 0 && (seg % E) == 0 &&
+                                   ((reinterpret_cast<uintptr_t>(orow) & 15) == 0);
+            if (aligned16 && j0 + kTile <= take) {
+#pragma unroll 1
+                for (uint64_t jp = j0; jp < j0 + kTile; jp += kPass) {
+                    int4 raw[kUnroll];
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) {
+                        const uint64_t j = jp + ((uint64_t)u * kThreads + threadIdx.x) * E;
+                        raw[u] = __ldg(reinterpret_cast<const int4*>(pcm + (start + j) * ch));
+                    }
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) {
+                        const uint64_t j = jp + ((uint64_t)u * kThreads + threadIdx.x) * E;
+                        float o[E];
+                        SL::convert(raw[u], o);
+                        if (E >= 4) {
+#pragma unroll
+                            for (int e = 0; e < E; e += 4) __stcs(reinterpret_cast<float4*>(orow + j + e), make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
+                        } else {
+                            __stcs(reinterpret_cast<float2*>(orow + j), make_float2(o[0], o[1]));
+                        }
+                    }
+                }
+                continue;
+            }
+        }
+        for (uint64_t js = j0; js < j0 + kTile; js += kSub) {
+        if (js >= seg) break;
         if (row_vec) {
             bool in_vec = false;
             if (CH_T != 0) {
@@ -96,12 +148,18 @@ pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_fr
             float4 v[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const uint64_t j = j0 + ((uint64_t)u * kThreads + threadIdx.x) * 4;
+                const uint64_t j = js + ((uint64_t)u * kThreads + threadIdx.x) * 4;
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (j < seg) {
+#ifdef BB_K1_NOLOAD
+                    if (true) { v[u] = make_float4((float)j, 0.f, 0.f, 0.f);
+#else
                     if (CH_T != 0 && in_vec && j + 4 <= take) {
+#endif
+#ifndef BB_K1_NOLOAD
                         constexpr int ch = CH_T == 0 ? 1 : CH_T;
                         v[u] = load4_aligned<S, ch>(pcm + (start + j) * ch);
+#endif
                     } else {
                         float t[4];
 #pragma unroll
@@ -117,11 +175,12 @@ pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_fr
                 if (j < seg) *reinterpret_cast<float4*>(orow + j) = v[u];
             }
         } else {
-            for (uint32_t e = threadIdx.x; e < (uint32_t)kTile; e += kThreads) {
-                const uint64_t j = j0 + e;
+            for (uint32_t e = threadIdx.x; e < (uint32_t)kSub; e += kThreads) {
+                const uint64_t j = js + e;
                 if (j < seg)
                     orow[j] = (j < take) ? downmix_frame(pcm + (start + j) * channels, channels, fch) : 0.0f;
             }
+        }
         }
     }
 }
