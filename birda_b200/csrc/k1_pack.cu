@@ -171,8 +171,8 @@ pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_fr
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const uint64_t j = j0 + ((uint64_t)u * kThreads + threadIdx.x) * 4;
-                if (j < seg) *reinterpret_cast<float4*>(orow + j) = v[u];
+                const uint64_t j = js + ((uint64_t)u * kThreads + threadIdx.x) * 4;
+                if (j < seg) __stcs(reinterpret_cast<float4*>(orow + j), v[u]);
             }
         } else {
             for (uint32_t e = threadIdx.x; e < (uint32_t)kSub; e += kThreads) {
