@@ -94,6 +94,7 @@ SIGNATURES = {
     "bb_pipeline_process_pcm": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(DetectionC),
                                             C.c_uint64, u64p, u64p, u32p]),
     "bb_pipeline_process_wav": (C.c_int32, [vp, C.c_char_p, C.c_uint64, C.POINTER(DetectionC), C.c_uint64, u64p, u64p, u32p]),
+    "bb_dense_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_int32, vp]),
     "bb_dev_alloc": (C.c_int32, [vp, C.c_uint64, C.POINTER(vp)]),
     "bb_dev_free": (None, [vp, vp]),
     "bb_memcpy_h2d": (C.c_int32, [vp, vp, vp, C.c_uint64]),

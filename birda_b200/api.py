@@ -168,6 +168,11 @@ class Context:
               self._h)
         return idx[:valid_B], conf[:valid_B], cnt[:valid_B]
 
+    def dense_run(self, d_x: int, B: int, K: int, d_W: int, d_b: Optional[int], N: int, activation: int, d_out: int):
+        """out[B,N] = act(x[B,K] W[K,N] + b[N]) on the device (geomodel forward, bat head)."""
+        check(lib.bb_dense_run(self._h, C.c_void_p(d_x), B, K, C.c_void_p(d_W), C.c_void_p(d_b) if d_b else None, N,
+                               activation, C.c_void_p(d_out)), self._h)
+
     def post_run_device(self, d_scores: int, B: int, Cc: int, valid_B: int, cfg: "PostConfig",
                         d_mask: Optional[int], d_species_keep: Optional[int], d_index: int, d_conf: int, d_count: int):
         c = cfg.to_c()

@@ -418,4 +418,18 @@ int32_t bb_post_run(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t C, ui
     return BB_OK;
 }
 
+// ------------------------------------------------------------------------------------ dense heads
+int32_t bb_dense_run(bb_ctx* c, const float* d_x, uint32_t B, uint32_t K, const float* d_W, const float* d_b, uint32_t N,
+                     int32_t activation, float* d_out) {
+    if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
+    if ((uint64_t)B * N == 0) return BB_OK;
+    if (!d_x || !d_W || !d_out || K == 0) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null argument");
+    if (activation < BB_ACT_NONE || activation > BB_ACT_SOFTMAX) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "unknown activation");
+    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    int n = 0;
+    BB_CUDA_OK(c, launch_dense(c->stream, d_x, B, K, d_W, d_b, N, activation, d_out, &n));
+    c->launches += n;
+    return BB_OK;
+}
+
 }  // extern "C"

@@ -94,6 +94,10 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
                                  uint64_t resampled_len, float* d_out, int* launches);
 void        resampler_dev_free(ResamplerDev* rs);
 
+// K4: tiny dense heads (geomodel forward, bat head).  k4_dense.cu
+cudaError_t launch_dense(cudaStream_t st, const float* d_x, uint32_t B, uint32_t K, const float* d_W, const float* d_b,
+                         uint32_t N, int activation, float* d_out, int* launches);
+
 // K3: activation + top-k + threshold + mask + threshold.  k3_post.cu
 cudaError_t launch_post(cudaStream_t st, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B,
                         const bb_post_cfg& cfg, const float* d_mask, const uint8_t* d_keep,

@@ -118,16 +118,30 @@ pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_fr
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u) {
                         const uint64_t j = jp + ((uint64_t)u * kThreads + threadIdx.x) * E;
+#ifdef BB_K1_LDCS
+                        raw[u] = __ldcs(reinterpret_cast<const int4*>(pcm + (start + j) * ch));
+#else
                         raw[u] = __ldg(reinterpret_cast<const int4*>(pcm + (start + j) * ch));
+#endif
                     }
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u) {
                         const uint64_t j = jp + ((uint64_t)u * kThreads + threadIdx.x) * E;
                         float o[E];
                         SL::convert(raw[u], o);
+#ifdef BB_K1_NOSTORE
+                        if (o[0] == 123.456f) orow[j] = o[1];       // experiment: loads only
+                        continue;
+#endif
                         if (E >= 4) {
 #pragma unroll
-                            for (int e = 0; e < E; e += 4) __stcs(reinterpret_cast<float4*>(orow + j + e), make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
+                            for (int e = 0; e < E; e += 4) {
+#if BB_K1_STREAM_STORE
+                                __stcs(reinterpret_cast<float4*>(orow + j + e), make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
+#else
+                                *reinterpret_cast<float4*>(orow + j + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+#endif
+                            }
                         } else {
                             __stcs(reinterpret_cast<float2*>(orow + j), make_float2(o[0], o[1]));
                         }

@@ -265,6 +265,15 @@ int32_t bb_pipeline_process_pcm(bb_pipeline*, const void* pcm, uint64_t frames, 
 int32_t bb_pipeline_process_wav(bb_pipeline*, const char* path, uint64_t piece_frames, bb_detection* out, uint64_t capacity,
                                 uint64_t* n_detections, uint64_t* n_segments, uint32_t* batch_used);
 
+/* ------------------------------------------------------------------------------------------
+ * Tiny dense heads on the device: out[B,N] = act(x[B,K] W[K,N] + b[N]), f32.
+ * The geomodel forward ([1,3] -> [1,12012] sigmoid, once per run: src/inference/classifier.rs:117-188,
+ * fixture tests/fixtures/make_fixture_geomodel.py:20-28) and the bat head over embeddings
+ * (src/pipeline/processor.rs:323-360) without a host hop.  b may be NULL.  Asynchronous on the ctx stream.
+ * ---------------------------------------------------------------------------------------- */
+int32_t bb_dense_run(bb_ctx*, const float* d_x, uint32_t B, uint32_t K, const float* d_W, const float* d_b, uint32_t N,
+                     int32_t activation, float* d_out);
+
 /* Device memory helpers for hosts without a CUDA binding of their own (tests, Rust shim) */
 int32_t bb_dev_alloc(bb_ctx*, uint64_t bytes, void** out);
 void    bb_dev_free(bb_ctx*, void*);

@@ -5,7 +5,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 D=$ROOT/birda_b200/variants/obj_$1
 mkdir -p $D
 cd $ROOT/birda_b200/csrc
-for f in capi k1_pack k2_resample k2_warp k3_post; do
+for f in capi k1_pack k2_resample k2_warp k3_post k4_dense; do
   if [ "$f" = "k2_warp" ] || [ ! -f $D/$f.o ]; then
     nvcc $2 -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -diag-suppress 20011,20014 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O2,-fno-fast-math -Xptxas -v -c $f.cu -o $D/$f.o 2> $D/$f.log &
   fi
