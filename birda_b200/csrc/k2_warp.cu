@@ -548,10 +548,23 @@ void warp_tables_free(ResamplerDev* rs) {
     rs->fast = false;
 }
 
+static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
+                                    uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
+                                    uint64_t nseg, uint64_t last_start, uint64_t row_first, uint64_t rows_total, uint64_t seg,
+                                    uint64_t resampled_len, float* d_out, int* launches, bool allow_dual);
+
 cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
                                  uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
                                  uint64_t nseg, uint64_t last_start, uint64_t row_first, uint64_t rows_total, uint64_t seg,
                                  uint64_t resampled_len, float* d_out, int* launches) {
+    return launch_warp_impl(st, sm_count, rs, d_pcm, fmt, channels, total_frames, src_seg, hop, nseg, last_start, row_first,
+                            rows_total, seg, resampled_len, d_out, launches, true);
+}
+
+static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,
+                                    uint32_t channels, uint64_t total_frames, uint64_t src_seg, uint64_t hop,
+                                    uint64_t nseg, uint64_t last_start, uint64_t row_first, uint64_t rows_total, uint64_t seg,
+                                    uint64_t resampled_len, float* d_out, int* launches, bool allow_dual) {
     if (launches) *launches = 0;
     if (rows_total == 0) return cudaSuccess;
     WarpParams P{};
@@ -567,7 +580,7 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     if (P.nblk == 0) P.nblk = 1;
     auto a16 = [](size_t x) { return (uint32_t)((x + 15) & ~(size_t)15); };
     // two-stream mode: compile-time plans only, at least two rows
-    bool dual = rs.ct_index >= 0 && rows_total >= 2;
+    bool dual = allow_dual && rs.ct_index >= 0 && rows_total >= 2;
     if (const char* g = std::getenv("BIRDA_K2_DUAL")) if (g[0] == '0') dual = false;
     const size_t esz = dual ? 16 : 8;                   // bytes per complex element in shared memory
     const int max_threads = dual ? kDualThreads : kMaxThreads;
@@ -585,12 +598,9 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
     P.per_group = P.off_carry + a16((size_t)(PL.M / 2) * esz);
     if (P.tables + P.per_group > kSmemMax) {
         if (!dual) return cudaErrorInvalidConfiguration;
-        // does not fit with two streams: fall back to one stream per group
-        setenv("BIRDA_K2_DUAL", "0", 1);
-        cudaError_t e2 = launch_resample_warp(st, sm_count, rs, d_pcm, fmt, channels, total_frames, src_seg, hop, nseg, last_start,
-                                              row_first, rows_total, seg, resampled_len, d_out, launches);
-        unsetenv("BIRDA_K2_DUAL");
-        return e2;
+        // does not fit with two streams: one stream per group
+        return launch_warp_impl(st, sm_count, rs, d_pcm, fmt, channels, total_frames, src_seg, hop, nseg, last_start,
+                                row_first, rows_total, seg, resampled_len, d_out, launches, false);
     }
     int groups = (int)((kSmemMax - P.tables) / P.per_group);
     if (groups > kMaxGroups) groups = kMaxGroups;

@@ -7,9 +7,10 @@
 // `pred.confidence >= min_confidence` test at src/pipeline/processor.rs:374.  Order of the steps
 // is the reference's: the mask sees only the already truncated top-k list.
 //
-// HBM-bound: B*C*4 bytes read once, B*top_k*8 + B*4 written.  Per-thread register top-k lists
-// (each thread scans its elements in increasing class index, so a tie never displaces an
-// earlier entry), merged with warp-shuffle arg-max rounds; ties resolve to the lower index.
+// B*C*4 bytes read once, B*top_k*8 + B*4 written.  The scan is load + compare against a coarse
+// threshold in the score domain; survivors go to a shared-memory candidate list, are activated there
+// and ranked against each other under the total order (confidence desc, class index asc); a list
+// overflow falls back to top_k rounds of block-wide arg-max (warp shuffles).
 #include "common.cuh"
 #include <cfloat>
 
