@@ -471,19 +471,24 @@ template <class PL>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 resample_plan_kernel(const __grid_constant__ WarpParams P) { resample_body<CtView<PL>>(P); }
 
-#ifndef BB_K2_DUAL_THREADS
-#define BB_K2_DUAL_THREADS 384
-#endif
-constexpr int kDualThreads = BB_K2_DUAL_THREADS;     // 384 = 12 warps: register cap 170 per thread for the two-stream butterflies
-template <class PL>
-__global__ void __launch_bounds__(kDualThreads, 1)
+// two-stream kernel; THREADS is the plan's CTA size (BB_K2_CT_PLANS): register budget and warps per group
+template <class PL, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 resample_plan2_kernel(const __grid_constant__ WarpParams P) { resample_body_dual<CtView<PL>>(P); }
+
+int ct_plan_dual_threads(int ct_index) {
+    int i = 0;
+#define BB_CT(NAME, NI, NO, TH, ...) if (i == ct_index) return TH; ++i;
+    BB_K2_CT_PLANS(BB_CT)
+#undef BB_CT
+    return 384;
+}
 
 // index of the compile-time plan for (n_in, n_out), -1 when only the runtime plan applies
 int ct_plan_index(uint32_t n_in, uint32_t n_out) {
     if (const char* g = std::getenv("BIRDA_K2_RUNTIME_PLAN")) if (g[0] == '1') return -1;
     int i = 0;
-#define BB_CT(NAME, NI, NO, ...) if (n_in == NI && n_out == NO) return i; ++i;
+#define BB_CT(NAME, NI, NO, TH, ...) if (n_in == NI && n_out == NO) return i; ++i;
     BB_K2_CT_PLANS(BB_CT)
 #undef BB_CT
     return -1;
@@ -510,7 +515,7 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     rs->ct_index = ct_plan_index(spec.n_in, spec.n_out);
     if (rs->ct_index >= 0) {
         int i = 0;
-#define BB_CT(NAME, NI, NO, ...) if (i == rs->ct_index) ct_radices<__VA_ARGS__>(&fwd, &inv); ++i;
+#define BB_CT(NAME, NI, NO, TH, ...) if (i == rs->ct_index) ct_radices<__VA_ARGS__>(&fwd, &inv); ++i;
         BB_K2_CT_PLANS(BB_CT)
 #undef BB_CT
         if (!build_plan_from_radices((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
@@ -583,7 +588,7 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     bool dual = allow_dual && rs.ct_index >= 0 && rows_total >= 2;
     if (const char* g = std::getenv("BIRDA_K2_DUAL")) if (g[0] == '0') dual = false;
     const size_t esz = dual ? 16 : 8;                   // bytes per complex element in shared memory
-    const int max_threads = dual ? kDualThreads : kMaxThreads;
+    const int max_threads = dual ? ct_plan_dual_threads(rs.ct_index) : kMaxThreads;
     P.dual = dual ? 1 : 0;
     P.off_twi = a16((size_t)PL.twf_len * esz);
     P.off_posf = P.off_twi + a16((size_t)PL.twi_len * esz);
@@ -632,12 +637,12 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     const unsigned threads = (unsigned)(groups * gw * 32);
     bool launched = false;
     int i = 0;
-#define BB_CT(NAME, NI, NO, ...)                                                                                        \
+#define BB_CT(NAME, NI, NO, TH, ...)                                                                                    \
     if (!launched && i == rs.ct_index) {                                                                                 \
         if (dual) {                                                                                                      \
-            e = cudaFuncSetAttribute(resample_plan2_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            e = cudaFuncSetAttribute(resample_plan2_kernel<__VA_ARGS__, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                              \
-            resample_plan2_kernel<__VA_ARGS__><<<(unsigned)ctas, threads, smem, st>>>(P);                                \
+            resample_plan2_kernel<__VA_ARGS__, TH><<<(unsigned)ctas, threads, smem, st>>>(P);                            \
         } else {                                                                                                         \
             e = cudaFuncSetAttribute(resample_plan_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                              \

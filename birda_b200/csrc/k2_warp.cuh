@@ -383,14 +383,16 @@ BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, int split_c, typ
     inverse_half_ct<PL, C>(ex, T, B, carry, sink);
 }
 
-// X(NAME, N_IN, N_OUT, CtPlan<RSeq<forward DIF radices>, RSeq<inverse DIT radices, last one even>>)
+// X(NAME, N_IN, N_OUT, DUAL_THREADS, CtPlan<RSeq<forward DIF radices>, RSeq<inverse DIT radices, last one even>>)
+// DUAL_THREADS: CTA size of the two-stream kernel = register budget (65536 / threads) and warps per group;
+// 640 (5 warps per window pair, 102 registers) suits the radix <= 8 plans, the radix-19 / 16 plans need 384.
 #define BB_K2_CT_PLANS(X)                                                                                        \
-    X(p1029_1120, 1029, 1120, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 7, 3>, bb::k2w::RSeq<7, 5, 4, 8>>)  /* 44.1k -> 48k */ \
-    X(p1026_684, 1026, 684, bb::k2w::CtPlan<bb::k2w::RSeq<6, 19, 9>, bb::k2w::RSeq<19, 9, 4>>)        /* 48k -> 32k */   \
-    X(p1029_2240, 1029, 2240, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 7, 3>, bb::k2w::RSeq<7, 5, 8, 8>>)  /* 22.05k -> 48k */ \
-    X(p1024_512, 1024, 512, bb::k2w::CtPlan<bb::k2w::RSeq<16, 8, 8>, bb::k2w::RSeq<8, 8, 8>>)         /* 96k -> 48k */   \
-    X(p1024_1536, 1024, 1536, bb::k2w::CtPlan<bb::k2w::RSeq<16, 8, 8>, bb::k2w::RSeq<3, 8, 8, 8>>)    /* 32k -> 48k */   \
-    X(p1323_960, 1323, 960, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 9, 3>, bb::k2w::RSeq<5, 3, 8, 8>>)    /* 44.1k -> 32k */
+    X(p1029_1120, 1029, 1120, 640, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 7, 3>, bb::k2w::RSeq<7, 5, 4, 8>>)  /* 44.1k -> 48k */ \
+    X(p1026_684, 1026, 684, 384, bb::k2w::CtPlan<bb::k2w::RSeq<6, 19, 9>, bb::k2w::RSeq<19, 9, 4>>)        /* 48k -> 32k */   \
+    X(p1029_2240, 1029, 2240, 384, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 7, 3>, bb::k2w::RSeq<7, 5, 8, 8>>)  /* 22.05k -> 48k */ \
+    X(p1024_512, 1024, 512, 384, bb::k2w::CtPlan<bb::k2w::RSeq<16, 8, 8>, bb::k2w::RSeq<8, 8, 8>>)         /* 96k -> 48k */   \
+    X(p1024_1536, 1024, 1536, 384, bb::k2w::CtPlan<bb::k2w::RSeq<16, 8, 8>, bb::k2w::RSeq<3, 8, 8, 8>>)    /* 32k -> 48k */   \
+    X(p1323_960, 1323, 960, 384, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 9, 3>, bb::k2w::RSeq<5, 3, 8, 8>>)    /* 44.1k -> 32k */
 
 // ------------------------------------------------------------------ host-side plan construction
 inline bool radix_supported(int r) {

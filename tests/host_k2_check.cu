@@ -105,7 +105,7 @@ int main() {
                             {1323, 960}, {1323, 1920}, {1024, 2048}, {1026, 342}, {1029, 560}, {1125, 216}, {1024, 256}};
     for (auto& c : cases) for (int nl : {32, 64}) bad += check_impl<void, float2>(c[0], c[1], nl);
     for (auto& c : cases) bad += check_impl<void, cx2>(c[0], c[1], 96);
-#define BB_CT(NAME, NI, NO, ...) bad += check_impl<__VA_ARGS__, float2>(NI, NO, 64); bad += check_impl<__VA_ARGS__, cx2>(NI, NO, 96);
+#define BB_CT(NAME, NI, NO, TH, ...) bad += check_impl<__VA_ARGS__, float2>(NI, NO, 64); bad += check_impl<__VA_ARGS__, cx2>(NI, NO, 96); bad += check_impl<__VA_ARGS__, cx2>(NI, NO, 160);
     BB_K2_CT_PLANS(BB_CT)
 #undef BB_CT
     printf(bad ? "FAILED\n" : "all plans ok\n");
