@@ -274,29 +274,39 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
 // f32x2 op, so index math, loads/stores and FP issue slots are shared by the two rows.
 struct DualStream { uint64_t base; int valid; int shift; bool active; };
 
-struct DualLoader {
-    const Source* src; const float4* A; DualStream s0, s1;
-    __device__ __forceinline__ void conv(int kind, int a, int b, int shift, float& re, float& im) const {
-        if (kind == 0) {
-            re = __fmul_rn(__int2float_rn((int)(short)(a & 0xffff) + (a >> 16)), 1.0f / 65536.0f);
-            im = __fmul_rn(__int2float_rn((int)(short)(b & 0xffff) + (b >> 16)), 1.0f / 65536.0f);
-        } else {
-            const int w = __funnelshift_r(a, b, shift);
-            re = __fmul_rn(__int2float_rn((int)(short)(w & 0xffff)), 1.0f / 32768.0f);
-            im = __fmul_rn(__int2float_rn(w >> 16), 1.0f / 32768.0f);
-        }
+template <int KIND>
+__device__ __forceinline__ void conv_pair(int a, int b, int shift, float& re, float& im) {
+    if constexpr (KIND == 0) {           // two packed L|R words: exact integer channel sum, then * 2^-15 / 2
+        re = __fmul_rn(__int2float_rn((int)(short)(a & 0xffff) + (a >> 16)), 1.0f / 65536.0f);
+        im = __fmul_rn(__int2float_rn((int)(short)(b & 0xffff) + (b >> 16)), 1.0f / 65536.0f);
+    } else {                             // mono: the aligned word(s) covering the frame pair
+        const int w = __funnelshift_r(a, b, shift);
+        re = __fmul_rn(__int2float_rn((int)(short)(w & 0xffff)), 1.0f / 32768.0f);
+        im = __fmul_rn(__int2float_rn(w >> 16), 1.0f / 32768.0f);
     }
-    __device__ __forceinline__ cx2 operator()(int n) const {
-        const int i0 = 2 * n;
+}
+
+// Loader of one block of the two streams.  KIND: 0 = S16 stereo staged in A, 1 = S16 mono staged in A,
+// 2 = direct global loads (other formats).  FULL: both streams hold `n` valid frames (interior block),
+// so only the odd tail sample needs zeroing.
+template <int KIND, bool FULL>
+struct DualLoaderT {
+    const Source* src; const float4* A; DualStream s0, s1; int n;
+    __device__ __forceinline__ cx2 operator()(int e) const {
+        const int i0 = 2 * e;
         float r0 = 0.f, m0 = 0.f, r1 = 0.f, m1 = 0.f;
-        if (src->kind != 2) {
-            const int4 v = *reinterpret_cast<const int4*>(A + n);
-            conv(src->kind, v.x, v.y, s0.shift, r0, m0);
-            conv(src->kind, v.z, v.w, s1.shift, r1, m1);
-            if (i0 >= s0.valid) r0 = 0.f;
-            if (i0 + 1 >= s0.valid) m0 = 0.f;
-            if (i0 >= s1.valid) r1 = 0.f;
-            if (i0 + 1 >= s1.valid) m1 = 0.f;
+        if constexpr (KIND != 2) {
+            const int4 v = *reinterpret_cast<const int4*>(A + e);
+            conv_pair<KIND>(v.x, v.y, s0.shift, r0, m0);
+            conv_pair<KIND>(v.z, v.w, s1.shift, r1, m1);
+            if constexpr (FULL) {
+                if (i0 + 1 >= n) { m0 = 0.f; m1 = 0.f; }
+            } else {
+                if (i0 >= s0.valid) r0 = 0.f;
+                if (i0 + 1 >= s0.valid) m0 = 0.f;
+                if (i0 >= s1.valid) r1 = 0.f;
+                if (i0 + 1 >= s1.valid) m1 = 0.f;
+            }
         } else {
             if (i0 < s0.valid) r0 = src->direct(s0.base + i0);
             if (i0 + 1 < s0.valid) m0 = src->direct(s0.base + i0 + 1);
@@ -307,14 +317,45 @@ struct DualLoader {
         return c;
     }
 };
+// picks the interior-block loader once per block (k2_warp.cuh: loader_pick); the test is uniform over the group
+template <int KIND>
+struct DualLoaderSet {
+    const Source* src; const float4* A; DualStream s0, s1; int n;
+    template <class F> __device__ __forceinline__ void pick(F&& f) const {
+        if constexpr (KIND == 2) f(DualLoaderT<2, false>{src, A, s0, s1, n});
+        else {
+            if (s0.valid == n && s1.valid == n) f(DualLoaderT<KIND, true>{src, A, s0, s1, n});
+            else f(DualLoaderT<KIND, false>{src, A, s0, s1, n});
+        }
+    }
+};
 
-// stage one stream's raw PCM of a block into its 8-byte half of the float4 slots
-__device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int half, uint64_t base, int valid, int half_in, int lane, int nl) {
+__device__ __forceinline__ void cp_async4_full(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8_full(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// stage one stream's raw PCM of a block into its 8-byte half of the float4 slots.  Interior blocks (all
+// `n_full` frames valid and the rounded-up copy inside the buffer) take a loop without bounds arithmetic.
+template <int KIND>
+__device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int half, uint64_t base, int valid, int half_in, int n_full,
+                                             int lane, int nl) {
     int shift = 0;
     char* dst0 = reinterpret_cast<char*>(A) + half * 8;
-    if (s.kind == 0) {
+    if constexpr (KIND == 0) {
         const char* g0 = reinterpret_cast<const char*>(s.pcm) + base * 4;
         const bool al8 = (reinterpret_cast<uintptr_t>(g0) & 7) == 0;
+        if (valid == n_full && g0 + (size_t)half_in * 8 <= s.pcm_end) {
+            const char* g = g0 + (size_t)lane * 8;
+            char* d = dst0 + (size_t)lane * 16;
+            if (al8) for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 8, d += (size_t)nl * 16) cp_async8_full(d, g);
+            else for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 8, d += (size_t)nl * 16) { cp_async4_full(d, g); cp_async4_full(d + 4, g + 4); }
+            return 0;
+        }
         for (int n = lane; n < half_in; n += nl) {
             if (2 * n >= valid) break;
             const char* g = g0 + (size_t)n * 8;
@@ -323,11 +364,18 @@ __device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int hal
             if (al8) cp_async8(d, g, room >= 8 ? 8 : (room > 0 ? (int)room : 0));
             else { cp_async4(d, g, room >= 4 ? 4 : 0); cp_async4(d + 4, g + 4, room >= 8 ? 4 : 0); }
         }
-    } else if (s.kind == 1) {
+    } else if constexpr (KIND == 1) {
         const char* g0 = reinterpret_cast<const char*>(s.pcm) + base * 2;
         const bool odd = (reinterpret_cast<uintptr_t>(g0) & 3) != 0;
         shift = odd ? 16 : 0;
         g0 -= odd ? 2 : 0;
+        if (valid == n_full && g0 + (size_t)half_in * 4 + 4 <= s.pcm_end) {
+            const char* g = g0 + (size_t)lane * 4;
+            char* d = dst0 + (size_t)lane * 16;
+            if (!odd) for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 4, d += (size_t)nl * 16) cp_async4_full(d, g);
+            else for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 4, d += (size_t)nl * 16) { cp_async4_full(d, g); cp_async4_full(d + 4, g + 4); }
+            return shift;
+        }
         for (int n = lane; n < half_in; n += nl) {
             if (2 * n >= valid) break;
             const char* g = g0 + (size_t)n * 4;
@@ -353,7 +401,7 @@ struct DualSink {
     }
 };
 
-template <class PV>
+template <class PV, int KIND>
 __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const RtPlan& PL = P.plan;
@@ -361,17 +409,17 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     float4* s_twi = reinterpret_cast<float4*>(smem + P.off_twi);
     uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + P.off_posf);
     uint16_t* s_posi = reinterpret_cast<uint16_t*>(smem + P.off_posi);
-    float4* s_P = reinterpret_cast<float4*>(smem + P.off_P);
-    float4* s_Q = reinterpret_cast<float4*>(smem + P.off_Q);
-    float4* s_WI = reinterpret_cast<float4*>(smem + P.off_WI);
+    float2* s_P = reinterpret_cast<float2*>(smem + P.off_P);
+    float2* s_Q = reinterpret_cast<float2*>(smem + P.off_Q);
+    float2* s_WI = reinterpret_cast<float2*>(smem + P.off_WI);
     const int NT = blockDim.x;
     auto bc = [](float2 w) { return make_float4(w.x, w.x, w.y, w.y); };
     for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = bc(P.twf[i]);
     for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = bc(P.twi[i]);
     for (int i = threadIdx.x; i < PL.N; i += NT) s_posf[i] = P.pos_f[i];
     for (int i = threadIdx.x; i < PL.M; i += NT) s_posi[i] = P.pos_i[i];
-    for (int i = threadIdx.x; i < PL.nkeep; i += NT) { s_P[i] = bc(P.Pt[i]); s_Q[i] = bc(P.Qt[i]); }
-    for (int i = threadIdx.x; i <= PL.M / 2; i += NT) s_WI[i] = bc(P.WI[i]);
+    for (int i = threadIdx.x; i < PL.nkeep; i += NT) { s_P[i] = P.Pt[i]; s_Q[i] = P.Qt[i]; }
+    for (int i = threadIdx.x; i <= PL.M / 2; i += NT) s_WI[i] = P.WI[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5;
@@ -393,9 +441,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     src.pcm = P.pcm; src.fmt = P.fmt; src.ch = P.channels; src.fch = (float)P.channels;
     const uint32_t bps = P.fmt == BB_S16 ? 2u : 4u;
     src.pcm_end = reinterpret_cast<const char*>(P.pcm) + P.total_frames * P.channels * bps;
-    src.kind = 2;
-    if (P.fmt == BB_S16 && P.channels == 2 && (reinterpret_cast<uintptr_t>(P.pcm) & 3) == 0) src.kind = 0;
-    if (P.fmt == BB_S16 && P.channels == 1 && (reinterpret_cast<uintptr_t>(P.pcm) & 1) == 0) src.kind = 1;
+    src.kind = KIND;                                   // chosen by the launcher (source_kind)
     const uint64_t row_end = P.row_first + P.rows_total;
 
     for (;;) {
@@ -439,12 +485,12 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
         for (int j = lane; j < M / 2; j += nl) carry[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
         DualStream c0 = stream_of(0, bfirst), c1 = stream_of(1, bfirst);
-        c0.shift = prefetch_half(src, A, 0, c0.base, c0.valid, HALF_IN, lane, nl);
-        c1.shift = prefetch_half(src, A, 1, c1.base, c1.valid, HALF_IN, lane, nl);
+        c0.shift = prefetch_half<KIND>(src, A, 0, c0.base, c0.valid, HALF_IN, N, lane, nl);
+        c1.shift = prefetch_half<KIND>(src, A, 1, c1.base, c1.valid, HALF_IN, N, lane, nl);
         for (uint32_t b = bfirst; b < b1; ++b) {
             cp_async_wait_all();
             ex.sync();
-            DualLoader ld{&src, A, c0, c1};
+            DualLoaderSet<KIND> ld{&src, A, c0, c1, N};
             DualSink sink;
             const int64_t lim = (int64_t)o_hi - (int64_t)b * M;
             const int l = b < b0 ? 0 : (int)(lim < 0 ? 0 : (lim > M ? M : lim));   // recomputed block: carry only
@@ -455,8 +501,8 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
             PV::template block<cx2>(ex, PL, T, A, B, carry, ld, sink, [&] {
                 if (b + 1 < b1) {
                     n0 = stream_of(0, b + 1); n1 = stream_of(1, b + 1);
-                    n0.shift = prefetch_half(src, A, 0, n0.base, n0.valid, HALF_IN, lane, nl);
-                    n1.shift = prefetch_half(src, A, 1, n1.base, n1.valid, HALF_IN, lane, nl);
+                    n0.shift = prefetch_half<KIND>(src, A, 0, n0.base, n0.valid, HALF_IN, N, lane, nl);
+                    n1.shift = prefetch_half<KIND>(src, A, 1, n1.base, n1.valid, HALF_IN, N, lane, nl);
                 }
             });
             c0 = n0; c1 = n1;
@@ -472,9 +518,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
 resample_plan_kernel(const __grid_constant__ WarpParams P) { resample_body<CtView<PL>>(P); }
 
 // two-stream kernel; THREADS is the plan's CTA size (BB_K2_CT_PLANS): register budget and warps per group
-template <class PL, int THREADS>
+template <class PL, int THREADS, int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
-resample_plan2_kernel(const __grid_constant__ WarpParams P) { resample_body_dual<CtView<PL>>(P); }
+resample_plan2_kernel(const __grid_constant__ WarpParams P) { resample_body_dual<CtView<PL>, KIND>(P); }
+
+// how the kernels read the PCM: 0 = S16 stereo staged with cp.async, 1 = S16 mono staged, 2 = direct loads
+int source_kind(const void* pcm, int fmt, uint32_t channels) {
+    if (fmt == BB_S16 && channels == 2 && (reinterpret_cast<uintptr_t>(pcm) & 3) == 0) return 0;
+    if (fmt == BB_S16 && channels == 1 && (reinterpret_cast<uintptr_t>(pcm) & 1) == 0) return 1;
+    return 2;
+}
+
+template <class PL, int THREADS>
+cudaError_t launch_plan2(int kind, unsigned ctas, unsigned threads, size_t smem, cudaStream_t st, const WarpParams& P) {
+    cudaError_t e = cudaSuccess;
+#define BB_L2(K)                                                                                                          \
+    e = cudaFuncSetAttribute(resample_plan2_kernel<PL, THREADS, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                        \
+    resample_plan2_kernel<PL, THREADS, K><<<ctas, threads, smem, st>>>(P);
+    if (kind == 0) { BB_L2(0) } else if (kind == 1) { BB_L2(1) } else { BB_L2(2) }
+#undef BB_L2
+    return e;
+}
 
 int ct_plan_dual_threads(int ct_index) {
     int i = 0;
@@ -594,9 +659,9 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     P.off_posf = P.off_twi + a16((size_t)PL.twi_len * esz);
     P.off_posi = P.off_posf + a16((size_t)PL.N * 2);
     P.off_P = P.off_posi + a16((size_t)PL.M * 2);
-    P.off_Q = P.off_P + a16((size_t)PL.nkeep * esz);
-    P.off_WI = P.off_Q + a16((size_t)PL.nkeep * esz);
-    P.off_items = P.off_WI + a16((size_t)(PL.M / 2 + 1) * esz);
+    P.off_Q = P.off_P + a16((size_t)PL.nkeep * 8);       // split tables stay float2 in both modes
+    P.off_WI = P.off_Q + a16((size_t)PL.nkeep * 8);
+    P.off_items = P.off_WI + a16((size_t)(PL.M / 2 + 1) * 8);
     P.tables = P.off_items + a16((size_t)kMaxGroups * 8);
     P.off_B = a16((size_t)PL.N * esz);
     P.off_carry = P.off_B + a16((size_t)PL.M * esz);
@@ -640,9 +705,8 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
 #define BB_CT(NAME, NI, NO, TH, ...)                                                                                    \
     if (!launched && i == rs.ct_index) {                                                                                 \
         if (dual) {                                                                                                      \
-            e = cudaFuncSetAttribute(resample_plan2_kernel<__VA_ARGS__, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            e = launch_plan2<__VA_ARGS__, TH>(source_kind(d_pcm, fmt, channels), (unsigned)ctas, threads, smem, st, P);  \
             if (e != cudaSuccess) return e;                                                                              \
-            resample_plan2_kernel<__VA_ARGS__, TH><<<(unsigned)ctas, threads, smem, st>>>(P);                            \
         } else {                                                                                                         \
             e = cudaFuncSetAttribute(resample_plan_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return e;                                                                              \

@@ -211,7 +211,7 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 template <class C> struct Tables {
     using T = typename Mem<C>::T;
     const T* twf; const T* twi; const uint16_t* pos_f; const uint16_t* pos_i;
-    const T* Pt; const T* Qt; const T* WI;
+    const float2* Pt; const float2* Qt; const float2* WI;     // compact: broadcast to the stream(s) at load time
 };
 
 // ---- fused split / filter / re-bin / inverse pack:  A (digit-reversed forward result) -> B
@@ -229,17 +229,17 @@ BB_UNROLL_N(BB_K2W_UNROLL)
         C yk = czero<C>(), yk2 = czero<C>();
         if (k < nkeep) {
             const C zk = Mem<C>::ld(A + T.pos_f[k == N ? 0 : k]), zn = cconj(Mem<C>::ld(A + T.pos_f[k == 0 ? 0 : N - k]));
-            yk = cadd(cmul(Mem<C>::ld(T.Pt + k), zk), cmul(Mem<C>::ld(T.Qt + k), zn));
+            yk = cadd(cmul(Mem<C>::bcast(T.Pt[k]), zk), cmul(Mem<C>::bcast(T.Qt[k]), zn));
         }
         if (k2 < nkeep) {
             const C zk = Mem<C>::ld(A + T.pos_f[k2 == N ? 0 : k2]), zn = cconj(Mem<C>::ld(A + T.pos_f[N - k2]));
-            yk2 = cadd(cmul(Mem<C>::ld(T.Pt + k2), zk), cmul(Mem<C>::ld(T.Qt + k2), zn));
+            yk2 = cadd(cmul(Mem<C>::bcast(T.Pt[k2]), zk), cmul(Mem<C>::bcast(T.Qt[k2]), zn));
         }
         if (k == 0) {                                   // DC / Nyquist are real (realfft ignores their imag)
             yk = Cx<C>::make(Cx<C>::re(yk), kzero(typename Cx<C>::K()));
             yk2 = Cx<C>::make(Cx<C>::re(yk2), kzero(typename Cx<C>::K()));
         }
-        const C wi = Mem<C>::ld(T.WI + k);
+        const C wi = Mem<C>::bcast(T.WI[k]);
         {
             const C e = cadd(yk, cconj(yk2)), o = cmul(wi, csub(yk, cconj(yk2)));
             Mem<C>::st(B + T.pos_i[k], Cx<C>::make(ksub(Cx<C>::re(e), Cx<C>::im(o)), kadd(Cx<C>::im(e), Cx<C>::re(o))));
@@ -341,6 +341,11 @@ struct CtPlan {
     static_assert(INV_::at(INV_::count - 1) % 2 == 0, "last inverse radix must be even");
 };
 
+// A loader may offer `pick(f)`: it calls f with one of several specialised loaders (chosen by a test that is
+// uniform over the thread group), so the choice is made once per block instead of once per element.
+template <class L, class F> BB_HD auto loader_pick(const L& l, F&& f, int) -> decltype(l.pick(f)) { return l.pick(f); }
+template <class L, class F> BB_HD void loader_pick(const L& l, F&& f, long) { f(l); }
+
 template <class PL, class C, class Exec, int T> struct CtFwdRest {
     static BB_HD void run(const Exec& ex, typename Mem<C>::T* A, const typename Mem<C>::T* twf) {
         if constexpr (T < PL::Fwd::count) {
@@ -364,7 +369,9 @@ template <class PL, class C, class Exec, class Loader, class BeforeSplit>
 BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, int split_c, typename Mem<C>::T* A, typename Mem<C>::T* B, const Loader& ld,
                            BeforeSplit&& before_split) {
     using S0 = typename PL::template FwdStage<0>;
-    ex.each([&](int lane, int nl) { dif_first<S0::radix, C>(A, T.twf, S0{}, PL::HALF_IN, ld, lane, nl); });
+    loader_pick(ld, [&](const auto& l) {
+        ex.each([&](int lane, int nl) { dif_first<S0::radix, C>(A, T.twf, S0{}, PL::HALF_IN, l, lane, nl); });
+    }, 0);
     CtFwdRest<PL, C, Exec, 1>::run(ex, A, T.twf);
     before_split();
     ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::N, PL::M, PL::NKEEP, split_c, lane, nl); });

@@ -45,8 +45,8 @@ static int check_impl(int N, int M, int nl) {
     std::vector<float2> Pt(NKEEP), Qt(NKEEP), WI(M / 2 + 1), twf(P.twf_len), twi(P.twi_len);
     build_split_tables(N, M, NKEEP, fre.data(), fim.data(), Pt.data(), Qt.data(), WI.data());
     build_twiddles(P, twf.data(), twi.data());
-    auto twf_e = expand_table<C>(twf), twi_e = expand_table<C>(twi), Pt_e = expand_table<C>(Pt), Qt_e = expand_table<C>(Qt), WI_e = expand_table<C>(WI);
-    Tables<C> T{twf_e.data(), twi_e.data(), pos_f.data(), pos_i.data(), Pt_e.data(), Qt_e.data(), WI_e.data()};
+    auto twf_e = expand_table<C>(twf), twi_e = expand_table<C>(twi);
+    Tables<C> T{twf_e.data(), twi_e.data(), pos_f.data(), pos_i.data(), Pt.data(), Qt.data(), WI.data()};
 
     const int NB = 3;
     std::vector<float> x(NB * N), x2(NB * N);
