@@ -181,5 +181,12 @@ template <int R1, int R2, bool INV> struct DftComposite {
 template <bool INV> struct Dft<6, INV>  : DftComposite<2, 3, INV> {};
 template <bool INV> struct Dft<9, INV>  : DftComposite<3, 3, INV> {};
 template <bool INV> struct Dft<16, INV> : DftComposite<4, 4, INV> {};
+template <bool INV> struct Dft<10, INV> : DftComposite<2, 5, INV> {};
+template <bool INV> struct Dft<12, INV> : DftComposite<4, 3, INV> {};
+template <bool INV> struct Dft<14, INV> : DftComposite<2, 7, INV> {};
+template <bool INV> struct Dft<15, INV> : DftComposite<3, 5, INV> {};
+template <bool INV> struct Dft<18, INV> : DftComposite<2, 9, INV> {};
+template <bool INV> struct Dft<20, INV> : DftComposite<4, 5, INV> {};
+template <bool INV> struct Dft<21, INV> : DftComposite<3, 7, INV> {};
 
 }  // namespace bb

@@ -10,6 +10,7 @@
 // frames from L2.  128-bit stores always; 64/128-bit loads whenever the window start is
 // aligned (warp-uniform test per row), scalar loads otherwise.
 #include "common.cuh"
+#include <type_traits>
 
 namespace bb {
 namespace {
@@ -67,10 +68,16 @@ __device__ __forceinline__ float4 load4_aligned(const S* __restrict__ p) {
     return o;
 }
 
-// 16 bytes of interleaved PCM -> E = 16 / (CH * sizeof(S)) mono samples, reference operation order
-template <typename S, int CH> struct Slot16 {
-    static constexpr int E = 16 / (CH * (int)sizeof(S));
-    static __device__ __forceinline__ void convert(const int4& raw, float (&o)[E]) {
+// One aligned raw load per thread -> E mono samples in the reference's operation order.  The load is sized so
+// that E <= 4: a thread then issues ONE 16-byte (or 8-byte) store per load and a warp's store instruction covers
+// contiguous memory.  (A 16-byte load of mono s16 gives 8 samples = two float4 per thread; the warp's stores then
+// hit 16-byte pieces 32 bytes apart, and that pattern tops out at ~4.2-4.6 TB/s against ~6.2 TB/s for contiguous
+// stores — tools/micro/rw.cu, profiles/r01_hbm_mix_micro.txt.)
+template <typename S, int CH> struct SlotRaw {
+    static constexpr int kBytes = (CH * (int)sizeof(S) * 4 < 16) ? CH * (int)sizeof(S) * 4 : 16;
+    using Raw = typename std::conditional<kBytes == 8, int2, int4>::type;
+    static constexpr int E = kBytes / (CH * (int)sizeof(S));
+    static __device__ __forceinline__ void convert(const Raw& raw, float (&o)[E]) {
         const S* s = reinterpret_cast<const S*>(&raw);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -105,46 +112,30 @@ pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_fr
             // aligned -> all loads of the tile are issued back to back (kUnroll x 16 B in flight per thread),
             // no per-element control flow between a load and the next one
             constexpr int ch = CH_T == 0 ? 1 : CH_T;
-            using SL = Slot16<S, ch>;
+            using SL = SlotRaw<S, ch>;
+            using Raw = typename SL::Raw;
             constexpr int E = SL::E;
-            constexpr int kPass = kThreads * kUnroll * E;         // floats per pass: kUnroll x 16 B loads in flight per thread
+            constexpr int UN = kUnroll * (16 / SL::kBytes);       // the same bytes in flight per thread for 8-byte loads
+            constexpr int kPass = kThreads * UN * E;              // floats per pass
             static_assert(kTile % kPass == 0, "tile must be a whole number of passes");
-            const bool aligned16 = ((reinterpret_cast<uintptr_t>(pcm) + start * ch * sizeof(S)) & 15) == 0 && (seg % E) == 0 &&
+            const bool aligned16 = ((reinterpret_cast<uintptr_t>(pcm) + start * ch * sizeof(S)) & 15) == 0 && (seg % 4) == 0 &&
                                    ((reinterpret_cast<uintptr_t>(orow) & 15) == 0);
             if (aligned16 && j0 + kTile <= take) {
 #pragma unroll 1
                 for (uint64_t jp = j0; jp < j0 + kTile; jp += kPass) {
-                    int4 raw[kUnroll];
+                    Raw raw[UN];
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) {
+                    for (int u = 0; u < UN; ++u) {
                         const uint64_t j = jp + ((uint64_t)u * kThreads + threadIdx.x) * E;
-#ifdef BB_K1_LDCS
-                        raw[u] = __ldcs(reinterpret_cast<const int4*>(pcm + (start + j) * ch));
-#else
-                        raw[u] = __ldg(reinterpret_cast<const int4*>(pcm + (start + j) * ch));
-#endif
+                        raw[u] = __ldg(reinterpret_cast<const Raw*>(pcm + (start + j) * ch));
                     }
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) {
+                    for (int u = 0; u < UN; ++u) {
                         const uint64_t j = jp + ((uint64_t)u * kThreads + threadIdx.x) * E;
                         float o[E];
                         SL::convert(raw[u], o);
-#ifdef BB_K1_NOSTORE
-                        if (o[0] == 123.456f) orow[j] = o[1];       // experiment: loads only
-                        continue;
-#endif
-                        if (E >= 4) {
-#pragma unroll
-                            for (int e = 0; e < E; e += 4) {
-#if BB_K1_STREAM_STORE
-                                __stcs(reinterpret_cast<float4*>(orow + j + e), make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
-#else
-                                *reinterpret_cast<float4*>(orow + j + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
-#endif
-                            }
-                        } else {
-                            __stcs(reinterpret_cast<float2*>(orow + j), make_float2(o[0], o[1]));
-                        }
+                        if (E == 4) *reinterpret_cast<float4*>(orow + j) = make_float4(o[0], o[1], o[2], o[3]);
+                        else *reinterpret_cast<float2*>(orow + j) = make_float2(o[0], o[1]);
                     }
                 }
                 continue;
@@ -165,15 +156,9 @@ pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_fr
                 const uint64_t j = js + ((uint64_t)u * kThreads + threadIdx.x) * 4;
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (j < seg) {
-#ifdef BB_K1_NOLOAD
-                    if (true) { v[u] = make_float4((float)j, 0.f, 0.f, 0.f);
-#else
                     if (CH_T != 0 && in_vec && j + 4 <= take) {
-#endif
-#ifndef BB_K1_NOLOAD
                         constexpr int ch = CH_T == 0 ? 1 : CH_T;
                         v[u] = load4_aligned<S, ch>(pcm + (start + j) * ch);
-#endif
                     } else {
                         float t[4];
 #pragma unroll

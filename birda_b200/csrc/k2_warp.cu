@@ -388,6 +388,55 @@ __device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int hal
     return shift;
 }
 
+// Stage the raw PCM of one block of BOTH streams.  Interior blocks use a lane mapping in which consecutive lanes
+// fill adjacent 4- or 8-byte pieces of the same float4 slot, so a warp's cp.async writes cover contiguous shared
+// memory (no bank conflicts); anything else goes stream by stream through prefetch_half.
+template <int KIND>
+__device__ __forceinline__ void prefetch_pair(const Source& s, float4* A, DualStream& a, DualStream& b, int half_in, int n_full,
+                                              int lane, int nl) {
+    if constexpr (KIND == 0) {
+        const char* g0 = reinterpret_cast<const char*>(s.pcm) + a.base * 4;
+        const char* g1 = reinterpret_cast<const char*>(s.pcm) + b.base * 4;
+        if (a.valid == n_full && b.valid == n_full && g0 + (size_t)half_in * 8 <= s.pcm_end && g1 + (size_t)half_in * 8 <= s.pcm_end) {
+            a.shift = 0; b.shift = 0;
+            if (((reinterpret_cast<uintptr_t>(g0) | reinterpret_cast<uintptr_t>(g1)) & 7) == 0) {
+                const int st = lane & 1, n0 = lane >> 1, dn = nl >> 1;
+                const char* g = (st ? g1 : g0) + (size_t)n0 * 8;
+                char* d = reinterpret_cast<char*>(A) + (size_t)n0 * 16 + st * 8;
+                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 8, d += (size_t)dn * 16) cp_async8_full(d, g);
+            } else {
+                const int qd = lane & 3, n0 = lane >> 2, dn = nl >> 2;
+                const char* g = ((qd >> 1) ? g1 : g0) + (size_t)n0 * 8 + (qd & 1) * 4;
+                char* d = reinterpret_cast<char*>(A) + (size_t)n0 * 16 + qd * 4;
+                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 8, d += (size_t)dn * 16) cp_async4_full(d, g);
+            }
+            return;
+        }
+    } else if constexpr (KIND == 1) {
+        const char* g0 = reinterpret_cast<const char*>(s.pcm) + a.base * 2;
+        const char* g1 = reinterpret_cast<const char*>(s.pcm) + b.base * 2;
+        const bool odd0 = (reinterpret_cast<uintptr_t>(g0) & 3) != 0, odd1 = (reinterpret_cast<uintptr_t>(g1) & 3) != 0;
+        g0 -= odd0 ? 2 : 0; g1 -= odd1 ? 2 : 0;
+        if (a.valid == n_full && b.valid == n_full && g0 + (size_t)half_in * 4 + 4 <= s.pcm_end && g1 + (size_t)half_in * 4 + 4 <= s.pcm_end) {
+            a.shift = odd0 ? 16 : 0; b.shift = odd1 ? 16 : 0;
+            if (!odd0 && !odd1) {                       // one aligned word per frame pair and stream
+                const int st = lane & 1, n0 = lane >> 1, dn = nl >> 1;
+                const char* g = (st ? g1 : g0) + (size_t)n0 * 4;
+                char* d = reinterpret_cast<char*>(A) + (size_t)n0 * 16 + st * 8;
+                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 4, d += (size_t)dn * 16) cp_async4_full(d, g);
+            } else {                                    // two words (the funnel shift picks the pair)
+                const int qd = lane & 3, n0 = lane >> 2, dn = nl >> 2;
+                const char* g = ((qd >> 1) ? g1 : g0) + (size_t)n0 * 4 + (qd & 1) * 4;
+                char* d = reinterpret_cast<char*>(A) + (size_t)n0 * 16 + qd * 4;
+                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 4, d += (size_t)dn * 16) cp_async4_full(d, g);
+            }
+            return;
+        }
+    }
+    a.shift = prefetch_half<KIND>(s, A, 0, a.base, a.valid, half_in, n_full, lane, nl);
+    b.shift = prefetch_half<KIND>(s, A, 1, b.base, b.valid, half_in, n_full, lane, nl);
+}
+
 struct DualSink {
     float* p0; float* p1; int lim0, lim1; bool vec0, vec1;
     __device__ __forceinline__ void put(float* p, int lim, bool vec, int o, float a, float b) const {
@@ -485,8 +534,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
         for (int j = lane; j < M / 2; j += nl) carry[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
         DualStream c0 = stream_of(0, bfirst), c1 = stream_of(1, bfirst);
-        c0.shift = prefetch_half<KIND>(src, A, 0, c0.base, c0.valid, HALF_IN, N, lane, nl);
-        c1.shift = prefetch_half<KIND>(src, A, 1, c1.base, c1.valid, HALF_IN, N, lane, nl);
+        prefetch_pair<KIND>(src, A, c0, c1, HALF_IN, N, lane, nl);
         for (uint32_t b = bfirst; b < b1; ++b) {
             cp_async_wait_all();
             ex.sync();
@@ -501,8 +549,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
             PV::template block<cx2>(ex, PL, T, A, B, carry, ld, sink, [&] {
                 if (b + 1 < b1) {
                     n0 = stream_of(0, b + 1); n1 = stream_of(1, b + 1);
-                    n0.shift = prefetch_half<KIND>(src, A, 0, n0.base, n0.valid, HALF_IN, N, lane, nl);
-                    n1.shift = prefetch_half<KIND>(src, A, 1, n1.base, n1.valid, HALF_IN, N, lane, nl);
+                    prefetch_pair<KIND>(src, A, n0, n1, HALF_IN, N, lane, nl);
                 }
             });
             c0 = n0; c1 = n1;

@@ -393,9 +393,20 @@ BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, int split_c, typ
 // X(NAME, N_IN, N_OUT, DUAL_THREADS, CtPlan<RSeq<forward DIF radices>, RSeq<inverse DIT radices, last one even>>)
 // DUAL_THREADS: CTA size of the two-stream kernel = register budget (65536 / threads) and warps per group;
 // 640 (5 warps per window pair, 102 registers) suits the radix <= 8 plans, the radix-19 / 16 plans need 384.
+// the two headline plans can be overridden from the command line for A/B builds (tools/build_variant.sh)
+#ifndef BB_P1029_1120_TH
+#define BB_P1029_1120_TH 640
+#define BB_P1029_1120_F 7, 7, 7, 3
+#define BB_P1029_1120_I 7, 5, 4, 8
+#endif
+#ifndef BB_P1026_684_TH
+#define BB_P1026_684_TH 384
+#define BB_P1026_684_F 6, 19, 9
+#define BB_P1026_684_I 19, 9, 4
+#endif
 #define BB_K2_CT_PLANS(X)                                                                                        \
-    X(p1029_1120, 1029, 1120, 640, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 7, 3>, bb::k2w::RSeq<7, 5, 4, 8>>)  /* 44.1k -> 48k */ \
-    X(p1026_684, 1026, 684, 384, bb::k2w::CtPlan<bb::k2w::RSeq<6, 19, 9>, bb::k2w::RSeq<19, 9, 4>>)        /* 48k -> 32k */   \
+    X(p1029_1120, 1029, 1120, BB_P1029_1120_TH, bb::k2w::CtPlan<bb::k2w::RSeq<BB_P1029_1120_F>, bb::k2w::RSeq<BB_P1029_1120_I>>)  /* 44.1k -> 48k */ \
+    X(p1026_684, 1026, 684, BB_P1026_684_TH, bb::k2w::CtPlan<bb::k2w::RSeq<BB_P1026_684_F>, bb::k2w::RSeq<BB_P1026_684_I>>)        /* 48k -> 32k */   \
     X(p1029_2240, 1029, 2240, 384, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 7, 3>, bb::k2w::RSeq<7, 5, 8, 8>>)  /* 22.05k -> 48k */ \
     X(p1024_512, 1024, 512, 384, bb::k2w::CtPlan<bb::k2w::RSeq<16, 8, 8>, bb::k2w::RSeq<8, 8, 8>>)         /* 96k -> 48k */   \
     X(p1024_1536, 1024, 1536, 384, bb::k2w::CtPlan<bb::k2w::RSeq<16, 8, 8>, bb::k2w::RSeq<3, 8, 8, 8>>)    /* 32k -> 48k */   \

@@ -1,13 +1,17 @@
 #!/bin/bash
-# usage: tools/build_variant.sh NAME "-DFLAG=.. -DFLAG2=.."  -> birda_b200/variants/libbirda_b200_NAME.so
+# usage: tools/build_variant.sh NAME "-DFLAG=.." [header-with-plan-overrides]  -> birda_b200/variants/libbirda_b200_NAME.so
+# The optional header is pre-included into k2_warp.cu (plan overrides hold commas, which -D cannot carry).
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 D=$ROOT/birda_b200/variants/obj_$1
 mkdir -p $D
 cd $ROOT/birda_b200/csrc
+INC=""
+if [ -n "$3" ]; then INC="-include $3"; fi
 for f in capi k1_pack k2_resample k2_warp k3_post k4_dense; do
   if [ "$f" = "k2_warp" ] || [ ! -f $D/$f.o ]; then
-    nvcc $2 -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -diag-suppress 20011,20014 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O2,-fno-fast-math -Xptxas -v -c $f.cu -o $D/$f.o 2> $D/$f.log &
+    X=""; if [ "$f" = "k2_warp" ]; then X="$INC"; fi
+    nvcc $2 $X -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -diag-suppress 20011,20014 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O2,-fno-fast-math -Xptxas -v -c $f.cu -o $D/$f.o 2> $D/$f.log &
   fi
 done
 g++ -O2 -std=c++17 -fPIC -fno-fast-math -ffp-contract=off -c rules.cpp -o $D/rules.o
