@@ -36,8 +36,8 @@ struct ResamplerDev {
     bool fast = false;
     alignas(8) unsigned char plan_blob[768] = {0};
     int ct_index = -1;                 // compile-time plan (k2_warp.cuh: BB_K2_CT_PLANS) or -1
-    float2 *f_twf = nullptr, *f_twi = nullptr, *f_P = nullptr, *f_Q = nullptr, *f_WI = nullptr;
-    uint16_t *f_pos_f = nullptr, *f_pos_i = nullptr;
+    float2 *f_twf = nullptr, *f_twi = nullptr, *f_WI = nullptr;
+    uint4* f_sidx = nullptr; float4 *f_pq1 = nullptr, *f_pq2 = nullptr;   // split-pass layout (k2_warp.cuh: build_split_layout)
     unsigned long long* f_counter = nullptr;
 };
 

@@ -19,11 +19,11 @@ struct WarpParams {
     const void* pcm; int fmt; uint32_t channels; uint64_t total_frames;
     uint64_t src_seg, hop, nseg, last_start, rows_total, row_first, seg;
     uint32_t out_len; float* out;
-    const float2 *twf, *twi, *Pt, *Qt, *WI; const uint16_t *pos_f, *pos_i;
+    const float2 *twf, *twi, *WI; const uint4* sidx; const float4 *pq1, *pq2;     // tables in global memory
     uint32_t nblk, R, items_per_row; uint64_t nitems;
     unsigned long long* counter;
     // shared memory layout (bytes)
-    uint32_t off_twi, off_posf, off_posi, off_P, off_Q, off_WI, off_items, tables, per_group, off_B, off_carry;
+    uint32_t off_twi, off_sidx, off_pq1, off_pq2, off_WI, off_items, tables, per_group, off_B, off_carry;
     int groups, gw;                    // thread groups per CTA, warps per group (a group owns one block at a time)
     int dual;                          // 1: two rows per group in lockstep (packed f32x2 math), tables are float4
 };
@@ -168,7 +168,7 @@ template <class PL> struct CtView {
     static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const Tables<C>& T, typename Mem<C>::T* A,
                                                  typename Mem<C>::T* B, typename Mem<C>::T* carry, const Loader& ld,
                                                  const Sink& sink, After&& after) {
-        process_block_ct<PL, C>(ex, T, p.split_c, A, B, carry, ld, sink, after);
+        process_block_ct<PL, C>(ex, T, A, B, carry, ld, sink, after);
     }
 };
 
@@ -178,18 +178,14 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
     const RtPlan& PL = P.plan;
     float2* s_twf = reinterpret_cast<float2*>(smem);
     float2* s_twi = reinterpret_cast<float2*>(smem + P.off_twi);
-    uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + P.off_posf);
-    uint16_t* s_posi = reinterpret_cast<uint16_t*>(smem + P.off_posi);
-    float2* s_P = reinterpret_cast<float2*>(smem + P.off_P);
-    float2* s_Q = reinterpret_cast<float2*>(smem + P.off_Q);
+    uint4* s_sidx = reinterpret_cast<uint4*>(smem + P.off_sidx);
+    float4* s_pq1 = reinterpret_cast<float4*>(smem + P.off_pq1);
+    float4* s_pq2 = reinterpret_cast<float4*>(smem + P.off_pq2);
     float2* s_WI = reinterpret_cast<float2*>(smem + P.off_WI);
     const int NT = blockDim.x;
     for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = P.twf[i];
     for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = P.twi[i];
-    for (int i = threadIdx.x; i < PL.N; i += NT) s_posf[i] = P.pos_f[i];
-    for (int i = threadIdx.x; i < PL.M; i += NT) s_posi[i] = P.pos_i[i];
-    for (int i = threadIdx.x; i < PL.nkeep; i += NT) { s_P[i] = P.Pt[i]; s_Q[i] = P.Qt[i]; }
-    for (int i = threadIdx.x; i <= PL.M / 2; i += NT) s_WI[i] = P.WI[i];
+    for (int i = threadIdx.x; i < PL.split_len; i += NT) { s_sidx[i] = P.sidx[i]; s_pq1[i] = P.pq1[i]; s_pq2[i] = P.pq2[i]; s_WI[i] = P.WI[i]; }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5;
@@ -204,7 +200,7 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
     float2* A = reinterpret_cast<float2*>(gbase);
     float2* B = reinterpret_cast<float2*>(gbase + P.off_B);
     float2* carry = reinterpret_cast<float2*>(gbase + P.off_carry);
-    const Tables<float2> T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
+    const Tables<float2> T{s_twf, s_twi, s_sidx, s_pq1, s_pq2, s_WI};
     const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
 
     Source src;
@@ -456,19 +452,15 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     const RtPlan& PL = P.plan;
     float4* s_twf = reinterpret_cast<float4*>(smem);
     float4* s_twi = reinterpret_cast<float4*>(smem + P.off_twi);
-    uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + P.off_posf);
-    uint16_t* s_posi = reinterpret_cast<uint16_t*>(smem + P.off_posi);
-    float2* s_P = reinterpret_cast<float2*>(smem + P.off_P);
-    float2* s_Q = reinterpret_cast<float2*>(smem + P.off_Q);
+    uint4* s_sidx = reinterpret_cast<uint4*>(smem + P.off_sidx);
+    float4* s_pq1 = reinterpret_cast<float4*>(smem + P.off_pq1);
+    float4* s_pq2 = reinterpret_cast<float4*>(smem + P.off_pq2);
     float2* s_WI = reinterpret_cast<float2*>(smem + P.off_WI);
     const int NT = blockDim.x;
     auto bc = [](float2 w) { return make_float4(w.x, w.x, w.y, w.y); };
     for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = bc(P.twf[i]);
     for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = bc(P.twi[i]);
-    for (int i = threadIdx.x; i < PL.N; i += NT) s_posf[i] = P.pos_f[i];
-    for (int i = threadIdx.x; i < PL.M; i += NT) s_posi[i] = P.pos_i[i];
-    for (int i = threadIdx.x; i < PL.nkeep; i += NT) { s_P[i] = P.Pt[i]; s_Q[i] = P.Qt[i]; }
-    for (int i = threadIdx.x; i <= PL.M / 2; i += NT) s_WI[i] = P.WI[i];
+    for (int i = threadIdx.x; i < PL.split_len; i += NT) { s_sidx[i] = P.sidx[i]; s_pq1[i] = P.pq1[i]; s_pq2[i] = P.pq2[i]; s_WI[i] = P.WI[i]; }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5;
@@ -483,7 +475,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     float4* A = reinterpret_cast<float4*>(gbase);
     float4* B = reinterpret_cast<float4*>(gbase + P.off_B);
     float4* carry = reinterpret_cast<float4*>(gbase + P.off_carry);
-    const Tables<cx2> T{s_twf, s_twi, s_posf, s_posi, s_P, s_Q, s_WI};
+    const Tables<cx2> T{s_twf, s_twi, s_sidx, s_pq1, s_pq2, s_WI};
     const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
 
     Source src;
@@ -619,7 +611,8 @@ bool warp_plan_available(const ResamplerSpec& spec) {
     RtPlan P; std::vector<int> f, i;
     if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &f, &i)) return false;
     const size_t per_group = (size_t)spec.n_in * 8 + (size_t)spec.n_out * 8 + (size_t)spec.n_out * 4 + 48;
-    return per_group + 80 * 1024 < kSmemMax;     // at least one block in flight next to the tables
+    const size_t tables = ((size_t)P.twf_len + P.twi_len) * 8 + (size_t)P.split_len * 56 + 512;
+    return per_group + tables < kSmemMax;        // at least one block in flight next to the tables
 }
 
 cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
@@ -634,10 +627,12 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     } else if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
     std::vector<uint16_t> pf(P.N), pi_(P.M);
     build_pos_tables(fwd, inv, P.N, P.M, pf.data(), pi_.data());
-    P.split_c = choose_split_stride(P.N, P.M, P.nkeep, pf.data(), pi_.data());
     std::vector<float2> Pt(P.nkeep), Qt(P.nkeep), WI(P.M / 2 + 1), twf(P.twf_len), twi(P.twi_len);
     build_split_tables(P.N, P.M, P.nkeep, spec.filt_re.data(), spec.filt_im.data(), Pt.data(), Qt.data(), WI.data());
     build_twiddles(P, twf.data(), twi.data());
+    // bank groups: 8 lanes of 16-byte elements in two-stream mode (compile-time plans), 16 lanes of 8-byte ones otherwise
+    SplitLayout SL;
+    build_split_layout(P.N, P.M, P.nkeep, pf.data(), pi_.data(), Pt.data(), Qt.data(), WI.data(), rs->ct_index >= 0 ? 8 : 16, &SL);
     auto up = [](const void* h, size_t bytes, void** d) -> cudaError_t {
         cudaError_t e = cudaMalloc(d, bytes);
         if (e != cudaSuccess) return e;
@@ -646,11 +641,10 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     cudaError_t e;
     if ((e = up(twf.data(), twf.size() * 8, (void**)&rs->f_twf)) != cudaSuccess) return e;
     if ((e = up(twi.data(), twi.size() * 8, (void**)&rs->f_twi)) != cudaSuccess) return e;
-    if ((e = up(pf.data(), pf.size() * 2, (void**)&rs->f_pos_f)) != cudaSuccess) return e;
-    if ((e = up(pi_.data(), pi_.size() * 2, (void**)&rs->f_pos_i)) != cudaSuccess) return e;
-    if ((e = up(Pt.data(), Pt.size() * 8, (void**)&rs->f_P)) != cudaSuccess) return e;
-    if ((e = up(Qt.data(), Qt.size() * 8, (void**)&rs->f_Q)) != cudaSuccess) return e;
-    if ((e = up(WI.data(), WI.size() * 8, (void**)&rs->f_WI)) != cudaSuccess) return e;
+    if ((e = up(SL.sidx.data(), SL.sidx.size() * 16, (void**)&rs->f_sidx)) != cudaSuccess) return e;
+    if ((e = up(SL.pq1.data(), SL.pq1.size() * 16, (void**)&rs->f_pq1)) != cudaSuccess) return e;
+    if ((e = up(SL.pq2.data(), SL.pq2.size() * 16, (void**)&rs->f_pq2)) != cudaSuccess) return e;
+    if ((e = up(SL.wi.data(), SL.wi.size() * 8, (void**)&rs->f_WI)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&rs->f_counter, sizeof(unsigned long long))) != cudaSuccess) return e;
     static_assert(sizeof(RtPlan) <= sizeof(rs->plan_blob), "plan blob too small");
     memcpy(rs->plan_blob, &P, sizeof(P));
@@ -659,9 +653,9 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
 }
 
 void warp_tables_free(ResamplerDev* rs) {
-    void* ptrs[] = {rs->f_twf, rs->f_twi, rs->f_pos_f, rs->f_pos_i, rs->f_P, rs->f_Q, rs->f_WI, rs->f_counter};
+    void* ptrs[] = {rs->f_twf, rs->f_twi, rs->f_sidx, rs->f_pq1, rs->f_pq2, rs->f_WI, rs->f_counter};
     for (void* p : ptrs) if (p) cudaFree(p);
-    rs->f_twf = rs->f_twi = rs->f_P = rs->f_Q = rs->f_WI = nullptr; rs->f_pos_f = rs->f_pos_i = nullptr; rs->f_counter = nullptr;
+    rs->f_twf = rs->f_twi = rs->f_WI = nullptr; rs->f_sidx = nullptr; rs->f_pq1 = rs->f_pq2 = nullptr; rs->f_counter = nullptr;
     rs->fast = false;
 }
 
@@ -691,7 +685,7 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     P.src_seg = src_seg; P.hop = hop; P.nseg = nseg; P.last_start = last_start; P.rows_total = rows_total; P.row_first = row_first; P.seg = seg;
     P.out_len = (uint32_t)(resampled_len < seg ? resampled_len : seg);
     P.out = d_out;
-    P.twf = rs.f_twf; P.twi = rs.f_twi; P.Pt = rs.f_P; P.Qt = rs.f_Q; P.WI = rs.f_WI; P.pos_f = rs.f_pos_f; P.pos_i = rs.f_pos_i;
+    P.twf = rs.f_twf; P.twi = rs.f_twi; P.WI = rs.f_WI; P.sidx = rs.f_sidx; P.pq1 = rs.f_pq1; P.pq2 = rs.f_pq2;
     P.counter = rs.f_counter;
     P.nblk = (P.out_len + rs.n_out - 1) / rs.n_out;
     if (P.nblk == 0) P.nblk = 1;
@@ -703,16 +697,18 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     const int max_threads = dual ? ct_plan_dual_threads(rs.ct_index) : kMaxThreads;
     P.dual = dual ? 1 : 0;
     P.off_twi = a16((size_t)PL.twf_len * esz);
-    P.off_posf = P.off_twi + a16((size_t)PL.twi_len * esz);
-    P.off_posi = P.off_posf + a16((size_t)PL.N * 2);
-    P.off_P = P.off_posi + a16((size_t)PL.M * 2);
-    P.off_Q = P.off_P + a16((size_t)PL.nkeep * 8);       // split tables stay float2 in both modes
-    P.off_WI = P.off_Q + a16((size_t)PL.nkeep * 8);
-    P.off_items = P.off_WI + a16((size_t)(PL.M / 2 + 1) * 8);
+    P.off_sidx = P.off_twi + a16((size_t)PL.twi_len * esz);
+    P.off_pq1 = P.off_sidx + a16((size_t)PL.split_len * 16);       // split tables have the same layout in both modes
+    P.off_pq2 = P.off_pq1 + a16((size_t)PL.split_len * 16);
+    P.off_WI = P.off_pq2 + a16((size_t)PL.split_len * 16);
+    P.off_items = P.off_WI + a16((size_t)PL.split_len * 8);
     P.tables = P.off_items + a16((size_t)kMaxGroups * 8);
     P.off_B = a16((size_t)PL.N * esz);
     P.off_carry = P.off_B + a16((size_t)PL.M * esz);
     P.per_group = P.off_carry + a16((size_t)(PL.M / 2) * esz);
+#ifdef BB_K2W_FAKE_CARRY        // timing experiment only (wrong results): the carry aliases A, one more group fits
+    P.per_group = P.off_carry; P.off_carry = 0;
+#endif
     if (P.tables + P.per_group > kSmemMax) {
         if (!dual) return cudaErrorInvalidConfiguration;
         // does not fit with two streams: one stream per group

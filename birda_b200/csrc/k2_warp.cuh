@@ -16,6 +16,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <utility>
 #include <vector>
 #include "fft_butterflies.cuh"
 
@@ -93,7 +94,7 @@ struct RtPlan {
     int nf, ni;
     RtStage f[kMaxStages], i[kMaxStages];
     int twf_len, twi_len;        // compact twiddle table sizes (float2 entries)
-    int split_c;                 // the split pass visits k = (idx * split_c) mod (M/2+1): spreads its scattered accesses over the banks
+    int split_len;               // pairs (k, M-k) the split pass visits = M/2 + 1 (order and addresses come from a host-built table)
 };
 
 // shared-memory storage of one element: float2 for a single stream, float4 (re0, re1, im0, im1) for two
@@ -208,10 +209,18 @@ BB_UNROLL_N(BB_K2W_UNROLL)
     }
 }
 
+// Split-pass entry of one (k, M-k) pair, built on the host (build_split_layout): the positions of the four forward
+// results it reads and of the two inverse inputs it writes (digit reversal folded in), plus flags.
+//   x = posA(Z[k]) | posA(Z[N-k]) << 16     y = posA(Z[k2]) | posA(Z[N-k2]) << 16     z = posB(k) | posB(k2) << 16
+//   w = flags: 1 = Y(k) present (k < nkeep), 2 = Y(k2) present, 4 = k == 0 (DC / Nyquist are real), 8 = write Z'(k2)
+constexpr unsigned kSplitHasK = 1u, kSplitHasK2 = 2u, kSplitDc = 4u, kSplitStore2 = 8u;
+
 template <class C> struct Tables {
     using T = typename Mem<C>::T;
-    const T* twf; const T* twi; const uint16_t* pos_f; const uint16_t* pos_i;
-    const float2* Pt; const float2* Qt; const float2* WI;     // compact: broadcast to the stream(s) at load time
+    const T* twf; const T* twi;
+    const uint4* sidx;                       // [split_len]
+    const float4* pq1; const float4* pq2;    // [split_len] (P[k], Q[k]) and (P[k2], Q[k2]); broadcast to the stream(s) at load time
+    const float2* WI;                        // [split_len] exp(+i pi k / M)
 };
 
 // ---- fused split / filter / re-bin / inverse pack:  A (digit-reversed forward result) -> B
@@ -219,35 +228,35 @@ template <class C> struct Tables {
 //   Z'(k) = Y(k) + conj(Y(M-k)) + i wi[k] (Y(k) - conj(Y(M-k)))
 template <class C>
 BB_HD void split_pass(const typename Mem<C>::T* __restrict__ A, typename Mem<C>::T* __restrict__ B, const Tables<C>& T,
-                      int N, int M, int nkeep, int split_c, int lane, int nl) {
-    const int half = M / 2, L = half + 1;
-    int k = (int)(((long long)lane * split_c) % L);
-    const int step = (int)(((long long)nl * split_c) % L);
+                      int L, int lane, int nl) {
 BB_UNROLL_N(BB_K2W_UNROLL)
-    for (int idx = lane; idx <= half; idx += nl, k = (k + step >= L) ? k + step - L : k + step) {
-        const int k2 = M - k;
+    for (int idx = lane; idx < L; idx += nl) {
+        const uint4 e = T.sidx[idx];
+        const unsigned fl = e.w;
         C yk = czero<C>(), yk2 = czero<C>();
-        if (k < nkeep) {
-            const C zk = Mem<C>::ld(A + T.pos_f[k == N ? 0 : k]), zn = cconj(Mem<C>::ld(A + T.pos_f[k == 0 ? 0 : N - k]));
-            yk = cadd(cmul(Mem<C>::bcast(T.Pt[k]), zk), cmul(Mem<C>::bcast(T.Qt[k]), zn));
+        if (fl & kSplitHasK) {
+            const float4 pq = T.pq1[idx];
+            const C zk = Mem<C>::ld(A + (e.x & 0xffffu)), zn = cconj(Mem<C>::ld(A + (e.x >> 16)));
+            yk = cadd(cmul(Mem<C>::bcast(make_float2(pq.x, pq.y)), zk), cmul(Mem<C>::bcast(make_float2(pq.z, pq.w)), zn));
         }
-        if (k2 < nkeep) {
-            const C zk = Mem<C>::ld(A + T.pos_f[k2 == N ? 0 : k2]), zn = cconj(Mem<C>::ld(A + T.pos_f[N - k2]));
-            yk2 = cadd(cmul(Mem<C>::bcast(T.Pt[k2]), zk), cmul(Mem<C>::bcast(T.Qt[k2]), zn));
+        if (fl & kSplitHasK2) {
+            const float4 pq = T.pq2[idx];
+            const C zk = Mem<C>::ld(A + (e.y & 0xffffu)), zn = cconj(Mem<C>::ld(A + (e.y >> 16)));
+            yk2 = cadd(cmul(Mem<C>::bcast(make_float2(pq.x, pq.y)), zk), cmul(Mem<C>::bcast(make_float2(pq.z, pq.w)), zn));
         }
-        if (k == 0) {                                   // DC / Nyquist are real (realfft ignores their imag)
+        if (fl & kSplitDc) {                            // DC / Nyquist are real (realfft ignores their imag)
             yk = Cx<C>::make(Cx<C>::re(yk), kzero(typename Cx<C>::K()));
             yk2 = Cx<C>::make(Cx<C>::re(yk2), kzero(typename Cx<C>::K()));
         }
-        const C wi = Mem<C>::bcast(T.WI[k]);
+        const C wi = Mem<C>::bcast(T.WI[idx]);
         {
-            const C e = cadd(yk, cconj(yk2)), o = cmul(wi, csub(yk, cconj(yk2)));
-            Mem<C>::st(B + T.pos_i[k], Cx<C>::make(ksub(Cx<C>::re(e), Cx<C>::im(o)), kadd(Cx<C>::im(e), Cx<C>::re(o))));
+            const C ev = cadd(yk, cconj(yk2)), o = cmul(wi, csub(yk, cconj(yk2)));
+            Mem<C>::st(B + (e.z & 0xffffu), Cx<C>::make(ksub(Cx<C>::re(ev), Cx<C>::im(o)), kadd(Cx<C>::im(ev), Cx<C>::re(o))));
         }
-        if (k != 0 && k2 != k) {
+        if (fl & kSplitStore2) {
             const C wi2 = Cx<C>::make(kneg(Cx<C>::re(wi)), Cx<C>::im(wi));    // exp(i pi (M-k)/M) = -conj(wi)
-            const C e = cadd(yk2, cconj(yk)), o = cmul(wi2, csub(yk2, cconj(yk)));
-            Mem<C>::st(B + T.pos_i[k2], Cx<C>::make(ksub(Cx<C>::re(e), Cx<C>::im(o)), kadd(Cx<C>::im(e), Cx<C>::re(o))));
+            const C ev = cadd(yk2, cconj(yk)), o = cmul(wi2, csub(yk2, cconj(yk)));
+            Mem<C>::st(B + (e.z >> 16), Cx<C>::make(ksub(Cx<C>::re(ev), Cx<C>::im(o)), kadd(Cx<C>::im(ev), Cx<C>::re(o))));
         }
     }
 }
@@ -283,7 +292,7 @@ BB_HD void forward_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typ
     for (int t = 1; t < P.nf; ++t)
         ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R, C>(A, T.twf, P.f[t], lane, nl))) });
     before_split();
-    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.N, P.M, P.nkeep, P.split_c, lane, nl); });
+    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.split_len, lane, nl); });
 }
 // inverse half: in-place DIT in B -> overlap-add with the carry -> sink
 template <class C, class Exec, class Sink>
@@ -366,7 +375,7 @@ template <class PL, class C, class Exec, int T> struct CtInvMid {
 };
 
 template <class PL, class C, class Exec, class Loader, class BeforeSplit>
-BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, int split_c, typename Mem<C>::T* A, typename Mem<C>::T* B, const Loader& ld,
+BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B, const Loader& ld,
                            BeforeSplit&& before_split) {
     using S0 = typename PL::template FwdStage<0>;
     loader_pick(ld, [&](const auto& l) {
@@ -374,7 +383,7 @@ BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, int split_c, type
     }, 0);
     CtFwdRest<PL, C, Exec, 1>::run(ex, A, T.twf);
     before_split();
-    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::N, PL::M, PL::NKEEP, split_c, lane, nl); });
+    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::M / 2 + 1, lane, nl); });
 }
 template <class PL, class C, class Exec, class Sink>
 BB_HD void inverse_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry, const Sink& sink) {
@@ -383,9 +392,9 @@ BB_HD void inverse_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::
     ex.each([&](int lane, int nl) { dit_last<SL::radix, C>(B, T.twi, SL{}, carry, sink, lane, nl); });
 }
 template <class PL, class C, class Exec, class Loader, class Sink, class AfterSplit>
-BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, int split_c, typename Mem<C>::T* A, typename Mem<C>::T* B,
+BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
                             typename Mem<C>::T* carry, const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
-    forward_half_ct<PL, C>(ex, T, split_c, A, B, ld, [] {});
+    forward_half_ct<PL, C>(ex, T, A, B, ld, [] {});
     after_split();
     inverse_half_ct<PL, C>(ex, T, B, carry, sink);
 }
@@ -467,7 +476,7 @@ inline bool build_plan(int N, int M, int nkeep, RtPlan* P, std::vector<int>* fwd
 inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const std::vector<int>* fwd, const std::vector<int>* inv) {
     if (M % 2 != 0 || N >= 65536 || M >= 65536) return false;
     if ((int)fwd->size() > kMaxStages || (int)inv->size() > kMaxStages || inv->empty() || inv->back() % 2) return false;
-    P->N = N; P->M = M; P->nkeep = nkeep; P->half_in = (N + 1) / 2;
+    P->N = N; P->M = M; P->nkeep = nkeep; P->half_in = (N + 1) / 2; P->split_len = M / 2 + 1;
     P->nf = (int)fwd->size(); P->ni = (int)inv->size();
     int span = N, off = 0;
     for (int t = 0; t < P->nf; ++t) {
@@ -531,29 +540,92 @@ inline void build_pos_tables(const std::vector<int>& fwd, const std::vector<int>
     }
 }
 
-// Pick the split-pass stride: odd, coprime with L = M/2+1, minimising 16-byte bank-quad collisions of the
-// six scattered accesses (4 reads of A through pos_f, 2 writes of B through pos_i) per quarter-warp.
-inline int choose_split_stride(int N, int M, int nkeep, const uint16_t* pos_f, const uint16_t* pos_i) {
+// ---- split-pass layout: visiting order of the (k, M-k) pairs and their addresses
+// The six scattered accesses of a pair (four reads of A through the forward digit reversal, two writes of B through
+// the inverse one) are served `group` lanes at a time (128 bytes of banks: 8 lanes of 16-byte elements, 16 lanes of
+// 8-byte ones); a group is conflict-free when, for each of the six, its lanes hit distinct residues mod `group`.
+// The order is built greedily group by group and polished by pair swaps (deterministic); a plain stride walk left
+// ~40 % extra wavefronts on 1029/1120, this leaves ~14 %.
+struct SplitLayout {
+    std::vector<uint4> sidx; std::vector<float4> pq1, pq2; std::vector<float2> wi;
+    int extra_wavefronts = 0;      // residual conflicts of the chosen order (diagnostic)
+};
+
+inline void build_split_layout(int N, int M, int nkeep, const uint16_t* pos_f, const uint16_t* pos_i,
+                               const float2* Pt, const float2* Qt, const float2* WI, int group, SplitLayout* out) {
     const int L = M / 2 + 1;
-    auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
-    long best_cost = -1; int best_c = 1;
-    for (int c = 1; c < 128 && c < L; c += 2) {
-        if (gcd(c, L) != 1) continue;
-        long cost = 0;
-        for (int i0 = 0; i0 < L; i0 += 8) {
-            int cnt[6][8] = {{0}};
-            for (int i = i0; i < i0 + 8 && i < L; ++i) {
-                const int k = (int)(((long long)i * c) % L), k2 = M - k;
-                if (k < nkeep) { cnt[0][pos_f[k == N ? 0 : k] & 7]++; cnt[1][pos_f[k == 0 ? 0 : N - k] & 7]++; }
-                if (k2 < nkeep) { cnt[2][pos_f[k2 == N ? 0 : k2] & 7]++; cnt[3][pos_f[N - k2] & 7]++; }
-                cnt[4][pos_i[k] & 7]++;
-                if (k != 0 && k2 != k) cnt[5][pos_i[k2 % M] & 7]++;
-            }
-            for (auto& a : cnt) { int mx = 0; for (int v : a) mx = v > mx ? v : mx; cost += mx; }
-        }
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+    struct Item { int v[6]; unsigned flags; };
+    std::vector<Item> it(L);
+    for (int k = 0; k < L; ++k) {
+        const int k2 = M - k;
+        Item& e = it[k];
+        for (int& x : e.v) x = -1;
+        e.flags = 0;
+        if (k < nkeep) { e.v[0] = pos_f[k == N ? 0 : k]; e.v[1] = pos_f[k == 0 ? 0 : N - k]; e.flags |= kSplitHasK; }
+        if (k2 < nkeep) { e.v[2] = pos_f[k2 == N ? 0 : k2]; e.v[3] = pos_f[N - k2]; e.flags |= kSplitHasK2; }
+        e.v[4] = pos_i[k];
+        if (k == 0) e.flags |= kSplitDc;
+        if (k != 0 && k2 != k) { e.v[5] = pos_i[k2]; e.flags |= kSplitStore2; }
     }
-    return best_c;
+    const int G = group;
+    auto group_cost = [&](const int* g, int n) {
+        int c = 0;
+        for (int a = 0; a < 6; ++a) {
+            int cnt[16] = {0}, mx = 0;
+            for (int i = 0; i < n; ++i) { const int p = it[g[i]].v[a]; if (p >= 0) { const int r = ++cnt[p % G]; mx = r > mx ? r : mx; } }
+            if (mx > 1) c += mx - 1;
+        }
+        return c;
+    };
+    // greedy: fill one group at a time with the pair that collides least with what the group already holds
+    std::vector<int> order; order.reserve(L);
+    std::vector<char> used(L, 0);
+    int left = L;
+    while (left > 0) {
+        bool seen[6][16] = {{false}};
+        for (int n = 0; n < G && left > 0; ++n) {
+            int best = -1, bc = 99;
+            for (int i = 0; i < L && bc > 0; ++i) {
+                if (used[i]) continue;
+                int c = 0;
+                for (int a = 0; a < 6; ++a) if (it[i].v[a] >= 0 && seen[a][it[i].v[a] % G]) ++c;
+                if (c < bc) { bc = c; best = i; }
+            }
+            used[best] = 1; --left; order.push_back(best);
+            for (int a = 0; a < 6; ++a) if (it[best].v[a] >= 0) seen[a][it[best].v[a] % G] = true;
+        }
+    }
+    // polish: swap pairs between a conflicting group and a random other one when that does not raise the cost
+    const int ng = (L + G - 1) / G;
+    auto gsize = [&](int g) { return g + 1 < ng ? G : L - g * G; };
+    std::vector<int> cost(ng);
+    int total = 0;
+    for (int g = 0; g < ng; ++g) { cost[g] = group_cost(&order[(size_t)g * G], gsize(g)); total += cost[g]; }
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
+    auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); };
+    for (int iter = 0; iter < 150000 && total > 0; ++iter) {
+        int g1 = (int)(next() % ng);
+        for (int tries = 0; tries < 8 && cost[g1] == 0; ++tries) g1 = (int)(next() % ng);
+        if (cost[g1] == 0) continue;
+        const int g2 = (int)(next() % ng);
+        if (g1 == g2) continue;
+        const int i1 = g1 * G + (int)(next() % gsize(g1)), i2 = g2 * G + (int)(next() % gsize(g2));
+        std::swap(order[i1], order[i2]);
+        const int c1 = group_cost(&order[(size_t)g1 * G], gsize(g1)), c2 = group_cost(&order[(size_t)g2 * G], gsize(g2));
+        if (c1 + c2 <= cost[g1] + cost[g2]) { total += c1 + c2 - cost[g1] - cost[g2]; cost[g1] = c1; cost[g2] = c2; }
+        else std::swap(order[i1], order[i2]);
+    }
+    out->extra_wavefronts = total;
+    out->sidx.resize(L); out->pq1.resize(L); out->pq2.resize(L); out->wi.resize(L);
+    for (int idx = 0; idx < L; ++idx) {
+        const int k = order[idx], k2 = M - k;
+        const Item& e = it[k];
+        auto u = [](int p) { return (unsigned)(p < 0 ? 0 : p); };
+        out->sidx[idx] = make_uint4(u(e.v[0]) | (u(e.v[1]) << 16), u(e.v[2]) | (u(e.v[3]) << 16), u(e.v[4]) | (u(e.v[5]) << 16), e.flags);
+        out->pq1[idx] = (e.flags & kSplitHasK) ? make_float4(Pt[k].x, Pt[k].y, Qt[k].x, Qt[k].y) : make_float4(0.f, 0.f, 0.f, 0.f);
+        out->pq2[idx] = (e.flags & kSplitHasK2) ? make_float4(Pt[k2].x, Pt[k2].y, Qt[k2].x, Qt[k2].y) : make_float4(0.f, 0.f, 0.f, 0.f);
+        out->wi[idx] = WI[k];
+    }
 }
 
 // P = A + B, Q = A - B with A = 0.5 Hf, B = -0.5 i exp(-i pi k / N) Hf;  WI[k] = exp(+i pi k / M)

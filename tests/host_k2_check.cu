@@ -34,7 +34,6 @@ static int check_impl(int N, int M, int nl) {
     } else if (!build_plan(N, M, NKEEP, &P, &fwd, &inv)) { printf("N=%d M=%d: no plan (generic kernel)\n", N, M); return 0; }
     std::vector<uint16_t> pos_f(N), pos_i(M);
     build_pos_tables(fwd, inv, N, M, pos_f.data(), pos_i.data());
-    P.split_c = choose_split_stride(N, M, NKEEP, pos_f.data(), pos_i.data());
     srand(1234 + N);
     std::vector<double> h(N);
     for (int n = 0; n < N; ++n) h[n] = (rand() / (double)RAND_MAX - 0.5) * exp(-0.5 * pow((n - N / 2) / (N / 8.0), 2)) / N;
@@ -46,7 +45,9 @@ static int check_impl(int N, int M, int nl) {
     build_split_tables(N, M, NKEEP, fre.data(), fim.data(), Pt.data(), Qt.data(), WI.data());
     build_twiddles(P, twf.data(), twi.data());
     auto twf_e = expand_table<C>(twf), twi_e = expand_table<C>(twi);
-    Tables<C> T{twf_e.data(), twi_e.data(), pos_f.data(), pos_i.data(), Pt.data(), Qt.data(), WI.data()};
+    SplitLayout SL;
+    build_split_layout(N, M, NKEEP, pos_f.data(), pos_i.data(), Pt.data(), Qt.data(), WI.data(), NS == 2 ? 8 : 16, &SL);
+    Tables<C> T{twf_e.data(), twi_e.data(), SL.sidx.data(), SL.pq1.data(), SL.pq2.data(), SL.wi.data()};
 
     const int NB = 3;
     std::vector<float> x(NB * N), x2(NB * N);
@@ -67,7 +68,7 @@ static int check_impl(int N, int M, int nl) {
             if constexpr (NS == 1) { out[b * M + 2 * n] = y.x; out[b * M + 2 * n + 1] = y.y; }
             else { out[b * M + 2 * n] = y.re.x; out[b * M + 2 * n + 1] = y.im.x; out2[b * M + 2 * n] = y.re.y; out2[b * M + 2 * n + 1] = y.im.y; }
         };
-        if constexpr (kCt) process_block_ct<CT, C>(HostExec{nl}, T, P.split_c, A.data(), B.data(), carry.data(), loader, sink, [] {});
+        if constexpr (kCt) process_block_ct<CT, C>(HostExec{nl}, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
         else process_block<C>(HostExec{nl}, P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
     }
     double worst = 0;
@@ -95,7 +96,7 @@ static int check_impl(int N, int M, int nl) {
     for (int r : fwd) printf(" %d", r);
     printf(" ] inv[");
     for (int r : inv) printf(" %d", r);
-    printf(" ] c=%d  rel err %.3e\n", P.split_c, worst);
+    printf(" ] split conflicts %d  rel err %.3e\n", SL.extra_wavefronts, worst);
     return worst < 5e-6 ? 0 : 1;
 }
 
