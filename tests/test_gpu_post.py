@@ -57,6 +57,21 @@ def test_post_plain(ctx, classes, act):
     assert sum(len(r) for r in ref) > 50
 
 
+@pytest.mark.parametrize("classes,act", [(6522, b.ACT_SIGMOID), (14795, b.ACT_SOFTMAX), (1001, b.ACT_SIGMOID)])
+def test_post_many_rows(ctx, classes, act):
+    """>= 1024 rows take the 64-thread-CTA variant of K3 (one launch over a whole file's windows); the row stride of
+    C = 6522 / 14795 / 1001 floats also walks through every 16-byte misalignment of the row start."""
+    rows = 1200
+    x = synth_logits(classes + 1, rows, classes)
+    if act == b.ACT_SOFTMAX:
+        x[6:, :] *= 3.0
+    cfg = b.PostConfig(activation=act, min_confidence=0.1)
+    got = gpu_post(ctx, x, rows, cfg)
+    ref = opost.post_process(x, rows, act, 0.1, 5)
+    compare(got, ref, opost.activate(x, act), 0.1)
+    assert sum(len(r) for r in ref) > 500
+
+
 def test_post_adversarial_rows_exact(ctx):
     x = synth_logits(1, 8, 6522)
     got = gpu_post(ctx, x, 8, b.PostConfig(min_confidence=0.1))

@@ -41,3 +41,9 @@ for _ in range(iters):
 e1.record(); torch.cuda.synchronize()
 print(f"{config}: {minutes} min audio, {r.nseg} windows: front end {e0.elapsed_time(e1)/iters:.3f} ms/iter "
       f"-> {minutes/60/(e0.elapsed_time(e1)/iters/1e3):.1f} audio-h/s")
+e0.record()
+for _ in range(iters):
+    ctx.post_run_device(scores.data_ptr(), rows, C, rows, cfg, None, None, d_idx.data_ptr(), d_conf.data_ptr(), d_cnt.data_ptr())
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / iters
+print(f"{config}: post {rows} x {C}: {ms*1e3:.1f} us/iter -> {rows*C*4/ms/1e6:.0f} GB/s")
