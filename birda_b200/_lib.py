@@ -38,6 +38,11 @@ class PostCfg(C.Structure):
                 ("range_threshold", C.c_float), ("keep_unmatched", C.c_int32), ("rerank", C.c_int32)]
 
 
+class MelSpecCfg(C.Structure):
+    _fields_ = [("n_fft", C.c_uint32), ("hop", C.c_uint32), ("n_frames", C.c_uint32), ("n_mels", C.c_uint32),
+                ("power", C.c_float), ("log_mode", C.c_int32), ("log_eps", C.c_float)]
+
+
 class PipelineCfg(C.Structure):
     _fields_ = [("target_rate", C.c_uint32), ("segment_duration", C.c_float), ("overlap", C.c_float),
                 ("batch_size", C.c_uint32), ("bat_mode", C.c_int32), ("post", PostCfg),
@@ -95,6 +100,10 @@ SIGNATURES = {
                                             C.c_uint64, u64p, u64p, u32p]),
     "bb_pipeline_process_wav": (C.c_int32, [vp, C.c_char_p, C.c_uint64, C.POINTER(DetectionC), C.c_uint64, u64p, u64p, u32p]),
     "bb_dense_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_int32, vp]),
+    "bb_melspec_create": (C.c_int32, [vp, C.POINTER(MelSpecCfg), f32p, f32p, C.POINTER(vp)]),
+    "bb_melspec_destroy": (None, [vp]),
+    "bb_melspec_info": (C.c_int32, [vp, u32p, u32p, u32p]),
+    "bb_melspec_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp]),
     "bb_dev_alloc": (C.c_int32, [vp, C.c_uint64, C.POINTER(vp)]),
     "bb_dev_free": (None, [vp, vp]),
     "bb_memcpy_h2d": (C.c_int32, [vp, vp, vp, C.c_uint64]),

@@ -9,7 +9,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import BirdaError, PostCfg, check, lib
+from ._lib import BirdaError, MelSpecCfg, PostCfg, check, lib
 
 FMT_S16, FMT_S32, FMT_F32 = 1, 2, 3
 ACT_NONE, ACT_SIGMOID, ACT_SOFTMAX = 0, 1, 2
@@ -283,6 +283,46 @@ class FrontEndPlan:
     def close(self):
         if self._h:
             lib.bb_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MelSpec:
+    """Spectrogram prefix on the device (``bb_melspec``): framed STFT power + tcgen05 mel projection.
+    ``window``: [n_fft] f32, ``mel_weights``: [n_mels, n_fft/2 + 1] f32 (host arrays, copied)."""
+
+    def __init__(self, ctx: Context, n_fft: int, hop: int, n_frames: int, window: np.ndarray, mel_weights: np.ndarray,
+                 power: float = 2.0, log_mode: int = 0, log_eps: float = 1e-6):
+        self.ctx = ctx
+        w = np.ascontiguousarray(window, dtype=np.float32)
+        mw = np.ascontiguousarray(mel_weights, dtype=np.float32)
+        if w.shape != (n_fft,) or mw.ndim != 2 or mw.shape[1] != n_fft // 2 + 1:
+            raise ValueError("window must be [n_fft] and mel_weights [n_mels, n_fft/2 + 1]")
+        self.n_fft, self.hop, self.n_frames, self.n_mels = n_fft, hop, n_frames, int(mw.shape[0])
+        cfg = MelSpecCfg(n_fft, hop, n_frames, self.n_mels, power, log_mode, log_eps)
+        self._h = C.c_void_p()
+        check(lib.bb_melspec_create(ctx.handle, C.byref(cfg), w.ctypes.data_as(_lib.f32p), mw.ctypes.data_as(_lib.f32p),
+                                    C.byref(self._h)), ctx.handle)
+        ctx._plans.add(self)
+
+    def info(self) -> Tuple[int, int, int]:
+        """(first bin with mel weight, bins with mel weight, GEMM K after padding to 32)."""
+        a, b_, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib.bb_melspec_info(self._h, C.byref(a), C.byref(b_), C.byref(c)), self.ctx.handle)
+        return a.value, b_.value, c.value
+
+    def run(self, d_segments: int, rows: int, samples: int, d_out: int) -> None:
+        """d_segments: device [rows, samples] f32; d_out: device [rows, n_mels, n_frames] f32.  Asynchronous."""
+        check(lib.bb_melspec_run(self._h, C.c_void_p(d_segments), rows, samples, C.c_void_p(d_out)), self.ctx.handle)
+
+    def close(self):
+        if self._h:
+            lib.bb_melspec_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

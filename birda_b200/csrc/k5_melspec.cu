@@ -1,0 +1,430 @@
+// K5 — spectrogram prefix of a classifier graph on the device (north_star: "an STFT +
+// mel-filterbank kernel whose mel projection runs on tcgen05 tensor cores").
+//
+//   packed windows [rows, samples] f32 (what K1 / K2 wrote)
+//     -> K5a  stft_power_kernel : frame t = samples [t*hop, t*hop + n_fft) * window, real FFT of length n_fft as a
+//                                 half-length complex FFT in shared memory (the K2 butterflies and stage tables),
+//                                 |X|^power of the bins the mel filters touch -> P [frames, Kpad] f32 (L2-sized chunks)
+//     -> K5b  mel_gemm_kernel   : D[frame, mel] = sum_k P[frame, k] * W[mel, k] on the 5th-gen tensor cores
+//                                 (tcgen05.mma kind::tf32, accumulator in TMEM), run as THREE tf32 products of an
+//                                 error-free hi/lo split (P_hi W_hi + P_lo W_hi + P_hi W_lo, "3xTF32") so that the
+//                                 result carries f32 accuracy; epilogue (tcgen05.ld) applies the log scaling and
+//                                 stores [rows, n_mels, n_frames].
+//
+// The reference has no code for this step (the spectrogram lives inside the ONNX graph, and no file in the
+// reference pins frame length, hop, mel edges or scaling — SURVEY.md §8f-3), so the layer is a general one: window,
+// mel weights and scaling are inputs; parity is against the float64 statement of the layer kept with the tests.
+#include "common.cuh"
+#include "k2_warp.cuh"
+#include <cstring>
+#include <string>
+#include <vector>
+
+struct bb_melspec {
+    bb_ctx* ctx = nullptr;
+    bb_melspec_cfg cfg{};
+    int N = 0;                          // complex FFT length = n_fft / 2
+    uint32_t bin_lo = 0, nb = 0, kpad = 0;    // mel support [bin_lo, bin_lo + nb), padded to a multiple of 32
+    bb::k2w::RtPlan plan{};
+    float2* d_twf = nullptr; uint16_t* d_posf = nullptr; float2* d_wk = nullptr;   // stage twiddles, digit reversal, exp(-i pi k / N)
+    float* d_window = nullptr;
+    float* d_whi = nullptr; float* d_wlo = nullptr;                                 // [n_mels, kpad] tf32 hi / lo parts
+    float* d_P = nullptr; uint64_t p_capacity_frames = 0;                            // [frames (multiple of 128), kpad]
+};
+
+namespace bb {
+namespace {
+
+using namespace bb::k2w;
+
+// ------------------------------------------------------------------------------------------ K5a
+constexpr int kFftThreads = 256;         // 4 groups of 2 warps; a group owns one frame at a time
+constexpr int kFftGroupWarps = 2;
+
+struct FftExec {
+    int glane, nl, bar_id;
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nl) : "memory"); }
+    template <class F> __device__ __forceinline__ void each(F&& f) const { f(glane, nl); sync(); }
+};
+
+struct StftParams {
+    RtPlan plan;
+    const float* x; const float* window; const float2* twf; const uint16_t* posf; const float2* wk;
+    float* P;
+    uint32_t samples, hop, n_frames, n_fft, bin_lo, nb, kpad;
+    uint64_t frame0, nframes;            // flattened frame range of this launch (frame = row * n_frames + t)
+    float power;
+    uint32_t off_posf, off_wk, off_win, tables, per_group;
+};
+
+__global__ void __launch_bounds__(kFftThreads)
+stft_power_kernel(const __grid_constant__ StftParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const RtPlan& PL = p.plan;
+    const int N = PL.N;
+    float2* s_twf = reinterpret_cast<float2*>(smem);
+    uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + p.off_posf);
+    float2* s_wk = reinterpret_cast<float2*>(smem + p.off_wk);
+    float* s_win = reinterpret_cast<float*>(smem + p.off_win);
+    for (int i = threadIdx.x; i < PL.twf_len; i += kFftThreads) s_twf[i] = p.twf[i];
+    for (int i = threadIdx.x; i < N; i += kFftThreads) s_posf[i] = p.posf[i];
+    for (int i = threadIdx.x; i <= N; i += kFftThreads) s_wk[i] = p.wk[i];
+    for (int i = threadIdx.x; i < (int)p.n_fft; i += kFftThreads) s_win[i] = p.window[i];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, group = warp / kFftGroupWarps;
+    constexpr int kGroups = kFftThreads / 32 / kFftGroupWarps;
+    FftExec ex;
+    ex.nl = kFftGroupWarps * 32;
+    ex.glane = (warp - group * kFftGroupWarps) * 32 + (int)(threadIdx.x & 31);
+    ex.bar_id = 1 + group;
+    const int lane = ex.glane, nl = ex.nl;
+    float2* A = reinterpret_cast<float2*>(smem + p.tables + (size_t)group * p.per_group);
+
+    for (uint64_t fi = (uint64_t)blockIdx.x * kGroups + group; fi < p.nframes; fi += (uint64_t)gridDim.x * kGroups) {
+        const uint64_t f = p.frame0 + fi;
+        const uint64_t row = f / p.n_frames;
+        const uint32_t t = (uint32_t)(f - row * p.n_frames);
+        const float* __restrict__ xr = p.x + row * p.samples;
+        const uint32_t s0 = t * p.hop;
+        // z[n] = x[s0 + 2n] w[2n] + i x[s0 + 2n + 1] w[2n + 1], zero past the end of the window
+        auto ld = [&](int n) -> float2 {
+            const uint32_t i0 = s0 + 2u * (uint32_t)n;
+            const float a = i0 < p.samples ? __ldg(xr + i0) : 0.f;
+            const float b = i0 + 1u < p.samples ? __ldg(xr + i0 + 1u) : 0.f;
+            return make_float2(a * s_win[2 * n], b * s_win[2 * n + 1]);
+        };
+        ex.each([&](int l, int n_l) { BB_K2W_RADIX_SWITCH(PL.f[0].radix, (dif_first<R, float2>(A, s_twf, PL.f[0], PL.half_in, ld, l, n_l))) });
+        for (int st = 1; st < PL.nf; ++st)
+            ex.each([&](int l, int n_l) { BB_K2W_RADIX_SWITCH(PL.f[st].radix, (dif_stage<R, float2>(A, s_twf, PL.f[st], l, n_l))) });
+        // bins of the mel support: X[k] = (Z[k] + conj Z[N-k]) / 2 - (i/2) exp(-i pi k / N) (Z[k] - conj Z[N-k])
+        float* __restrict__ Pf = p.P + fi * p.kpad;
+        for (uint32_t j = lane; j < p.kpad; j += nl) {
+            float v = 0.f;
+            if (j < p.nb) {
+                const int k = (int)(p.bin_lo + j);
+                const float2 zk = A[s_posf[k == N ? 0 : k]], zq = A[s_posf[k == 0 ? 0 : N - k]];
+                const float2 zn = make_float2(zq.x, -zq.y);
+                const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y + zn.y);
+                const float dr = 0.5f * (zk.x - zn.x), di = 0.5f * (zk.y - zn.y);
+                const float2 w = s_wk[k];
+                // -i w d = (w.y dr + w.x di) + i (w.y di - w.x dr)
+                const float xr_ = er + (w.y * dr + w.x * di), xi_ = ei + (w.y * di - w.x * dr);
+                const float pw = xr_ * xr_ + xi_ * xi_;
+                v = p.power == 2.0f ? pw : (p.power == 1.0f ? sqrtf(pw) : powf(pw, 0.5f * p.power));
+            }
+            Pf[j] = v;
+        }
+        ex.sync();                       // A is rewritten by the next frame's first stage
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K5b
+constexpr int kBM = 128;                 // frames per tile = UMMA M
+constexpr int kBK = 32;                  // tf32 elements per K chunk = one 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr int kGemmThreads = 160;        // warps 0-3: producers, then epilogue (TMEM lane quarters); warp 4: TMEM owner + MMA issuer
+
+struct GemmParams {
+    const float* P; const float* whi; const float* wlo; float* out;
+    uint32_t kpad, n_mels, n_frames, tmem_cols, idesc;
+    uint64_t frame0, nframes;            // flattened frames of this launch; P row 0 = frame0
+    int32_t log_mode; float log_eps;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        uint32_t done;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// K-major, 128-byte swizzle, rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// error-free split for the tf32 pipe: hi keeps the top 19 bits (sign, exponent, 10 mantissa bits), lo = v - hi exactly
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    lo = v - hi;
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 2)
+mel_gemm_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 1024-byte alignment for the 128-byte swizzle atoms
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = kBM * 128, b_bytes = p.n_mels * 128;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_done;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t nk = p.kpad / kBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
+        mbar_init(&s_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kBM;         // first frame of the tile, relative to frame0
+
+    if (warp < 4) {
+        // ===== producers: global P / W chunks -> hi / lo tiles in the canonical K-major 128B-swizzled layout
+        for (uint32_t kc = 0; kc < nk; ++kc) {
+            const uint32_t s = kc % kStages, ph = (kc / kStages) & 1u;
+            mbar_wait(&s_empty[s], ph ^ 1u);
+            unsigned char* st = smem + (size_t)s * stage_bytes;
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                      // A: 128 rows x 8 pieces of 16 bytes
+                const uint32_t piece = (uint32_t)i * 128u + (uint32_t)tid, r = piece >> 3, c = piece & 7u;
+                const uint64_t fr = tile0 + r;
+                v[i] = fr < p.nframes ? __ldg(reinterpret_cast<const float4*>(p.P + fr * p.kpad + kc * kBK + c * 4))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t piece = (uint32_t)i * 128u + (uint32_t)tid, r = piece >> 3, c = piece & 7u;
+                const uint32_t off = r * 128u + ((c ^ (r & 7u)) << 4);
+                float4 hi, lo;
+                split_tf32(v[i].x, hi.x, lo.x); split_tf32(v[i].y, hi.y, lo.y); split_tf32(v[i].z, hi.z, lo.z); split_tf32(v[i].w, hi.w, lo.w);
+                *reinterpret_cast<float4*>(st + off) = hi;
+                *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
+            }
+            for (uint32_t piece = tid; piece < p.n_mels * 8u; piece += 128u) {   // B: n_mels rows x 8 pieces, hi and lo prepared on the host
+                const uint32_t r = piece >> 3, c = piece & 7u;
+                const uint32_t off = r * 128u + ((c ^ (r & 7u)) << 4);
+                const size_t g = (size_t)r * p.kpad + kc * kBK + c * 4;
+                *reinterpret_cast<float4*>(st + 2 * a_bytes + off) = __ldg(reinterpret_cast<const float4*>(p.whi + g));
+                *reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes + off) = __ldg(reinterpret_cast<const float4*>(p.wlo + g));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+            mbar_arrive(&s_full[s]);
+        }
+        // ===== epilogue: TMEM -> registers -> scaling -> [rows, n_mels, n_frames]
+        mbar_wait(&s_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t fr = tile0 + (uint32_t)(warp * 32 + lane);             // this thread's frame = TMEM lane
+        const bool live = fr < p.nframes;
+        const uint64_t f = p.frame0 + fr;
+        const uint64_t row = f / p.n_frames;
+        const uint32_t t = (uint32_t)(f - row * p.n_frames);
+        float* __restrict__ o = p.out + (row * p.n_mels) * (uint64_t)p.n_frames + t;
+        for (uint32_t c0 = 0; c0 < p.n_mels; c0 += 16) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float v = __uint_as_float(r[j]);
+                    if (p.log_mode == 1) v = logf(v + p.log_eps);
+                    else if (p.log_mode == 2) v = 10.0f * log10f(fmaxf(v, p.log_eps));
+                    o[(uint64_t)(c0 + j) * p.n_frames] = v;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===== MMA issuer: one elected lane
+        if (lane == 0) {
+            for (uint32_t kc = 0; kc < nk; ++kc) {
+                const uint32_t s = kc % kStages, ph = (kc / kStages) & 1u;
+                mbar_wait(&s_full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+#pragma unroll
+                for (uint32_t k4 = 0; k4 < 4; ++k4) {          // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte row
+                    const uint64_t a_hi = umma_desc(base + k4 * 32u), a_lo = umma_desc(base + a_bytes + k4 * 32u);
+                    const uint64_t b_hi = umma_desc(base + 2 * a_bytes + k4 * 32u), b_lo = umma_desc(base + 2 * a_bytes + b_bytes + k4 * 32u);
+                    umma_tf32(tmem, a_hi, b_hi, p.idesc, (kc | k4) != 0u ? 1u : 0u);
+                    umma_tf32(tmem, a_lo, b_hi, p.idesc, 1u);
+                    umma_tf32(tmem, a_hi, b_lo, p.idesc, 1u);
+                }
+                umma_commit(&s_empty[s]);                      // the stage is free once these MMAs have read it
+            }
+            umma_commit(&s_done);                              // accumulator complete
+        }
+        __syncwarp();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace
+}  // namespace bb
+
+// ------------------------------------------------------------------------------------------ C ABI
+using namespace bb;
+
+extern "C" {
+
+void bb_melspec_destroy(bb_melspec* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    void* ptrs[] = {m->d_twf, m->d_posf, m->d_wk, m->d_window, m->d_whi, m->d_wlo, m->d_P};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    delete m;
+}
+
+int32_t bb_melspec_create(bb_ctx* c, const bb_melspec_cfg* cfg, const float* window, const float* mel_weights, bb_melspec** out) {
+    if (!c || !cfg || !window || !mel_weights || !out) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    const uint32_t nfft = cfg->n_fft;
+    if (nfft < 256 || nfft > 4096 || (nfft & (nfft - 1)) != 0) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "n_fft must be a power of two in [256, 4096]");
+    if (cfg->hop == 0 || cfg->n_frames == 0) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "hop and n_frames must be > 0");
+    if (cfg->n_mels < 16 || cfg->n_mels > 256 || cfg->n_mels % 16 != 0) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "n_mels must be a multiple of 16 in [16, 256]");
+    if (!(cfg->power > 0.f)) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "power must be > 0");
+    if (cfg->log_mode < 0 || cfg->log_mode > 2) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "log_mode must be 0, 1 or 2");
+    bb_melspec* m = new (std::nothrow) bb_melspec();
+    if (!m) BB_SET_ERR(c, BB_ERR_OOM, "out of host memory");
+    m->ctx = c; m->cfg = *cfg; m->N = (int)nfft / 2;
+    const uint32_t bins = nfft / 2 + 1;
+    // support of the mel filters: only those bins are produced and multiplied
+    uint32_t lo = bins, hi = 0;
+    for (uint32_t r = 0; r < cfg->n_mels; ++r)
+        for (uint32_t k = 0; k < bins; ++k)
+            if (mel_weights[(size_t)r * bins + k] != 0.0f) { lo = k < lo ? k : lo; hi = k + 1 > hi ? k + 1 : hi; }
+    if (hi <= lo) { lo = 0; hi = 1; }
+    m->bin_lo = lo; m->nb = hi - lo; m->kpad = (m->nb + 31u) & ~31u;
+    std::vector<int> fwd, inv;
+    if (!k2w::choose_radices(m->N, false, &fwd)) { delete m; BB_SET_ERR(c, BB_ERR_INTERNAL, "no radix plan"); }
+    // only the forward half of the plan is used; the inverse half is filled in to keep the plan well formed
+    if (!k2w::choose_radices(m->N, true, &inv) || !k2w::build_plan_from_radices(m->N, m->N, m->N, &m->plan, &fwd, &inv)) {
+        delete m; BB_SET_ERR(c, BB_ERR_INTERNAL, "no radix plan");
+    }
+    m->plan.half_in = m->N;                                              // no zero padding: every input slot is live
+    std::vector<float2> twf(m->plan.twf_len), twi(m->plan.twi_len), wk(m->N + 1);
+    k2w::build_twiddles(m->plan, twf.data(), twi.data());
+    std::vector<uint16_t> pf(m->N), pi_(m->N);
+    k2w::build_pos_tables(fwd, inv, m->N, m->N, pf.data(), pi_.data());
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k <= m->N; ++k) wk[k] = make_float2((float)cos(-pi * k / m->N), (float)sin(-pi * k / m->N));
+    std::vector<float> whi((size_t)cfg->n_mels * m->kpad, 0.f), wlo((size_t)cfg->n_mels * m->kpad, 0.f);
+    for (uint32_t r = 0; r < cfg->n_mels; ++r)
+        for (uint32_t j = 0; j < m->nb; ++j) {
+            const float w = mel_weights[(size_t)r * bins + lo + j];
+            uint32_t b; memcpy(&b, &w, 4); b &= 0xFFFFE000u;
+            float h; memcpy(&h, &b, 4);
+            whi[(size_t)r * m->kpad + j] = h; wlo[(size_t)r * m->kpad + j] = w - h;
+        }
+    cudaSetDevice(c->device);
+    auto up = [&](const void* h, size_t bytes, void** d) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, bytes);
+        return e != cudaSuccess ? e : cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = up(twf.data(), twf.size() * 8, (void**)&m->d_twf);
+    if (e == cudaSuccess) e = up(pf.data(), pf.size() * 2, (void**)&m->d_posf);
+    if (e == cudaSuccess) e = up(wk.data(), wk.size() * 8, (void**)&m->d_wk);
+    if (e == cudaSuccess) e = up(window, (size_t)nfft * 4, (void**)&m->d_window);
+    if (e == cudaSuccess) e = up(whi.data(), whi.size() * 4, (void**)&m->d_whi);
+    if (e == cudaSuccess) e = up(wlo.data(), wlo.size() * 4, (void**)&m->d_wlo);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("melspec init: ") + cudaGetErrorString(e);
+        bb_melspec_destroy(m);
+        BB_SET_ERR(c, e == cudaErrorMemoryAllocation ? BB_ERR_OOM : BB_ERR_CUDA, msg);
+    }
+    *out = m;
+    return BB_OK;
+}
+
+int32_t bb_melspec_info(const bb_melspec* m, uint32_t* bin_lo, uint32_t* n_bins, uint32_t* k_padded) {
+    if (!m) return BB_ERR_INVALID_ARG;
+    if (bin_lo) *bin_lo = m->bin_lo;
+    if (n_bins) *n_bins = m->nb;
+    if (k_padded) *k_padded = m->kpad;
+    return BB_OK;
+}
+
+int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, uint32_t samples, float* d_out) {
+    if (!m) return BB_ERR_INVALID_ARG;
+    bb_ctx* c = m->ctx;
+    if (rows == 0) return BB_OK;
+    if (!d_segments || !d_out || samples == 0) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null argument");
+    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    const bb_melspec_cfg& cfg = m->cfg;
+    // P is produced and consumed in chunks of whole rows that stay in L2 (<= 64 MB)
+    const uint64_t row_bytes = (uint64_t)cfg.n_frames * m->kpad * 4;
+    uint64_t rows_per_chunk = (64ull << 20) / row_bytes;
+    if (rows_per_chunk == 0) rows_per_chunk = 1;
+    if (rows_per_chunk > rows) rows_per_chunk = rows;
+    const uint64_t cap_frames = ((rows_per_chunk * cfg.n_frames + kBM - 1) / kBM) * kBM;
+    if (cap_frames > m->p_capacity_frames) {
+        if (m->d_P) { BB_CUDA_OK(c, cudaStreamSynchronize(c->stream)); cudaFree(m->d_P); m->d_P = nullptr; m->p_capacity_frames = 0; }
+        BB_CUDA_OK(c, cudaMalloc((void**)&m->d_P, cap_frames * m->kpad * 4));
+        m->p_capacity_frames = cap_frames;
+    }
+    StftParams sp{};
+    sp.plan = m->plan; sp.x = d_segments; sp.window = m->d_window; sp.twf = m->d_twf; sp.posf = m->d_posf; sp.wk = m->d_wk;
+    sp.P = m->d_P; sp.samples = samples; sp.hop = cfg.hop; sp.n_frames = cfg.n_frames; sp.n_fft = cfg.n_fft;
+    sp.bin_lo = m->bin_lo; sp.nb = m->nb; sp.kpad = m->kpad; sp.power = cfg.power;
+    auto a16 = [](size_t x) { return (uint32_t)((x + 15) & ~(size_t)15); };
+    sp.off_posf = a16((size_t)m->plan.twf_len * 8);
+    sp.off_wk = sp.off_posf + a16((size_t)m->N * 2);
+    sp.off_win = sp.off_wk + a16((size_t)(m->N + 1) * 8);
+    sp.tables = sp.off_win + a16((size_t)cfg.n_fft * 4);
+    sp.per_group = a16((size_t)m->N * 8);
+    const size_t fft_smem = sp.tables + (size_t)(kFftThreads / 32 / kFftGroupWarps) * sp.per_group;
+    BB_CUDA_OK(c, cudaFuncSetAttribute(stft_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem));
+    GemmParams gp{};
+    gp.P = m->d_P; gp.whi = m->d_whi; gp.wlo = m->d_wlo; gp.out = d_out;
+    gp.kpad = m->kpad; gp.n_mels = cfg.n_mels; gp.n_frames = cfg.n_frames;
+    gp.tmem_cols = cfg.n_mels <= 32 ? 32 : cfg.n_mels <= 64 ? 64 : cfg.n_mels <= 128 ? 128 : 256;
+    // cute::UMMA::InstrDescriptor: c = F32 (1 << 4), a = b = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+    gp.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((cfg.n_mels >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    gp.log_mode = cfg.log_mode; gp.log_eps = cfg.log_eps;
+    const size_t gemm_smem = (size_t)kStages * (2 * kBM * 128 + 2 * (size_t)cfg.n_mels * 128) + 1024;
+    BB_CUDA_OK(c, cudaFuncSetAttribute(mel_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    for (uint64_t r0 = 0; r0 < rows; r0 += rows_per_chunk) {
+        const uint64_t nr = rows - r0 < rows_per_chunk ? rows - r0 : rows_per_chunk;
+        const uint64_t nframes = nr * cfg.n_frames;
+        sp.frame0 = r0 * cfg.n_frames; sp.nframes = nframes;
+        const uint64_t want = (nframes + 3) / 4;
+        const unsigned grid = (unsigned)(want < (uint64_t)c->sm_count * 4 ? want : (uint64_t)c->sm_count * 4);
+        stft_power_kernel<<<grid, kFftThreads, fft_smem, c->stream>>>(sp);
+        gp.frame0 = sp.frame0; gp.nframes = nframes;
+        mel_gemm_kernel<<<(unsigned)((nframes + kBM - 1) / kBM), kGemmThreads, gemm_smem, c->stream>>>(gp);
+        BB_CUDA_OK(c, cudaGetLastError());
+        c->launches += 2;
+    }
+    return BB_OK;
+}
+
+}  // extern "C"

@@ -274,6 +274,35 @@ int32_t bb_pipeline_process_wav(bb_pipeline*, const char* path, uint64_t piece_f
 int32_t bb_dense_run(bb_ctx*, const float* d_x, uint32_t B, uint32_t K, const float* d_W, const float* d_b, uint32_t N,
                      int32_t activation, float* d_out);
 
+/* ------------------------------------------------------------------------------------------
+ * Spectrogram prefix on the device: framed STFT power + mel projection for classifiers
+ * whose ONNX graph opens with an STFT / mel prefix (manifests/Perch-v2-Models.models.json:15,46; BirdNET v2.4's
+ * in-graph spectrogram layers).  The truncated graph then takes [rows, n_mels, n_frames] f32 through IoBinding.
+ * The reference has no host code for this step and pins none of its parameters, so window, mel weights and
+ * scaling are inputs.  Frame t of a row covers samples [t*hop, t*hop + n_fft) (zero past the end of the row),
+ * is multiplied by `window`, transformed by a real FFT of length n_fft; |X|^power of the bins the mel filters touch
+ * is projected with `mel_weights` on the tcgen05 tensor cores (three tf32 products of an error-free hi/lo split:
+ * f32 accuracy) and scaled: log_mode 0 = linear, 1 = ln(x + log_eps), 2 = 10 log10(max(x, log_eps)).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bb_melspec bb_melspec;
+typedef struct {
+    uint32_t n_fft;      /* power of two, 256..4096                                   */
+    uint32_t hop;        /* frame step in samples                                      */
+    uint32_t n_frames;   /* frames per row                                             */
+    uint32_t n_mels;     /* multiple of 16, 16..256                                    */
+    float    power;      /* 1 = magnitude, 2 = power                                   */
+    int32_t  log_mode;
+    float    log_eps;
+} bb_melspec_cfg;
+/* window: host [n_fft]; mel_weights: host [n_mels, n_fft/2 + 1] row-major.  Both are copied. */
+int32_t bb_melspec_create(bb_ctx*, const bb_melspec_cfg*, const float* window, const float* mel_weights, bb_melspec** out);
+void    bb_melspec_destroy(bb_melspec*);
+/* bins [bin_lo, bin_lo + n_bins) carry non-zero mel weight; the GEMM runs over k_padded = n_bins rounded up to 32 */
+int32_t bb_melspec_info(const bb_melspec*, uint32_t* bin_lo, uint32_t* n_bins, uint32_t* k_padded);
+/* d_segments: device [rows, samples] f32 (the packed tensor of bb_frontend_run); d_out: device [rows, n_mels, n_frames].
+ * Asynchronous on the ctx stream. */
+int32_t bb_melspec_run(bb_melspec*, const float* d_segments, uint32_t rows, uint32_t samples, float* d_out);
+
 /* Device memory helpers for hosts without a CUDA binding of their own (tests, Rust shim) */
 int32_t bb_dev_alloc(bb_ctx*, uint64_t bytes, void** out);
 void    bb_dev_free(bb_ctx*, void*);

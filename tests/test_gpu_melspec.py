@@ -1,0 +1,88 @@
+"""K5 — spectrogram prefix (STFT power + tcgen05 mel projection) through the C ABI against the float64 oracle.
+The reference pins none of this layer's parameters: parity here is against our own statement."""
+import numpy as np
+import pytest
+
+import birda_b200 as b
+from birda_b200.synth import synth_pcm
+from oracle import melspec as om
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 2e-5     # of the row's largest mel energy (f32 FFT + three-product tf32 split; measured ~2e-6)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b.Context(0)
+    yield c
+    c.close()
+
+
+def run_gpu(ctx, seg, n_fft, hop, n_frames, window, mw, **kw):
+    import torch
+    d = torch.from_numpy(seg).cuda()
+    out = torch.full((seg.shape[0], mw.shape[0], n_frames), float("nan"), device="cuda")
+    ms = b.MelSpec(ctx, n_fft, hop, n_frames, window, mw, **kw)
+    ms.run(d.data_ptr(), seg.shape[0], seg.shape[1], out.data_ptr())
+    ctx.sync()
+    info = ms.info()
+    ms.close()
+    return out.cpu().numpy(), info
+
+
+def windows(seed, rows, samples, rate):
+    pcm = synth_pcm(seed, rows * samples / rate, rate, 1).astype(np.float32) / 32768.0
+    return np.ascontiguousarray(pcm[: rows * samples].reshape(rows, samples))
+
+
+@pytest.mark.parametrize("n_fft,hop,n_frames,n_mels,fmin,fmax", [
+    (2048, 278, 511, 96, 0.0, 3000.0),          # BirdNET-v2.4-like low band (narrow support: 129 bins)
+    (1024, 280, 511, 96, 500.0, 15000.0),       # BirdNET-v2.4-like high band
+    (512, 160, 300, 64, 60.0, 16000.0),         # wide support, other sizes
+    (2048, 512, 281, 128, 0.0, 24000.0),        # full band: every bin, K = 1025 -> 1056
+])
+def test_melspec_linear(ctx, n_fft, hop, n_frames, n_mels, fmin, fmax):
+    rate, samples, rows = 48_000, 144_000, 5
+    seg = windows(11, rows, samples, rate)
+    w, mw = om.hann(n_fft), om.mel_filterbank(n_mels, n_fft, rate, fmin, fmax)
+    got, (lo, nb, kpad) = run_gpu(ctx, seg, n_fft, hop, n_frames, w, mw)
+    ref = om.melspec(seg, n_fft, hop, n_frames, w, mw)
+    assert kpad % 32 == 0 and kpad >= nb and np.all(mw[:, :lo] == 0) and np.all(mw[:, lo + nb:] == 0)
+    assert np.isfinite(got).all()
+    scale = np.abs(ref).max(axis=(1, 2), keepdims=True)
+    err = (np.abs(got - ref) / scale).max()
+    assert err <= REL_TOL, err
+
+
+def test_melspec_log_modes_and_magnitude(ctx):
+    rate, samples, rows, n_fft, hop, n_frames = 32_000, 160_000, 3, 1024, 320, 500
+    seg = windows(12, rows, samples, rate)
+    w, mw = om.hann(n_fft), om.mel_filterbank(64, n_fft, rate, 100.0, 14000.0)
+    for kw in (dict(power=1.0), dict(log_mode=1, log_eps=1e-6), dict(log_mode=2, log_eps=1e-10), dict(power=1.5)):
+        got, _ = run_gpu(ctx, seg, n_fft, hop, n_frames, w, mw, **kw)
+        ref = om.melspec(seg, n_fft, hop, n_frames, w, mw, **kw)
+        tol = 2e-5 * np.abs(ref).max() if kw.get("log_mode", 0) == 0 else 2e-3      # log of tiny energies amplifies f32 noise
+        assert np.abs(got - ref).max() <= tol, (kw, np.abs(got - ref).max())
+
+
+def test_melspec_many_rows_chunked(ctx):
+    """More rows than one L2-sized chunk of the power buffer holds (several STFT / GEMM launch pairs), ragged tail tile."""
+    rate, samples, rows, n_fft, hop, n_frames = 48_000, 48_000, 37, 2048, 93, 511
+    seg = windows(13, rows, samples, rate)
+    w, mw = om.hann(n_fft), om.mel_filterbank(80, n_fft, rate, 0.0, 24000.0)
+    l0 = ctx.kernel_launches
+    got, _ = run_gpu(ctx, seg, n_fft, hop, n_frames, w, mw)
+    assert ctx.kernel_launches - l0 >= 4
+    ref = om.melspec(seg, n_fft, hop, n_frames, w, mw)
+    scale = np.abs(ref).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(got - ref) / scale).max() <= REL_TOL
+
+
+def test_melspec_errors(ctx):
+    w, mw = om.hann(1024), om.mel_filterbank(64, 1024, 48_000, 0.0, 24000.0)
+    with pytest.raises(b.BirdaError):
+        b.MelSpec(ctx, 1000, 100, 10, np.ones(1000, np.float32), np.ones((64, 501), np.float32))   # not a power of two
+    with pytest.raises(b.BirdaError):
+        b.MelSpec(ctx, 1024, 100, 10, w, mw[:60])                                                  # n_mels % 16
+    with pytest.raises(b.BirdaError):
+        b.MelSpec(ctx, 1024, 0, 10, w, mw)
