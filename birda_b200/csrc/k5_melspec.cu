@@ -119,6 +119,113 @@ stft_power_kernel(const __grid_constant__ StftParams p) {
     }
 }
 
+// Two-stream variant for the common frame lengths: a group transforms TWO frames at once, every element is a float4
+// (re0, re1, im0, im1) and every butterfly instruction a packed f32x2 op (the K2 trick), stage constants are
+// compile-time.  6 groups of 2 warps per CTA: 64 lanes = the butterfly count of the radix-16 stage of N = 1024.
+constexpr int kFft2Threads = 384;
+template <class FWD> struct CtFwdPlan {              // forward half of a k2w::CtPlan (the inverse half is not used here)
+    using Plan = CtPlan<FWD, RSeq<2>>;
+    static constexpr int N = FWD::total();
+};
+template <class PL, int T> struct Fft2Rest {
+    template <class Ex> static __device__ __forceinline__ void run(const Ex& ex, float4* A, const float4* twf) {
+        if constexpr (T < PL::Fwd::count) {
+            using S = typename PL::template FwdStage<T>;
+            ex.each([&](int l, int n_l) { dif_stage<S::radix, cx2>(A, twf, S{}, l, n_l); });
+            Fft2Rest<PL, T + 1>::run(ex, A, twf);
+        }
+    }
+};
+
+template <class FWD>
+__global__ void __launch_bounds__(kFft2Threads, 1)
+stft_power2_kernel(const __grid_constant__ StftParams p) {
+    using PL = typename CtFwdPlan<FWD>::Plan;
+    constexpr int N = CtFwdPlan<FWD>::N;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const RtPlan& RP = p.plan;
+    float4* s_twf = reinterpret_cast<float4*>(smem);
+    uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + p.off_posf);
+    float2* s_wk = reinterpret_cast<float2*>(smem + p.off_wk);
+    float2* s_win = reinterpret_cast<float2*>(smem + p.off_win);
+    for (int i = threadIdx.x; i < RP.twf_len; i += kFft2Threads) { const float2 w = p.twf[i]; s_twf[i] = make_float4(w.x, w.x, w.y, w.y); }
+    for (int i = threadIdx.x; i < N; i += kFft2Threads) s_posf[i] = p.posf[i];
+    for (int i = threadIdx.x; i <= N; i += kFft2Threads) s_wk[i] = p.wk[i];
+    for (int i = threadIdx.x; i < N; i += kFft2Threads) s_win[i] = make_float2(p.window[2 * i], p.window[2 * i + 1]);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, group = warp / kFftGroupWarps;
+    constexpr int kGroups = kFft2Threads / 32 / kFftGroupWarps;
+    FftExec ex;
+    ex.nl = kFftGroupWarps * 32;
+    ex.glane = (warp - group * kFftGroupWarps) * 32 + (int)(threadIdx.x & 31);
+    ex.bar_id = 1 + group;
+    const int lane = ex.glane, nl = ex.nl;
+    float4* A = reinterpret_cast<float4*>(smem + p.tables + (size_t)group * p.per_group);
+    const uint64_t npairs = (p.nframes + 1) / 2;
+
+    for (uint64_t pi = (uint64_t)blockIdx.x * kGroups + group; pi < npairs; pi += (uint64_t)gridDim.x * kGroups) {
+        const float* xr[2]; uint32_t s0[2]; bool act[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const uint64_t fi = 2 * pi + s;
+            act[s] = fi < p.nframes;
+            const uint64_t f = p.frame0 + (act[s] ? fi : 0);
+            const uint64_t row = f / p.n_frames;
+            xr[s] = p.x + row * p.samples;
+            s0[s] = (uint32_t)(f - row * p.n_frames) * p.hop;
+        }
+        const bool fast = act[0] && act[1] && s0[0] + 2u * N <= p.samples && s0[1] + 2u * N <= p.samples &&
+                          ((reinterpret_cast<uintptr_t>(xr[0] + s0[0]) | reinterpret_cast<uintptr_t>(xr[1] + s0[1])) & 7u) == 0;
+        if (fast) {
+            const float2* __restrict__ x0 = reinterpret_cast<const float2*>(xr[0] + s0[0]);
+            const float2* __restrict__ x1 = reinterpret_cast<const float2*>(xr[1] + s0[1]);
+            auto ld = [&](int n) -> cx2 {
+                const float2 a = __ldg(x0 + n), b = __ldg(x1 + n), w = s_win[n];
+                cx2 c; c.re = make_float2(a.x * w.x, b.x * w.x); c.im = make_float2(a.y * w.y, b.y * w.y);
+                return c;
+            };
+            using S0 = typename PL::template FwdStage<0>;
+            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2>(A, s_twf, S0{}, N, ld, l, n_l); });
+        } else {
+            auto ld = [&](int n) -> cx2 {
+                float v[2][2];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const uint32_t i0 = s0[s] + 2u * (uint32_t)n;
+                    v[s][0] = act[s] && i0 < p.samples ? __ldg(xr[s] + i0) : 0.f;
+                    v[s][1] = act[s] && i0 + 1u < p.samples ? __ldg(xr[s] + i0 + 1u) : 0.f;
+                }
+                const float2 w = s_win[n];
+                cx2 c; c.re = make_float2(v[0][0] * w.x, v[1][0] * w.x); c.im = make_float2(v[0][1] * w.y, v[1][1] * w.y);
+                return c;
+            };
+            using S0 = typename PL::template FwdStage<0>;
+            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2>(A, s_twf, S0{}, N, ld, l, n_l); });
+        }
+        Fft2Rest<PL, 1>::run(ex, A, s_twf);
+        float* __restrict__ P0 = p.P + (2 * pi) * p.kpad;
+        float* __restrict__ P1 = P0 + p.kpad;
+        for (uint32_t j = lane; j < p.kpad; j += nl) {
+            float2 v = make_float2(0.f, 0.f);
+            if (j < p.nb) {
+                const int k = (int)(p.bin_lo + j);
+                const cx2 zk = Mem<cx2>::ld(A + s_posf[k == N ? 0 : k]), zn = cconj(Mem<cx2>::ld(A + s_posf[k == 0 ? 0 : N - k]));
+                const cx2 e = cadd(zk, zn), d = csub(zk, zn);
+                const cx2 o = rot90<false>(cmul(Mem<cx2>::bcast(s_wk[k]), d));      // -i w d
+                const float2 xr_ = kmulc(kadd(e.re, o.re), 0.5f), xi_ = kmulc(kadd(e.im, o.im), 0.5f);
+                const float2 pw = kfma(xr_, xr_, kmul(xi_, xi_));
+                if (p.power == 2.0f) v = pw;
+                else if (p.power == 1.0f) v = make_float2(sqrtf(pw.x), sqrtf(pw.y));
+                else v = make_float2(powf(pw.x, 0.5f * p.power), powf(pw.y, 0.5f * p.power));
+            }
+            P0[j] = v.x;
+            if (act[1]) P1[j] = v.y;
+        }
+        ex.sync();
+    }
+}
+
 // ------------------------------------------------------------------------------------------ K5b
 constexpr int kBM = 128;                 // frames per tile = UMMA M
 constexpr int kBK = 32;                  // tf32 elements per K chunk = one 128-byte swizzle row
@@ -416,9 +523,29 @@ int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, ui
         const uint64_t nr = rows - r0 < rows_per_chunk ? rows - r0 : rows_per_chunk;
         const uint64_t nframes = nr * cfg.n_frames;
         sp.frame0 = r0 * cfg.n_frames; sp.nframes = nframes;
-        const uint64_t want = (nframes + 3) / 4;
-        const unsigned grid = (unsigned)(want < (uint64_t)c->sm_count * 4 ? want : (uint64_t)c->sm_count * 4);
-        stft_power_kernel<<<grid, kFftThreads, fft_smem, c->stream>>>(sp);
+        if (m->N == 1024 || m->N == 512) {
+            StftParams s2 = sp;
+            s2.off_posf = a16((size_t)m->plan.twf_len * 16);
+            s2.off_wk = s2.off_posf + a16((size_t)m->N * 2);
+            s2.off_win = s2.off_wk + a16((size_t)(m->N + 1) * 8);
+            s2.tables = s2.off_win + a16((size_t)cfg.n_fft * 4);
+            s2.per_group = a16((size_t)m->N * 16);
+            constexpr int groups2 = kFft2Threads / 32 / kFftGroupWarps;
+            const size_t smem2 = s2.tables + (size_t)groups2 * s2.per_group;
+            const uint64_t want2 = ((nframes + 1) / 2 + groups2 - 1) / groups2;
+            const unsigned grid2 = (unsigned)(want2 < (uint64_t)c->sm_count ? want2 : (uint64_t)c->sm_count);
+            if (m->N == 1024) {
+                BB_CUDA_OK(c, cudaFuncSetAttribute(stft_power2_kernel<RSeq<16, 8, 8>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                stft_power2_kernel<RSeq<16, 8, 8>><<<grid2, kFft2Threads, smem2, c->stream>>>(s2);
+            } else {
+                BB_CUDA_OK(c, cudaFuncSetAttribute(stft_power2_kernel<RSeq<8, 8, 8>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                stft_power2_kernel<RSeq<8, 8, 8>><<<grid2, kFft2Threads, smem2, c->stream>>>(s2);
+            }
+        } else {
+            const uint64_t want = (nframes + 3) / 4;
+            const unsigned grid = (unsigned)(want < (uint64_t)c->sm_count * 4 ? want : (uint64_t)c->sm_count * 4);
+            stft_power_kernel<<<grid, kFftThreads, fft_smem, c->stream>>>(sp);
+        }
         gp.frame0 = sp.frame0; gp.nframes = nframes;
         mel_gemm_kernel<<<(unsigned)((nframes + kBM - 1) / kBM), kGemmThreads, gemm_smem, c->stream>>>(gp);
         BB_CUDA_OK(c, cudaGetLastError());
