@@ -28,7 +28,7 @@ struct bb_melspec {
     bb::k2w::RtPlan plan{};
     float2* d_twf = nullptr; uint16_t* d_posf = nullptr; float2* d_wk = nullptr;   // stage twiddles, digit reversal, exp(-i pi k / N)
     float* d_window = nullptr;
-    float* d_whi = nullptr; float* d_wlo = nullptr;                                 // [n_mels, kpad] tf32 hi / lo parts
+    float* d_w = nullptr;                                                            // [n_mels, 2 * kpad]: tf32 hi | lo parts per 32-bin chunk
     float* d_P = nullptr; uint64_t p_capacity_frames = 0;                            // [frames (multiple of 128), kpad]
 };
 
@@ -46,6 +46,20 @@ struct FftExec {
     __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nl) : "memory"); }
     template <class F> __device__ __forceinline__ void each(F&& f) const { f(glane, nl); sync(); }
 };
+
+// error-free split for the tf32 pipe: hi keeps the top 19 bits (sign, exponent, 10 mantissa bits), lo = v - hi exactly
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    lo = v - hi;
+}
+// P row layout: per chunk of 32 bins, 32 hi values then 32 lo values (one 256-byte run per frame and chunk, so the
+// GEMM's producers copy straight into its hi and lo operand tiles)
+__device__ __forceinline__ void store_split(float* __restrict__ row, uint32_t j, float v) {
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    float* q = row + (size_t)(j >> 5) * 64 + (j & 31u);
+    q[0] = hi; q[32] = lo;
+}
 
 struct StftParams {
     RtPlan plan;
@@ -98,7 +112,7 @@ stft_power_kernel(const __grid_constant__ StftParams p) {
         for (int st = 1; st < PL.nf; ++st)
             ex.each([&](int l, int n_l) { BB_K2W_RADIX_SWITCH(PL.f[st].radix, (dif_stage<R, float2>(A, s_twf, PL.f[st], l, n_l))) });
         // bins of the mel support: X[k] = (Z[k] + conj Z[N-k]) / 2 - (i/2) exp(-i pi k / N) (Z[k] - conj Z[N-k])
-        float* __restrict__ Pf = p.P + fi * p.kpad;
+        float* __restrict__ Pf = p.P + fi * (2ull * p.kpad);
         for (uint32_t j = lane; j < p.kpad; j += nl) {
             float v = 0.f;
             if (j < p.nb) {
@@ -113,7 +127,7 @@ stft_power_kernel(const __grid_constant__ StftParams p) {
                 const float pw = xr_ * xr_ + xi_ * xi_;
                 v = p.power == 2.0f ? pw : (p.power == 1.0f ? sqrtf(pw) : powf(pw, 0.5f * p.power));
             }
-            Pf[j] = v;
+            store_split(Pf, j, v);
         }
         ex.sync();                       // A is rewritten by the next frame's first stage
     }
@@ -204,8 +218,8 @@ stft_power2_kernel(const __grid_constant__ StftParams p) {
             ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2>(A, s_twf, S0{}, N, ld, l, n_l); });
         }
         Fft2Rest<PL, 1>::run(ex, A, s_twf);
-        float* __restrict__ P0 = p.P + (2 * pi) * p.kpad;
-        float* __restrict__ P1 = P0 + p.kpad;
+        float* __restrict__ P0 = p.P + (2 * pi) * (2ull * p.kpad);
+        float* __restrict__ P1 = P0 + 2ull * p.kpad;
         for (uint32_t j = lane; j < p.kpad; j += nl) {
             float2 v = make_float2(0.f, 0.f);
             if (j < p.nb) {
@@ -219,8 +233,8 @@ stft_power2_kernel(const __grid_constant__ StftParams p) {
                 else if (p.power == 1.0f) v = make_float2(sqrtf(pw.x), sqrtf(pw.y));
                 else v = make_float2(powf(pw.x, 0.5f * p.power), powf(pw.y, 0.5f * p.power));
             }
-            P0[j] = v.x;
-            if (act[1]) P1[j] = v.y;
+            store_split(P0, j, v.x);
+            if (act[1]) store_split(P1, j, v.y);
         }
         ex.sync();
     }
@@ -229,12 +243,12 @@ stft_power2_kernel(const __grid_constant__ StftParams p) {
 // ------------------------------------------------------------------------------------------ K5b
 constexpr int kBM = 128;                 // frames per tile = UMMA M
 constexpr int kBK = 32;                  // tf32 elements per K chunk = one 128-byte swizzle row
-constexpr int kStages = 2;
+constexpr int kGemmMaxStages = 4;
 constexpr int kGemmThreads = 160;        // warps 0-3: producers, then epilogue (TMEM lane quarters); warp 4: TMEM owner + MMA issuer
 
 struct GemmParams {
-    const float* P; const float* whi; const float* wlo; float* out;
-    uint32_t kpad, n_mels, n_frames, tmem_cols, idesc;
+    const float* P; const float* W; float* out;      // both in the chunked hi | lo layout (store_split)
+    uint32_t kpad, n_mels, n_frames, tmem_cols, idesc, stages;
     uint64_t frame0, nframes;            // flattened frames of this launch; P row 0 = frame0
     int32_t log_mode; float log_eps;
 };
@@ -269,12 +283,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// error-free split for the tf32 pipe: hi keeps the top 19 bits (sign, exponent, 10 mantissa bits), lo = v - hi exactly
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    lo = v - hi;
-}
-
 __global__ void __launch_bounds__(kGemmThreads, 2)
 mel_gemm_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -282,13 +290,13 @@ mel_gemm_kernel(const __grid_constant__ GemmParams p) {
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = kBM * 128, b_bytes = p.n_mels * 128;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_done;
+    __shared__ __align__(8) uint64_t s_full[kGemmMaxStages], s_empty[kGemmMaxStages], s_done;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t nk = p.kpad / kBK;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < kGemmMaxStages; ++s) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
         mbar_init(&s_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -303,37 +311,46 @@ mel_gemm_kernel(const __grid_constant__ GemmParams p) {
     const uint64_t tile0 = (uint64_t)blockIdx.x * kBM;         // first frame of the tile, relative to frame0
 
     if (warp < 4) {
-        // ===== producers: global P / W chunks -> hi / lo tiles in the canonical K-major 128B-swizzled layout
-        for (uint32_t kc = 0; kc < nk; ++kc) {
-            const uint32_t s = kc % kStages, ph = (kc / kStages) & 1u;
-            mbar_wait(&s_empty[s], ph ^ 1u);
-            unsigned char* st = smem + (size_t)s * stage_bytes;
-            float4 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {                      // A: 128 rows x 8 pieces of 16 bytes
-                const uint32_t piece = (uint32_t)i * 128u + (uint32_t)tid, r = piece >> 3, c = piece & 7u;
+        // ===== producers: a classic multi-stage cp.async pipeline.  A frame's (or mel row's) chunk is 256 contiguous
+        // bytes in global memory: 8 pieces of 16 bytes for the hi tile, 8 for the lo tile, each copied straight to its
+        // place in the canonical K-major 128B-swizzled layout (piece c of row r lands at r*128 + ((c ^ (r & 7)) << 4)).
+        const uint32_t S = p.stages;
+        auto issue = [&](uint32_t kc) {
+            unsigned char* st = smem + (size_t)(kc % S) * stage_bytes;
+            const uint32_t a_pieces = kBM * 16u, w_pieces = p.n_mels * 16u;
+            for (uint32_t piece = tid; piece < a_pieces; piece += 128u) {
+                const uint32_t r = piece >> 4, c16 = piece & 15u, c = c16 & 7u, half = c16 >> 3;
                 const uint64_t fr = tile0 + r;
-                v[i] = fr < p.nframes ? __ldg(reinterpret_cast<const float4*>(p.P + fr * p.kpad + kc * kBK + c * 4))
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool in = fr < p.nframes;
+                const float* g = p.P + (in ? fr : 0) * (2ull * p.kpad) + (size_t)kc * 64 + c16 * 4;
+                const uint32_t d = smem_u32(st + half * a_bytes + r * 128u + ((c ^ (r & 7u)) << 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(in ? 16 : 0) : "memory");
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t piece = (uint32_t)i * 128u + (uint32_t)tid, r = piece >> 3, c = piece & 7u;
-                const uint32_t off = r * 128u + ((c ^ (r & 7u)) << 4);
-                float4 hi, lo;
-                split_tf32(v[i].x, hi.x, lo.x); split_tf32(v[i].y, hi.y, lo.y); split_tf32(v[i].z, hi.z, lo.z); split_tf32(v[i].w, hi.w, lo.w);
-                *reinterpret_cast<float4*>(st + off) = hi;
-                *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
+            for (uint32_t piece = tid; piece < w_pieces; piece += 128u) {
+                const uint32_t r = piece >> 4, c16 = piece & 15u, c = c16 & 7u, half = c16 >> 3;
+                const float* g = p.W + (size_t)r * (2ull * p.kpad) + (size_t)kc * 64 + c16 * 4;
+                const uint32_t d = smem_u32(st + 2 * a_bytes + half * b_bytes + r * 128u + ((c ^ (r & 7u)) << 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
             }
-            for (uint32_t piece = tid; piece < p.n_mels * 8u; piece += 128u) {   // B: n_mels rows x 8 pieces, hi and lo prepared on the host
-                const uint32_t r = piece >> 3, c = piece & 7u;
-                const uint32_t off = r * 128u + ((c ^ (r & 7u)) << 4);
-                const size_t g = (size_t)r * p.kpad + kc * kBK + c * 4;
-                *reinterpret_cast<float4*>(st + 2 * a_bytes + off) = __ldg(reinterpret_cast<const float4*>(p.whi + g));
-                *reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes + off) = __ldg(reinterpret_cast<const float4*>(p.wlo + g));
+        };
+        // prologue: S - 1 chunks in flight
+        for (uint32_t kc = 0; kc + 1 < S; ++kc) {
+            if (kc < nk) issue(kc);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (uint32_t kc = 0; kc < nk; ++kc) {
+            const uint32_t nxt = kc + S - 1;
+            if (nxt < nk) {
+                mbar_wait(&s_empty[nxt % S], ((nxt / S) & 1u) ^ 1u);        // the MMAs that read this slot have retired
+                issue(nxt);
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            // chunk kc has landed once at most S - 1 newer groups are pending
+            if (S == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else if (S == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else asm volatile("cp.async.wait_group 3;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
-            mbar_arrive(&s_full[s]);
+            mbar_arrive(&s_full[kc % S]);
         }
         // ===== epilogue: TMEM -> registers -> scaling -> [rows, n_mels, n_frames]
         mbar_wait(&s_done, 0);
@@ -367,7 +384,7 @@ mel_gemm_kernel(const __grid_constant__ GemmParams p) {
         // ===== MMA issuer: one elected lane
         if (lane == 0) {
             for (uint32_t kc = 0; kc < nk; ++kc) {
-                const uint32_t s = kc % kStages, ph = (kc / kStages) & 1u;
+                const uint32_t s = kc % p.stages, ph = (kc / p.stages) & 1u;
                 mbar_wait(&s_full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
@@ -405,7 +422,7 @@ void bb_melspec_destroy(bb_melspec* m) {
     if (!m) return;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    void* ptrs[] = {m->d_twf, m->d_posf, m->d_wk, m->d_window, m->d_whi, m->d_wlo, m->d_P};
+    void* ptrs[] = {m->d_twf, m->d_posf, m->d_wk, m->d_window, m->d_w, m->d_P};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete m;
 }
@@ -443,13 +460,14 @@ int32_t bb_melspec_create(bb_ctx* c, const bb_melspec_cfg* cfg, const float* win
     k2w::build_pos_tables(fwd, inv, m->N, m->N, pf.data(), pi_.data());
     const double pi = 3.14159265358979323846;
     for (int k = 0; k <= m->N; ++k) wk[k] = make_float2((float)cos(-pi * k / m->N), (float)sin(-pi * k / m->N));
-    std::vector<float> whi((size_t)cfg->n_mels * m->kpad, 0.f), wlo((size_t)cfg->n_mels * m->kpad, 0.f);
+    std::vector<float> w2((size_t)cfg->n_mels * m->kpad * 2, 0.f);        // same chunked hi | lo layout as P
     for (uint32_t r = 0; r < cfg->n_mels; ++r)
         for (uint32_t j = 0; j < m->nb; ++j) {
             const float w = mel_weights[(size_t)r * bins + lo + j];
             uint32_t b; memcpy(&b, &w, 4); b &= 0xFFFFE000u;
             float h; memcpy(&h, &b, 4);
-            whi[(size_t)r * m->kpad + j] = h; wlo[(size_t)r * m->kpad + j] = w - h;
+            float* q = &w2[(size_t)r * m->kpad * 2 + (size_t)(j >> 5) * 64 + (j & 31u)];
+            q[0] = h; q[32] = w - h;
         }
     cudaSetDevice(c->device);
     auto up = [&](const void* h, size_t bytes, void** d) -> cudaError_t {
@@ -461,8 +479,7 @@ int32_t bb_melspec_create(bb_ctx* c, const bb_melspec_cfg* cfg, const float* win
     if (e == cudaSuccess) e = up(pf.data(), pf.size() * 2, (void**)&m->d_posf);
     if (e == cudaSuccess) e = up(wk.data(), wk.size() * 8, (void**)&m->d_wk);
     if (e == cudaSuccess) e = up(window, (size_t)nfft * 4, (void**)&m->d_window);
-    if (e == cudaSuccess) e = up(whi.data(), whi.size() * 4, (void**)&m->d_whi);
-    if (e == cudaSuccess) e = up(wlo.data(), wlo.size() * 4, (void**)&m->d_wlo);
+    if (e == cudaSuccess) e = up(w2.data(), w2.size() * 4, (void**)&m->d_w);
     if (e != cudaSuccess) {
         std::string msg = std::string("melspec init: ") + cudaGetErrorString(e);
         bb_melspec_destroy(m);
@@ -487,15 +504,18 @@ int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, ui
     if (!d_segments || !d_out || samples == 0) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null argument");
     BB_CUDA_OK(c, cudaSetDevice(c->device));
     const bb_melspec_cfg& cfg = m->cfg;
-    // P is produced and consumed in chunks of whole rows that stay in L2 (<= 64 MB)
-    const uint64_t row_bytes = (uint64_t)cfg.n_frames * m->kpad * 4;
+    // P is produced and consumed in chunks of whole rows: L2-sized (<= 64 MB) when that still fills the GPU
+    const uint64_t row_bytes = (uint64_t)cfg.n_frames * m->kpad * 8;       // hi and lo parts
     uint64_t rows_per_chunk = (64ull << 20) / row_bytes;
+    // ... but never so few that the GEMM grid (one CTA per 128 frames, two CTAs per SM) drops below ~4 waves
+    const uint64_t min_rows = ((uint64_t)c->sm_count * 2 * 4 * kBM + cfg.n_frames - 1) / cfg.n_frames;
+    if (rows_per_chunk < min_rows) rows_per_chunk = min_rows;
     if (rows_per_chunk == 0) rows_per_chunk = 1;
     if (rows_per_chunk > rows) rows_per_chunk = rows;
     const uint64_t cap_frames = ((rows_per_chunk * cfg.n_frames + kBM - 1) / kBM) * kBM;
     if (cap_frames > m->p_capacity_frames) {
         if (m->d_P) { BB_CUDA_OK(c, cudaStreamSynchronize(c->stream)); cudaFree(m->d_P); m->d_P = nullptr; m->p_capacity_frames = 0; }
-        BB_CUDA_OK(c, cudaMalloc((void**)&m->d_P, cap_frames * m->kpad * 4));
+        BB_CUDA_OK(c, cudaMalloc((void**)&m->d_P, cap_frames * m->kpad * 8));
         m->p_capacity_frames = cap_frames;
     }
     StftParams sp{};
@@ -511,13 +531,17 @@ int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, ui
     const size_t fft_smem = sp.tables + (size_t)(kFftThreads / 32 / kFftGroupWarps) * sp.per_group;
     BB_CUDA_OK(c, cudaFuncSetAttribute(stft_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem));
     GemmParams gp{};
-    gp.P = m->d_P; gp.whi = m->d_whi; gp.wlo = m->d_wlo; gp.out = d_out;
+    gp.P = m->d_P; gp.W = m->d_w; gp.out = d_out;
     gp.kpad = m->kpad; gp.n_mels = cfg.n_mels; gp.n_frames = cfg.n_frames;
     gp.tmem_cols = cfg.n_mels <= 32 ? 32 : cfg.n_mels <= 64 ? 64 : cfg.n_mels <= 128 ? 128 : 256;
     // cute::UMMA::InstrDescriptor: c = F32 (1 << 4), a = b = TF32 (2 << 7, 2 << 10), K-major both, N >> 3 at bit 17, M >> 4 at bit 24
     gp.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((cfg.n_mels >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     gp.log_mode = cfg.log_mode; gp.log_eps = cfg.log_eps;
-    const size_t gemm_smem = (size_t)kStages * (2 * kBM * 128 + 2 * (size_t)cfg.n_mels * 128) + 1024;
+    // two stages when two CTAs then share an SM (their main loops and epilogues overlap), else as many as fit
+    const size_t stage_bytes = 2 * (size_t)kBM * 128 + 2 * (size_t)cfg.n_mels * 128;
+    gp.stages = 2;
+    if (2 * (2 * stage_bytes + 2048) > 227 * 1024) { gp.stages = (uint32_t)((220 * 1024) / stage_bytes); if (gp.stages > kGemmMaxStages) gp.stages = kGemmMaxStages; }
+    const size_t gemm_smem = (size_t)gp.stages * stage_bytes + 1024;
     BB_CUDA_OK(c, cudaFuncSetAttribute(mel_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
     for (uint64_t r0 = 0; r0 < rows; r0 += rows_per_chunk) {
         const uint64_t nr = rows - r0 < rows_per_chunk ? rows - r0 : rows_per_chunk;

@@ -66,8 +66,8 @@ def test_melspec_log_modes_and_magnitude(ctx):
 
 
 def test_melspec_many_rows_chunked(ctx):
-    """More rows than one L2-sized chunk of the power buffer holds (several STFT / GEMM launch pairs), ragged tail tile."""
-    rate, samples, rows, n_fft, hop, n_frames = 48_000, 48_000, 37, 2048, 93, 511
+    """More rows than one chunk of the power buffer holds (two STFT / GEMM launch pairs), ragged tail tile."""
+    rate, samples, rows, n_fft, hop, n_frames = 48_000, 24_000, 310, 1024, 47, 511
     seg = windows(13, rows, samples, rate)
     w, mw = om.hann(n_fft), om.mel_filterbank(80, n_fft, rate, 0.0, 24000.0)
     l0 = ctx.kernel_launches
