@@ -29,7 +29,25 @@ pub const BB_F32: i32 = 3;
 pub const BB_ERR_OVERLAP_GE_SEGMENT: i32 = -2;
 pub const BB_ERR_UNSUPPORTED_RATE: i32 = -3;
 
+#[repr(C)] pub struct bb_melspec { _p: [u8; 0] }
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct bb_melspec_cfg {
+    pub n_fft: u32,
+    pub hop: u32,
+    pub n_frames: u32,
+    pub n_mels: u32,
+    pub power: f32,
+    pub log_mode: i32,
+    pub log_eps: f32,
+}
+
 extern "C" {
+    pub fn bb_melspec_create(ctx: *mut bb_ctx, cfg: *const bb_melspec_cfg, window: *const f32, mel_weights: *const f32,
+                             out: *mut *mut bb_melspec) -> i32;
+    pub fn bb_melspec_run(ms: *mut bb_melspec, d_segments: *const f32, rows: u32, samples: u32, d_out: *mut f32) -> i32;
+    pub fn bb_melspec_destroy(ms: *mut bb_melspec);
     pub fn bb_ctx_create(device: i32, out: *mut *mut bb_ctx) -> i32;
     pub fn bb_ctx_create_on_stream(device: i32, stream: *mut c_void, out: *mut *mut bb_ctx) -> i32;
     pub fn bb_ctx_destroy(ctx: *mut bb_ctx);
