@@ -112,6 +112,13 @@ template <> struct Mem<cx2> {
     static BB_HD cx2 bcast(float2 w) { cx2 c; c.re = make_float2(w.x, w.x); c.im = make_float2(w.y, w.y); return c; }
 };
 
+// Address map of a transform buffer: logical slot -> physical slot.  MapPad8 leaves one slot of padding after every
+// eight: a power-of-two plan's stride-8 stage (span 8, m = 1: lanes 8 slots = 128 bytes apart, an 8-way bank conflict
+// with 16-byte elements) becomes a stride-9 walk, and the runs of 8 consecutive slots the other stages touch stay
+// contiguous.
+struct MapId  { static BB_HD constexpr int at(int i) { return i; } };
+struct MapPad8 { static BB_HD constexpr int at(int i) { return i + (i >> 3); } };
+
 // a[k] *= w_span^(p k), k = 1..R-1.  Table layout: chain mode [p] holds w^p; table mode [(k-1)*m + p]
 template <int R, class C> BB_HD void apply_twiddles(C (&a)[R], const typename Mem<C>::T* __restrict__ tw, int m, int p) {
     if constexpr (tw_table_mode(R)) {
@@ -128,26 +135,26 @@ template <int R, class C> BB_HD void apply_twiddles(C (&a)[R], const typename Me
 }
 
 // ---- forward DIF stage, in place
-template <int R, class C, class S>
+template <int R, class C, class AM = MapId, class S>
 BB_HD void dif_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl) {
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < s.NBF_(); q += nl) {
         int sb, p;
         s.decompose(q, sb, p);
-        typename Mem<C>::T* __restrict__ e = buf + sb * s.SPAN_() + p;
+        const int e = sb * s.SPAN_() + p;
         C a[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(e + j * m);
+        for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(buf + AM::at(e + j * m));
         Dft<R, false>::run(a);
         if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, p);
 #pragma unroll
-        for (int k = 0; k < R; ++k) Mem<C>::st(e + k * m, a[k]);
+        for (int k = 0; k < R; ++k) Mem<C>::st(buf + AM::at(e + k * m), a[k]);
     }
 }
 
 // first forward stage: input z[n] comes from `ld(n)` for n < half_in, zero above
-template <int R, class C, class S, class Loader>
+template <int R, class C, class AM = MapId, class S, class Loader>
 BB_HD void dif_first(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int half_in,
                      const Loader& ld, int lane, int nl) {
     const int m = s.M_();
@@ -161,9 +168,8 @@ BB_UNROLL_N(BB_K2W_UNROLL)
         }
         Dft<R, false>::run(a);
         if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, q);
-        typename Mem<C>::T* __restrict__ e = buf + q;
 #pragma unroll
-        for (int k = 0; k < R; ++k) Mem<C>::st(e + k * m, a[k]);
+        for (int k = 0; k < R; ++k) Mem<C>::st(buf + AM::at(q + k * m), a[k]);
     }
 }
 

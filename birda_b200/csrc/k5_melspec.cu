@@ -145,7 +145,7 @@ template <class PL, int T> struct Fft2Rest {
     template <class Ex> static __device__ __forceinline__ void run(const Ex& ex, float4* A, const float4* twf) {
         if constexpr (T < PL::Fwd::count) {
             using S = typename PL::template FwdStage<T>;
-            ex.each([&](int l, int n_l) { dif_stage<S::radix, cx2>(A, twf, S{}, l, n_l); });
+            ex.each([&](int l, int n_l) { dif_stage<S::radix, cx2, MapPad8>(A, twf, S{}, l, n_l); });
             Fft2Rest<PL, T + 1>::run(ex, A, twf);
         }
     }
@@ -200,7 +200,7 @@ stft_power2_kernel(const __grid_constant__ StftParams p) {
                 return c;
             };
             using S0 = typename PL::template FwdStage<0>;
-            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2>(A, s_twf, S0{}, N, ld, l, n_l); });
+            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2, MapPad8>(A, s_twf, S0{}, N, ld, l, n_l); });
         } else {
             auto ld = [&](int n) -> cx2 {
                 float v[2][2];
@@ -215,7 +215,7 @@ stft_power2_kernel(const __grid_constant__ StftParams p) {
                 return c;
             };
             using S0 = typename PL::template FwdStage<0>;
-            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2>(A, s_twf, S0{}, N, ld, l, n_l); });
+            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2, MapPad8>(A, s_twf, S0{}, N, ld, l, n_l); });
         }
         Fft2Rest<PL, 1>::run(ex, A, s_twf);
         float* __restrict__ P0 = p.P + (2 * pi) * (2ull * p.kpad);
@@ -224,7 +224,7 @@ stft_power2_kernel(const __grid_constant__ StftParams p) {
             float2 v = make_float2(0.f, 0.f);
             if (j < p.nb) {
                 const int k = (int)(p.bin_lo + j);
-                const cx2 zk = Mem<cx2>::ld(A + s_posf[k == N ? 0 : k]), zn = cconj(Mem<cx2>::ld(A + s_posf[k == 0 ? 0 : N - k]));
+                const cx2 zk = Mem<cx2>::ld(A + MapPad8::at(s_posf[k == N ? 0 : k])), zn = cconj(Mem<cx2>::ld(A + MapPad8::at(s_posf[k == 0 ? 0 : N - k])));
                 const cx2 e = cadd(zk, zn), d = csub(zk, zn);
                 const cx2 o = rot90<false>(cmul(Mem<cx2>::bcast(s_wk[k]), d));      // -i w d
                 const float2 xr_ = kmulc(kadd(e.re, o.re), 0.5f), xi_ = kmulc(kadd(e.im, o.im), 0.5f);
@@ -553,7 +553,7 @@ int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, ui
             s2.off_wk = s2.off_posf + a16((size_t)m->N * 2);
             s2.off_win = s2.off_wk + a16((size_t)(m->N + 1) * 8);
             s2.tables = s2.off_win + a16((size_t)cfg.n_fft * 4);
-            s2.per_group = a16((size_t)m->N * 16);
+            s2.per_group = a16((size_t)(m->N + m->N / 8) * 16);      // MapPad8: one slot of padding after every eight
             constexpr int groups2 = kFft2Threads / 32 / kFftGroupWarps;
             const size_t smem2 = s2.tables + (size_t)groups2 * s2.per_group;
             const uint64_t want2 = ((nframes + 1) / 2 + groups2 - 1) / groups2;
