@@ -81,17 +81,18 @@ struct Source {
 };
 
 // z[n] = x[2n] + i x[2n+1] of one block; `valid` = real samples in the block (zero above)
+template <class AM>
 struct BlockLoader {
     const Source* src; const float2* A; uint64_t base; int valid; int shift;
     __device__ __forceinline__ float2 operator()(int n) const {
         const int i0 = 2 * n;
         float re = 0.f, im = 0.f;
         if (src->kind == 0) {                // slot n holds frames (2n, 2n+1) as two packed L|R words
-            const int2 v = *reinterpret_cast<const int2*>(A + n);
+            const int2 v = *reinterpret_cast<const int2*>(A + AM::at(n));
             re = __fmul_rn(__int2float_rn((int)(short)(v.x & 0xffff) + (v.x >> 16)), 1.0f / 65536.0f);
             im = __fmul_rn(__int2float_rn((int)(short)(v.y & 0xffff) + (v.y >> 16)), 1.0f / 65536.0f);
         } else if (src->kind == 1) {         // slot n holds the aligned word(s) covering frames (2n, 2n+1)
-            const int2 v = *reinterpret_cast<const int2*>(A + n);
+            const int2 v = *reinterpret_cast<const int2*>(A + AM::at(n));
             const int w = __funnelshift_r(v.x, v.y, shift);
             re = __fmul_rn(__int2float_rn((int)(short)(w & 0xffff)), 1.0f / 32768.0f);
             im = __fmul_rn(__int2float_rn(w >> 16), 1.0f / 32768.0f);
@@ -108,6 +109,7 @@ struct BlockLoader {
 
 // stage the raw PCM of one block into A with cp.async (A is dead between the split pass of the
 // previous block and the first stage of this one).  Returns the funnel shift for mono.
+template <class AM>
 __device__ __forceinline__ int prefetch_block(const Source& s, float2* A, uint64_t base, int valid, int half_in, int lane, int nl) {
     int shift = 0;
     if (s.kind == 0) {
@@ -117,10 +119,10 @@ __device__ __forceinline__ int prefetch_block(const Source& s, float2* A, uint64
             if (2 * n >= valid) break;
             const char* g = g0 + (size_t)n * 8;
             const long long room = s.pcm_end - g;
-            if (al8) cp_async8(A + n, g, room >= 8 ? 8 : (room > 0 ? (int)room : 0));
+            if (al8) cp_async8(A + AM::at(n), g, room >= 8 ? 8 : (room > 0 ? (int)room : 0));
             else {
-                cp_async4(A + n, g, room >= 4 ? 4 : 0);
-                cp_async4(reinterpret_cast<char*>(A + n) + 4, g + 4, room >= 8 ? 4 : 0);
+                cp_async4(A + AM::at(n), g, room >= 4 ? 4 : 0);
+                cp_async4(reinterpret_cast<char*>(A + AM::at(n)) + 4, g + 4, room >= 8 ? 4 : 0);
             }
         }
     } else if (s.kind == 1) {
@@ -132,8 +134,8 @@ __device__ __forceinline__ int prefetch_block(const Source& s, float2* A, uint64
             if (2 * n >= valid) break;
             const char* g = g0 + (size_t)n * 4;
             const long long room = s.pcm_end - g;
-            cp_async4(A + n, g, room >= 4 ? 4 : (room > 0 ? (int)room : 0));
-            if (odd) cp_async4(reinterpret_cast<char*>(A + n) + 4, g + 4, room >= 8 ? 4 : (room > 4 ? (int)(room - 4) : 0));
+            cp_async4(A + AM::at(n), g, room >= 4 ? 4 : (room > 0 ? (int)room : 0));
+            if (odd) cp_async4(reinterpret_cast<char*>(A + AM::at(n)) + 4, g + 4, room >= 8 ? 4 : (room > 4 ? (int)(room - 4) : 0));
         }
     }
     return shift;
@@ -149,7 +151,8 @@ struct DevSink {
 };
 
 // plan views: the runtime plan reads sizes from the stage table, a compile-time plan folds them
-struct RtView {
+template <class AM> struct RtView {
+    using MapA = AM; using MapB = AM;
     static __device__ __forceinline__ int n(const RtPlan& p) { return p.N; }
     static __device__ __forceinline__ int m(const RtPlan& p) { return p.M; }
     static __device__ __forceinline__ int half_in(const RtPlan& p) { return p.half_in; }
@@ -157,10 +160,11 @@ struct RtView {
     static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const Tables<C>& T, typename Mem<C>::T* A,
                                                  typename Mem<C>::T* B, typename Mem<C>::T* carry, const Loader& ld,
                                                  const Sink& sink, After&& after) {
-        process_block<C>(ex, p, T, A, B, carry, ld, sink, after);
+        process_block<C, AM>(ex, p, T, A, B, carry, ld, sink, after);
     }
 };
 template <class PL> struct CtView {
+    using MapA = typename PL::MapA; using MapB = typename PL::MapB;
     static __device__ __forceinline__ constexpr int n(const RtPlan&) { return PL::N; }
     static __device__ __forceinline__ constexpr int m(const RtPlan&) { return PL::M; }
     static __device__ __forceinline__ constexpr int half_in(const RtPlan&) { return PL::HALF_IN; }
@@ -243,11 +247,11 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
         for (int j = lane; j < M / 2; j += nl) carry[j] = make_float2(0.f, 0.f);
         const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 7) == 0);      // M is even: b*M keeps 8-byte alignment
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
-        int shift = prefetch_block(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), HALF_IN, lane, nl);
+        int shift = prefetch_block<typename PV::MapA>(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), HALF_IN, lane, nl);
         for (uint32_t b = bfirst; b < b1; ++b) {
             cp_async_wait_all();
             ex.sync();
-            BlockLoader ld{&src, A, start + (uint64_t)b * N, valid_of(b), shift};
+            BlockLoader<typename PV::MapA> ld{&src, A, start + (uint64_t)b * N, valid_of(b), shift};
             DevSink sink;
             const int64_t lim = (int64_t)o_hi - (int64_t)b * M;
             sink.p = orow + (size_t)b * M;
@@ -255,7 +259,7 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
             sink.vec = vec;
             int next_shift = 0;
             PV::template block<float2>(ex, PL, T, A, B, carry, ld, sink, [&] {
-                if (b + 1 < b1) next_shift = prefetch_block(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), HALF_IN, lane, nl);
+                if (b + 1 < b1) next_shift = prefetch_block<typename PV::MapA>(src, A, start + (uint64_t)(b + 1) * N, valid_of(b + 1), HALF_IN, lane, nl);
             });
             shift = next_shift;
         }
@@ -285,14 +289,14 @@ __device__ __forceinline__ void conv_pair(int a, int b, int shift, float& re, fl
 // Loader of one block of the two streams.  KIND: 0 = S16 stereo staged in A, 1 = S16 mono staged in A,
 // 2 = direct global loads (other formats).  FULL: both streams hold `n` valid frames (interior block),
 // so only the odd tail sample needs zeroing.
-template <int KIND, bool FULL>
+template <int KIND, bool FULL, class AM>
 struct DualLoaderT {
     const Source* src; const float4* A; DualStream s0, s1; int n;
     __device__ __forceinline__ cx2 operator()(int e) const {
         const int i0 = 2 * e;
         float r0 = 0.f, m0 = 0.f, r1 = 0.f, m1 = 0.f;
         if constexpr (KIND != 2) {
-            const int4 v = *reinterpret_cast<const int4*>(A + e);
+            const int4 v = *reinterpret_cast<const int4*>(A + AM::at(e));
             conv_pair<KIND>(v.x, v.y, s0.shift, r0, m0);
             conv_pair<KIND>(v.z, v.w, s1.shift, r1, m1);
             if constexpr (FULL) {
@@ -314,14 +318,14 @@ struct DualLoaderT {
     }
 };
 // picks the interior-block loader once per block (k2_warp.cuh: loader_pick); the test is uniform over the group
-template <int KIND>
+template <int KIND, class AM>
 struct DualLoaderSet {
     const Source* src; const float4* A; DualStream s0, s1; int n;
     template <class F> __device__ __forceinline__ void pick(F&& f) const {
-        if constexpr (KIND == 2) f(DualLoaderT<2, false>{src, A, s0, s1, n});
+        if constexpr (KIND == 2) f(DualLoaderT<2, false, AM>{src, A, s0, s1, n});
         else {
-            if (s0.valid == n && s1.valid == n) f(DualLoaderT<KIND, true>{src, A, s0, s1, n});
-            else f(DualLoaderT<KIND, false>{src, A, s0, s1, n});
+            if (s0.valid == n && s1.valid == n) f(DualLoaderT<KIND, true, AM>{src, A, s0, s1, n});
+            else f(DualLoaderT<KIND, false, AM>{src, A, s0, s1, n});
         }
     }
 };
@@ -337,7 +341,7 @@ __device__ __forceinline__ void cp_async8_full(void* smem_dst, const void* gsrc)
 
 // stage one stream's raw PCM of a block into its 8-byte half of the float4 slots.  Interior blocks (all
 // `n_full` frames valid and the rounded-up copy inside the buffer) take a loop without bounds arithmetic.
-template <int KIND>
+template <int KIND, class AM>
 __device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int half, uint64_t base, int valid, int half_in, int n_full,
                                              int lane, int nl) {
     int shift = 0;
@@ -347,15 +351,14 @@ __device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int hal
         const bool al8 = (reinterpret_cast<uintptr_t>(g0) & 7) == 0;
         if (valid == n_full && g0 + (size_t)half_in * 8 <= s.pcm_end) {
             const char* g = g0 + (size_t)lane * 8;
-            char* d = dst0 + (size_t)lane * 16;
-            if (al8) for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 8, d += (size_t)nl * 16) cp_async8_full(d, g);
-            else for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 8, d += (size_t)nl * 16) { cp_async4_full(d, g); cp_async4_full(d + 4, g + 4); }
+            if (al8) for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 8) cp_async8_full(dst0 + (size_t)AM::at(n) * 16, g);
+            else for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 8) { char* d = dst0 + (size_t)AM::at(n) * 16; cp_async4_full(d, g); cp_async4_full(d + 4, g + 4); }
             return 0;
         }
         for (int n = lane; n < half_in; n += nl) {
             if (2 * n >= valid) break;
             const char* g = g0 + (size_t)n * 8;
-            char* d = dst0 + (size_t)n * 16;
+            char* d = dst0 + (size_t)AM::at(n) * 16;
             const long long room = s.pcm_end - g;
             if (al8) cp_async8(d, g, room >= 8 ? 8 : (room > 0 ? (int)room : 0));
             else { cp_async4(d, g, room >= 4 ? 4 : 0); cp_async4(d + 4, g + 4, room >= 8 ? 4 : 0); }
@@ -367,15 +370,14 @@ __device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int hal
         g0 -= odd ? 2 : 0;
         if (valid == n_full && g0 + (size_t)half_in * 4 + 4 <= s.pcm_end) {
             const char* g = g0 + (size_t)lane * 4;
-            char* d = dst0 + (size_t)lane * 16;
-            if (!odd) for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 4, d += (size_t)nl * 16) cp_async4_full(d, g);
-            else for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 4, d += (size_t)nl * 16) { cp_async4_full(d, g); cp_async4_full(d + 4, g + 4); }
+            if (!odd) for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 4) cp_async4_full(dst0 + (size_t)AM::at(n) * 16, g);
+            else for (int n = lane; n < half_in; n += nl, g += (size_t)nl * 4) { char* d = dst0 + (size_t)AM::at(n) * 16; cp_async4_full(d, g); cp_async4_full(d + 4, g + 4); }
             return shift;
         }
         for (int n = lane; n < half_in; n += nl) {
             if (2 * n >= valid) break;
             const char* g = g0 + (size_t)n * 4;
-            char* d = dst0 + (size_t)n * 16;
+            char* d = dst0 + (size_t)AM::at(n) * 16;
             const long long room = s.pcm_end - g;
             cp_async4(d, g, room >= 4 ? 4 : (room > 0 ? (int)room : 0));
             if (odd) cp_async4(d + 4, g + 4, room >= 8 ? 4 : (room > 4 ? (int)(room - 4) : 0));
@@ -387,7 +389,7 @@ __device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int hal
 // Stage the raw PCM of one block of BOTH streams.  Interior blocks use a lane mapping in which consecutive lanes
 // fill adjacent 4- or 8-byte pieces of the same float4 slot, so a warp's cp.async writes cover contiguous shared
 // memory (no bank conflicts); anything else goes stream by stream through prefetch_half.
-template <int KIND>
+template <int KIND, class AM>
 __device__ __forceinline__ void prefetch_pair(const Source& s, float4* A, DualStream& a, DualStream& b, int half_in, int n_full,
                                               int lane, int nl) {
     if constexpr (KIND == 0) {
@@ -398,13 +400,13 @@ __device__ __forceinline__ void prefetch_pair(const Source& s, float4* A, DualSt
             if (((reinterpret_cast<uintptr_t>(g0) | reinterpret_cast<uintptr_t>(g1)) & 7) == 0) {
                 const int st = lane & 1, n0 = lane >> 1, dn = nl >> 1;
                 const char* g = (st ? g1 : g0) + (size_t)n0 * 8;
-                char* d = reinterpret_cast<char*>(A) + (size_t)n0 * 16 + st * 8;
-                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 8, d += (size_t)dn * 16) cp_async8_full(d, g);
+                char* d = reinterpret_cast<char*>(A) + st * 8;
+                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 8) cp_async8_full(d + (size_t)AM::at(n) * 16, g);
             } else {
                 const int qd = lane & 3, n0 = lane >> 2, dn = nl >> 2;
                 const char* g = ((qd >> 1) ? g1 : g0) + (size_t)n0 * 8 + (qd & 1) * 4;
-                char* d = reinterpret_cast<char*>(A) + (size_t)n0 * 16 + qd * 4;
-                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 8, d += (size_t)dn * 16) cp_async4_full(d, g);
+                char* d = reinterpret_cast<char*>(A) + qd * 4;
+                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 8) cp_async4_full(d + (size_t)AM::at(n) * 16, g);
             }
             return;
         }
@@ -418,19 +420,19 @@ __device__ __forceinline__ void prefetch_pair(const Source& s, float4* A, DualSt
             if (!odd0 && !odd1) {                       // one aligned word per frame pair and stream
                 const int st = lane & 1, n0 = lane >> 1, dn = nl >> 1;
                 const char* g = (st ? g1 : g0) + (size_t)n0 * 4;
-                char* d = reinterpret_cast<char*>(A) + (size_t)n0 * 16 + st * 8;
-                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 4, d += (size_t)dn * 16) cp_async4_full(d, g);
+                char* d = reinterpret_cast<char*>(A) + st * 8;
+                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 4) cp_async4_full(d + (size_t)AM::at(n) * 16, g);
             } else {                                    // two words (the funnel shift picks the pair)
                 const int qd = lane & 3, n0 = lane >> 2, dn = nl >> 2;
                 const char* g = ((qd >> 1) ? g1 : g0) + (size_t)n0 * 4 + (qd & 1) * 4;
-                char* d = reinterpret_cast<char*>(A) + (size_t)n0 * 16 + qd * 4;
-                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 4, d += (size_t)dn * 16) cp_async4_full(d, g);
+                char* d = reinterpret_cast<char*>(A) + qd * 4;
+                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 4) cp_async4_full(d + (size_t)AM::at(n) * 16, g);
             }
             return;
         }
     }
-    a.shift = prefetch_half<KIND>(s, A, 0, a.base, a.valid, half_in, n_full, lane, nl);
-    b.shift = prefetch_half<KIND>(s, A, 1, b.base, b.valid, half_in, n_full, lane, nl);
+    a.shift = prefetch_half<KIND, AM>(s, A, 0, a.base, a.valid, half_in, n_full, lane, nl);
+    b.shift = prefetch_half<KIND, AM>(s, A, 1, b.base, b.valid, half_in, n_full, lane, nl);
 }
 
 struct DualSink {
@@ -526,11 +528,11 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
         for (int j = lane; j < M / 2; j += nl) carry[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
         DualStream c0 = stream_of(0, bfirst), c1 = stream_of(1, bfirst);
-        prefetch_pair<KIND>(src, A, c0, c1, HALF_IN, N, lane, nl);
+        prefetch_pair<KIND, typename PV::MapA>(src, A, c0, c1, HALF_IN, N, lane, nl);
         for (uint32_t b = bfirst; b < b1; ++b) {
             cp_async_wait_all();
             ex.sync();
-            DualLoaderSet<KIND> ld{&src, A, c0, c1, N};
+            DualLoaderSet<KIND, typename PV::MapA> ld{&src, A, c0, c1, N};
             DualSink sink;
             const int64_t lim = (int64_t)o_hi - (int64_t)b * M;
             const int l = b < b0 ? 0 : (int)(lim < 0 ? 0 : (lim > M ? M : lim));   // recomputed block: carry only
@@ -541,7 +543,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
             PV::template block<cx2>(ex, PL, T, A, B, carry, ld, sink, [&] {
                 if (b + 1 < b1) {
                     n0 = stream_of(0, b + 1); n1 = stream_of(1, b + 1);
-                    prefetch_pair<KIND>(src, A, n0, n1, HALF_IN, N, lane, nl);
+                    prefetch_pair<KIND, typename PV::MapA>(src, A, n0, n1, HALF_IN, N, lane, nl);
                 }
             });
             c0 = n0; c1 = n1;
@@ -549,8 +551,9 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     }
 }
 
+template <class AM>
 __global__ void __launch_bounds__(kMaxThreads, 1)
-resample_warp_kernel(const __grid_constant__ WarpParams P) { resample_body<RtView>(P); }
+resample_warp_kernel(const __grid_constant__ WarpParams P) { resample_body<RtView<AM>>(P); }
 
 template <class PL>
 __global__ void __launch_bounds__(kMaxThreads, 1)
@@ -610,7 +613,8 @@ bool warp_plan_available(const ResamplerSpec& spec) {
     if (const char* g = std::getenv("BIRDA_K2_GENERIC")) if (g[0] == '1') return false;
     RtPlan P; std::vector<int> f, i;
     if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &f, &i)) return false;
-    const size_t per_group = (size_t)spec.n_in * 8 + (size_t)spec.n_out * 8 + (size_t)spec.n_out * 4 + 48;
+    rt_plan_pads(&P);
+    const size_t per_group = (size_t)phys_len(P.N, P.pad_a) * 8 + (size_t)phys_len(P.M, P.pad_b) * 8 + (size_t)spec.n_out * 4 + 48;
     const size_t tables = ((size_t)P.twf_len + P.twi_len) * 8 + (size_t)P.split_len * 56 + 512;
     return per_group + tables < kSmemMax;        // at least one block in flight next to the tables
 }
@@ -625,6 +629,7 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
 #undef BB_CT
         if (!build_plan_from_radices((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
     } else if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
+    if (rs->ct_index >= 0) ct_plan_pads(&P); else rt_plan_pads(&P);
     std::vector<uint16_t> pf(P.N), pi_(P.M);
     build_pos_tables(fwd, inv, P.N, P.M, pf.data(), pi_.data());
     std::vector<float2> Pt(P.nkeep), Qt(P.nkeep), WI(P.M / 2 + 1), twf(P.twf_len), twi(P.twi_len);
@@ -632,7 +637,8 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     build_twiddles(P, twf.data(), twi.data());
     // bank groups: 8 lanes of 16-byte elements in two-stream mode (compile-time plans), 16 lanes of 8-byte ones otherwise
     SplitLayout SL;
-    build_split_layout(P.N, P.M, P.nkeep, pf.data(), pi_.data(), Pt.data(), Qt.data(), WI.data(), rs->ct_index >= 0 ? 8 : 16, &SL);
+    build_split_layout(P.N, P.M, P.nkeep, pf.data(), pi_.data(), Pt.data(), Qt.data(), WI.data(), rs->ct_index >= 0 ? 8 : 16, &SL,
+                       P.pad_a, P.pad_b);
     auto up = [](const void* h, size_t bytes, void** d) -> cudaError_t {
         cudaError_t e = cudaMalloc(d, bytes);
         if (e != cudaSuccess) return e;
@@ -703,8 +709,8 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     P.off_WI = P.off_pq2 + a16((size_t)PL.split_len * 16);
     P.off_items = P.off_WI + a16((size_t)PL.split_len * 8);
     P.tables = P.off_items + a16((size_t)kMaxGroups * 8);
-    P.off_B = a16((size_t)PL.N * esz);
-    P.off_carry = P.off_B + a16((size_t)PL.M * esz);
+    P.off_B = a16((size_t)phys_len(PL.N, PL.pad_a) * esz);
+    P.off_carry = P.off_B + a16((size_t)phys_len(PL.M, PL.pad_b) * esz);
     P.per_group = P.off_carry + a16((size_t)(PL.M / 2) * esz);
 #ifdef BB_K2W_FAKE_CARRY        // timing experiment only (wrong results): the carry aliases A, one more group fits
     P.per_group = P.off_carry; P.off_carry = 0;
@@ -761,9 +767,15 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     BB_K2_CT_PLANS(BB_CT)
 #undef BB_CT
     if (!launched) {
-        e = cudaFuncSetAttribute(resample_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        resample_warp_kernel<<<(unsigned)ctas, threads, smem, st>>>(P);
+        if (PL.pad_a) {
+            e = cudaFuncSetAttribute(resample_warp_kernel<MapPad8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            resample_warp_kernel<MapPad8><<<(unsigned)ctas, threads, smem, st>>>(P);
+        } else {
+            e = cudaFuncSetAttribute(resample_warp_kernel<MapId>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            resample_warp_kernel<MapId><<<(unsigned)ctas, threads, smem, st>>>(P);
+        }
     }
     e = cudaGetLastError();
     if (e == cudaSuccess && launches) *launches = 1;

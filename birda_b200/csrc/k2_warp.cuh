@@ -16,6 +16,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <type_traits>
 #include <utility>
 #include <vector>
 #include "fft_butterflies.cuh"
@@ -94,6 +95,7 @@ struct RtPlan {
     int nf, ni;
     RtStage f[kMaxStages], i[kMaxStages];
     int twf_len, twi_len;        // compact twiddle table sizes (float2 entries)
+    int pad_a, pad_b;            // 1: the forward (A) / inverse (B) buffer uses MapPad8 (one slot of padding after every eight)
     int split_len;               // pairs (k, M-k) the split pass visits = M/2 + 1 (order and addresses come from a host-built table)
 };
 
@@ -174,28 +176,28 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 }
 
 // ---- inverse DIT stage, in place
-template <int R, class C, class S>
+template <int R, class C, class AM = MapId, class S>
 BB_HD void dit_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl) {
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < s.NBF_(); q += nl) {
         int sb, p;
         s.decompose(q, sb, p);
-        typename Mem<C>::T* __restrict__ e = buf + sb * s.SPAN_() + p;
+        const int e = sb * s.SPAN_() + p;
         C a[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(e + j * m);
+        for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(buf + AM::at(e + j * m));
         if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, p);
         Dft<R, true>::run(a);
 #pragma unroll
-        for (int k = 0; k < R; ++k) Mem<C>::st(e + k * m, a[k]);
+        for (int k = 0; k < R; ++k) Mem<C>::st(buf + AM::at(e + k * m), a[k]);
     }
 }
 
 // last inverse stage (span == M): output z'[n] = (y[2n], y[2n+1]).  n < M/2: add the carry and emit;
 // n >= M/2: becomes the carry of the next block.  R even, so both halves of one carry slot belong
 // to the same butterfly (no cross-lane hazard).
-template <int R, class C, class S, class Sink>
+template <int R, class C, class AM = MapId, class S, class Sink>
 BB_HD void dit_last(const typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s,
                     typename Mem<C>::T* __restrict__ carry, const Sink& sink, int lane, int nl) {
     const int m = s.M_();
@@ -203,7 +205,7 @@ BB_UNROLL_N(BB_K2W_UNROLL)
     for (int p = lane; p < m; p += nl) {
         C a[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(buf + p + j * m);
+        for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(buf + AM::at(p + j * m));
         if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, p);
         Dft<R, true>::run(a);
 #pragma unroll
@@ -289,33 +291,34 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 // One block, in two halves.  ex.each(f) runs f(lane, nlanes) for every lane of the thread group that owns
 // the block and orders memory between calls (device: __syncwarp or a named barrier; host harness: a loop).
 // forward half: loader -> in-place DIF in A -> (before_split) -> split / filter / re-bin into B
-template <class C, class Exec, class Loader, class BeforeSplit>
+template <class C, class AM = MapId, class Exec, class Loader, class BeforeSplit>
 BB_HD void forward_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
                         const Loader& ld, BeforeSplit&& before_split) {
     ex.each([&](int lane, int nl) {
-        BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R, C>(A, T.twf, P.f[0], P.half_in, ld, lane, nl)))
+        BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R, C, AM>(A, T.twf, P.f[0], P.half_in, ld, lane, nl)))
     });
     for (int t = 1; t < P.nf; ++t)
-        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R, C>(A, T.twf, P.f[t], lane, nl))) });
+        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R, C, AM>(A, T.twf, P.f[t], lane, nl))) });
     before_split();
     ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.split_len, lane, nl); });
 }
 // inverse half: in-place DIT in B -> overlap-add with the carry -> sink
-template <class C, class Exec, class Sink>
+template <class C, class AM = MapId, class Exec, class Sink>
 BB_HD void inverse_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry,
                         const Sink& sink) {
     for (int t = 0; t + 1 < P.ni; ++t)
-        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R, C>(B, T.twi, P.i[t], lane, nl))) });
+        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R, C, AM>(B, T.twi, P.i[t], lane, nl))) });
     ex.each([&](int lane, int nl) {
-        BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R, C>(B, T.twi, P.i[P.ni - 1], carry, sink, lane, nl)))
+        BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R, C, AM>(B, T.twi, P.i[P.ni - 1], carry, sink, lane, nl)))
     });
 }
-template <class C, class Exec, class Loader, class Sink, class AfterSplit>
+// runtime plans pad both buffers or neither (AM); the plan's pad_a / pad_b say which (rt_plan_pads)
+template <class C, class AM = MapId, class Exec, class Loader, class Sink, class AfterSplit>
 BB_HD void process_block(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
                          typename Mem<C>::T* carry, const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
-    forward_half<C>(ex, P, T, A, B, ld, [] {});
+    forward_half<C, AM>(ex, P, T, A, B, ld, [] {});
     after_split();
-    inverse_half<C>(ex, P, T, B, carry, sink);
+    inverse_half<C, AM>(ex, P, T, B, carry, sink);
 }
 
 
@@ -336,6 +339,18 @@ struct CtPlan {
     static constexpr int M = INV_::total();
     static constexpr int NKEEP = N < M ? N + 1 : M;
     static constexpr int HALF_IN = (N + 1) / 2;
+    // buffers whose length is a multiple of 64 have stride-8 stages: pad them (MapPad8) — unless the transform has
+    // two or more odd radices: their odd-stride walks are conflict-free only in the unpadded layout (measured:
+    // padding the 2240-point buffer of 1029/2240 = 7 5 8 8 costs 37 %, padding 1536 = 3 8 8 8 gains 25 %)
+    static constexpr int odd_radices(bool inverse) {
+        int c = 0;
+        if (inverse) { for (int i = 0; i < INV_::count; ++i) c += INV_::at(i) & 1; }
+        else { for (int i = 0; i < FWD::count; ++i) c += FWD::at(i) & 1; }
+        return c;
+    }
+    static constexpr bool PAD_A = N % 64 == 0 && odd_radices(false) <= 1, PAD_B = M % 64 == 0 && odd_radices(true) <= 1;
+    using MapA = typename std::conditional<PAD_A, MapPad8, MapId>::type;
+    using MapB = typename std::conditional<PAD_B, MapPad8, MapId>::type;
     static constexpr int tw_entries(int radix, int m) { return tw_table_mode(radix) ? m * (radix - 1) : m; }
     static constexpr int fwd_span(int t) { return N / FWD::prod_upto(t); }
     static constexpr int fwd_twoff(int t) {
@@ -365,7 +380,7 @@ template <class PL, class C, class Exec, int T> struct CtFwdRest {
     static BB_HD void run(const Exec& ex, typename Mem<C>::T* A, const typename Mem<C>::T* twf) {
         if constexpr (T < PL::Fwd::count) {
             using S = typename PL::template FwdStage<T>;
-            ex.each([&](int lane, int nl) { dif_stage<S::radix, C>(A, twf, S{}, lane, nl); });
+            ex.each([&](int lane, int nl) { dif_stage<S::radix, C, typename PL::MapA>(A, twf, S{}, lane, nl); });
             CtFwdRest<PL, C, Exec, T + 1>::run(ex, A, twf);
         }
     }
@@ -374,7 +389,7 @@ template <class PL, class C, class Exec, int T> struct CtInvMid {
     static BB_HD void run(const Exec& ex, typename Mem<C>::T* B, const typename Mem<C>::T* twi) {
         if constexpr (T + 1 < PL::Inv::count) {
             using S = typename PL::template InvStage<T>;
-            ex.each([&](int lane, int nl) { dit_stage<S::radix, C>(B, twi, S{}, lane, nl); });
+            ex.each([&](int lane, int nl) { dit_stage<S::radix, C, typename PL::MapB>(B, twi, S{}, lane, nl); });
             CtInvMid<PL, C, Exec, T + 1>::run(ex, B, twi);
         }
     }
@@ -385,7 +400,7 @@ BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::
                            BeforeSplit&& before_split) {
     using S0 = typename PL::template FwdStage<0>;
     loader_pick(ld, [&](const auto& l) {
-        ex.each([&](int lane, int nl) { dif_first<S0::radix, C>(A, T.twf, S0{}, PL::HALF_IN, l, lane, nl); });
+        ex.each([&](int lane, int nl) { dif_first<S0::radix, C, typename PL::MapA>(A, T.twf, S0{}, PL::HALF_IN, l, lane, nl); });
     }, 0);
     CtFwdRest<PL, C, Exec, 1>::run(ex, A, T.twf);
     before_split();
@@ -395,7 +410,7 @@ template <class PL, class C, class Exec, class Sink>
 BB_HD void inverse_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry, const Sink& sink) {
     CtInvMid<PL, C, Exec, 0>::run(ex, B, T.twi);
     using SL = typename PL::template InvStage<PL::Inv::count - 1>;
-    ex.each([&](int lane, int nl) { dit_last<SL::radix, C>(B, T.twi, SL{}, carry, sink, lane, nl); });
+    ex.each([&](int lane, int nl) { dit_last<SL::radix, C, typename PL::MapB>(B, T.twi, SL{}, carry, sink, lane, nl); });
 }
 template <class PL, class C, class Exec, class Loader, class Sink, class AfterSplit>
 BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
@@ -483,6 +498,7 @@ inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const st
     if (M % 2 != 0 || N >= 65536 || M >= 65536) return false;
     if ((int)fwd->size() > kMaxStages || (int)inv->size() > kMaxStages || inv->empty() || inv->back() % 2) return false;
     P->N = N; P->M = M; P->nkeep = nkeep; P->half_in = (N + 1) / 2; P->split_len = M / 2 + 1;
+    P->pad_a = 0; P->pad_b = 0;            // set by the caller: ct_plan_pads / rt_plan_pads
     P->nf = (int)fwd->size(); P->ni = (int)inv->size();
     int span = N, off = 0;
     for (int t = 0; t < P->nf; ++t) {
@@ -510,6 +526,19 @@ inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const st
     P->twi_len = off > 0 ? off : 1;
     return true;
 }
+
+// padding rules.  Compile-time plans pad each buffer on its own (CtPlan::PAD_A / PAD_B); the runtime-plan kernel has
+// one padded and one unpadded instantiation, so it pads both buffers or neither.
+inline int odd_radix_count(const RtStage* st, int n) { int c = 0; for (int t = 0; t < n; ++t) c += st[t].radix & 1; return c; }
+inline void ct_plan_pads(RtPlan* P) {                 // = CtPlan::PAD_A / PAD_B
+    P->pad_a = P->N % 64 == 0 && odd_radix_count(P->f, P->nf) <= 1;
+    P->pad_b = P->M % 64 == 0 && odd_radix_count(P->i, P->ni) <= 1;
+}
+inline void rt_plan_pads(RtPlan* P) {                 // positions stay 16-bit
+    ct_plan_pads(P);
+    P->pad_a = P->pad_b = (P->pad_a && P->pad_b && P->N < 50000 && P->M < 50000) ? 1 : 0;
+}
+inline int phys_len(int n, int pad) { return pad ? n + (n + 7) / 8 : n; }
 
 // compact per-stage twiddle tables: forward stage t holds exp(-2 pi i p / span_t), p < m_t;
 // inverse stage t holds exp(+2 pi i p / span_t), p < m_t
@@ -557,9 +586,15 @@ struct SplitLayout {
     int extra_wavefronts = 0;      // residual conflicts of the chosen order (diagnostic)
 };
 
-inline void build_split_layout(int N, int M, int nkeep, const uint16_t* pos_f, const uint16_t* pos_i,
-                               const float2* Pt, const float2* Qt, const float2* WI, int group, SplitLayout* out) {
+inline void build_split_layout(int N, int M, int nkeep, const uint16_t* pos_f_log, const uint16_t* pos_i_log,
+                               const float2* Pt, const float2* Qt, const float2* WI, int group, SplitLayout* out,
+                               int pad_a = 0, int pad_b = 0) {
     const int L = M / 2 + 1;
+    // physical positions (the buffers' address maps folded in)
+    std::vector<uint16_t> pfv(N), piv(M);
+    for (int i = 0; i < N; ++i) pfv[i] = (uint16_t)(pad_a ? MapPad8::at(pos_f_log[i]) : pos_f_log[i]);
+    for (int i = 0; i < M; ++i) piv[i] = (uint16_t)(pad_b ? MapPad8::at(pos_i_log[i]) : pos_i_log[i]);
+    const uint16_t* pos_f = pfv.data(); const uint16_t* pos_i = piv.data();
     struct Item { int v[6]; unsigned flags; };
     std::vector<Item> it(L);
     for (int k = 0; k < L; ++k) {

@@ -32,6 +32,7 @@ static int check_impl(int N, int M, int nl) {
         for (int i = 0; i < CT::Inv::count; ++i) inv.push_back(CT::Inv::at(i));
         if (!build_plan_from_radices(N, M, NKEEP, &P, &fwd, &inv)) { printf("bad ct plan\n"); return 1; }
     } else if (!build_plan(N, M, NKEEP, &P, &fwd, &inv)) { printf("N=%d M=%d: no plan (generic kernel)\n", N, M); return 0; }
+    if constexpr (kCt) ct_plan_pads(&P); else rt_plan_pads(&P);
     std::vector<uint16_t> pos_f(N), pos_i(M);
     build_pos_tables(fwd, inv, N, M, pos_f.data(), pos_i.data());
     srand(1234 + N);
@@ -46,7 +47,7 @@ static int check_impl(int N, int M, int nl) {
     build_twiddles(P, twf.data(), twi.data());
     auto twf_e = expand_table<C>(twf), twi_e = expand_table<C>(twi);
     SplitLayout SL;
-    build_split_layout(N, M, NKEEP, pos_f.data(), pos_i.data(), Pt.data(), Qt.data(), WI.data(), NS == 2 ? 8 : 16, &SL);
+    build_split_layout(N, M, NKEEP, pos_f.data(), pos_i.data(), Pt.data(), Qt.data(), WI.data(), NS == 2 ? 8 : 16, &SL, P.pad_a, P.pad_b);
     Tables<C> T{twf_e.data(), twi_e.data(), SL.sidx.data(), SL.pq1.data(), SL.pq2.data(), SL.wi.data()};
 
     const int NB = 3;
@@ -54,7 +55,7 @@ static int check_impl(int N, int M, int nl) {
     for (auto& v : x) v = (float)(rand() / (double)RAND_MAX - 0.5);
     for (auto& v : x2) v = (float)(rand() / (double)RAND_MAX - 0.5);
     const int valid_last = N - 77;                 // last block partially valid
-    std::vector<MT> A(N), B(M), carry(M / 2);
+    std::vector<MT> A(phys_len(N, P.pad_a)), B(phys_len(M, P.pad_b)), carry(M / 2);
     memset(carry.data(), 0, sizeof(MT) * carry.size());
     std::vector<float> out(NB * M, 0.f), out2(NB * M, 0.f);
     for (int b = 0; b < NB; ++b) {
@@ -69,6 +70,7 @@ static int check_impl(int N, int M, int nl) {
             else { out[b * M + 2 * n] = y.re.x; out[b * M + 2 * n + 1] = y.im.x; out2[b * M + 2 * n] = y.re.y; out2[b * M + 2 * n + 1] = y.im.y; }
         };
         if constexpr (kCt) process_block_ct<CT, C>(HostExec{nl}, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
+        else if (P.pad_a) process_block<C, MapPad8>(HostExec{nl}, P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
         else process_block<C>(HostExec{nl}, P, T, A.data(), B.data(), carry.data(), loader, sink, [] {});
     }
     double worst = 0;
@@ -96,7 +98,7 @@ static int check_impl(int N, int M, int nl) {
     for (int r : fwd) printf(" %d", r);
     printf(" ] inv[");
     for (int r : inv) printf(" %d", r);
-    printf(" ] split conflicts %d  rel err %.3e\n", SL.extra_wavefronts, worst);
+    printf(" ] pad %d%d split conflicts %d  rel err %.3e\n", P.pad_a, P.pad_b, SL.extra_wavefronts, worst);
     return worst < 5e-6 ? 0 : 1;
 }
 

@@ -19,6 +19,8 @@ if config == "c2":
     sr, ch, tr, seg, ovl, C = 44_100, 2, 48_000, 144_000, 72_000, 6522
 elif config == "c3":
     sr, ch, tr, seg, ovl, C = 48_000, 1, 32_000, 160_000, 0, 14795
+elif config.startswith("r"):          # r96000 / r32000 / r16000 / r22050: mono s16 at that rate -> 48 kHz BirdNET windows, overlap 0
+    sr, ch, tr, seg, ovl, C = int(config[1:]), 1, 48_000, 144_000, 0, 6522
 else:
     sr, ch, tr, seg, ovl, C = 256_000, 1, 256_000, 144_000, 36_000, 6522
 n = int(minutes * 60 * sr)
