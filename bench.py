@@ -342,7 +342,18 @@ def run_gpu(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    extras = side_kernels(torch, b, ctx, device, timed, args.steps) if rank == 0 else None
+    def timed_local(fn, steps):                 # rank-local (no collective): side kernels run on rank 0 only
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return float(e0.elapsed_time(e1))
+
+    extras = side_kernels(torch, b, ctx, device, timed_local, args.steps) if rank == 0 else None
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
