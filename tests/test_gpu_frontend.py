@@ -181,6 +181,35 @@ def test_resample_other_formats(ctx, dtype, fmt, channels):
     assert rel_err(out[: res.nseg], ref.segments.astype(np.float64)) <= RESAMPLE_TOL
 
 
+@pytest.mark.parametrize("sr,tr,seg,channels,skip", [
+    (44_100, 48_000, 144_000, 2, 1),      # stereo s16, device pointer 4 bytes past a 16-byte boundary: every block's staging is 4-byte aligned only
+    (44_100, 48_000, 144_000, 1, 1),      # mono s16 starting mid-word (funnel-shift path)
+    (44_100, 48_000, 144_000, 1, 2),
+    (48_000, 32_000, 160_000, 1, 3),
+    (96_000, 48_000, 144_000, 2, 3),      # padded power-of-two plan with an odd frame offset
+    (48_000, 48_000, 144_000, 1, 1),      # K1: row starts not 16-byte aligned -> general path
+    (48_000, 48_000, 144_000, 2, 3),
+])
+def test_device_pointer_at_odd_offsets(ctx, sr, tr, seg, channels, skip):
+    """The ABI takes any device pointer: interior fast paths, cp.async staging and vector loads must not assume alignment."""
+    import torch
+    full = synth_pcm(70 + skip, 9.0, sr, channels)
+    t = torch.from_numpy(full).cuda()
+    pcm = full[skip * channels:]
+    frames = pcm.size // channels
+    ref = ofe.decode_and_stream(pcm, channels, sr, tr, seg, 0, precision="f64")
+    plan = b.FrontEndPlan(ctx, sr, channels, b.FMT_S16, tr, seg, 0)
+    res = plan.run(t.data_ptr() + skip * channels * 2, frames, is_device=True)
+    ctx.sync()
+    out = res.torch().cpu().numpy().copy()
+    plan.close()
+    assert_tables(res, ref)
+    if sr == tr:
+        assert np.array_equal(out[: res.nseg], ref.segments)
+    else:
+        assert rel_err(out[: res.nseg], ref.segments.astype(np.float64)) <= RESAMPLE_TOL
+
+
 def test_resample_many_windows_split_runs(ctx):
     """Few windows -> the kernel splits each window into runs of blocks (recomputed carry)."""
     pcm = synth_pcm(21, 3.4, 44_100, 1)
