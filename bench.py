@@ -342,6 +342,8 @@ def run_gpu(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    # the same bytes as one plain pinned -> device copy: the PCIe floor of the end-to-end step on this box
+    ms_h2d_only = timed(lambda: pcm.copy_(h_pcm, non_blocking=True), args.steps) / args.steps
     def timed_local(fn, steps):                 # rank-local (no collective): side kernels run on rank 0 only
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -374,7 +376,8 @@ def run_gpu(args):
                        "ms_front_end": ms_front, "ms_post": ms_post, "host": numa_note,
                        "other_kernels": extras},
             "e2e": {"value": e2e, "unit": "audio-h/s", "h2d_bytes_per_step": int(h_pcm.numel() * 2),
-                    "d2h_bytes_per_step": int(rows * 5 * 8 + rows * 4), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": int(rows * 5 * 8 + rows * 4), "ms_per_step": ms_e2e / args.steps,
+                    "h2d_copy_alone_ms": ms_h2d_only, "frac_of_pcie_floor": ms_h2d_only / (ms_e2e / args.steps)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "resample_plan2_kernel (K2, two-stream compile-time plan 1029/1120, 640 threads)", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": k2_traffic_bytes(), "algorithmic_bytes": ALGO_BYTES_FRONT,

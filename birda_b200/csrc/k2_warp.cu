@@ -386,10 +386,36 @@ __device__ __forceinline__ int prefetch_half(const Source& s, float4* A, int hal
     return shift;
 }
 
+// One lane's share of a staging pass: slots n0, n0 + dn, ... < half_in; the piece of slot n comes from g + k * dn *
+// SRC_STRIDE (k-th step) and goes to d + map(n) * 16.  When the thread-group size is the one the kernel was built for
+// (NLH lanes, HALF slots: compile-time), the loop unrolls into cp.async instructions with immediate offsets.
+template <int BYTES, int SRC_STRIDE, int LANES_PER_SLOT, class AM, int NLH, int HALF>
+__device__ __forceinline__ void stage_loop(char* d, const char* g, int n0, int half_in, int nl) {
+    if constexpr (NLH > 0 && HALF > 0) {
+        if (nl == NLH && half_in == HALF) {
+            constexpr int DN = NLH / LANES_PER_SLOT, IT = (HALF + DN - 1) / DN;
+#pragma unroll
+            for (int k = 0; k < IT; ++k) {
+                const int n = n0 + k * DN;
+                if (k + 1 < IT || n < HALF) {
+                    if (BYTES == 8) cp_async8_full(d + (size_t)AM::at(n) * 16, g + (size_t)k * DN * SRC_STRIDE);
+                    else cp_async4_full(d + (size_t)AM::at(n) * 16, g + (size_t)k * DN * SRC_STRIDE);
+                }
+            }
+            return;
+        }
+    }
+    const int dn = nl / LANES_PER_SLOT;
+    for (int n = n0; n < half_in; n += dn, g += (size_t)dn * SRC_STRIDE) {
+        if (BYTES == 8) cp_async8_full(d + (size_t)AM::at(n) * 16, g);
+        else cp_async4_full(d + (size_t)AM::at(n) * 16, g);
+    }
+}
+
 // Stage the raw PCM of one block of BOTH streams.  Interior blocks use a lane mapping in which consecutive lanes
 // fill adjacent 4- or 8-byte pieces of the same float4 slot, so a warp's cp.async writes cover contiguous shared
 // memory (no bank conflicts); anything else goes stream by stream through prefetch_half.
-template <int KIND, class AM>
+template <int KIND, class AM, int NLH, int HALF>
 __device__ __forceinline__ void prefetch_pair(const Source& s, float4* A, DualStream& a, DualStream& b, int half_in, int n_full,
                                               int lane, int nl) {
     if constexpr (KIND == 0) {
@@ -398,15 +424,12 @@ __device__ __forceinline__ void prefetch_pair(const Source& s, float4* A, DualSt
         if (a.valid == n_full && b.valid == n_full && g0 + (size_t)half_in * 8 <= s.pcm_end && g1 + (size_t)half_in * 8 <= s.pcm_end) {
             a.shift = 0; b.shift = 0;
             if (((reinterpret_cast<uintptr_t>(g0) | reinterpret_cast<uintptr_t>(g1)) & 7) == 0) {
-                const int st = lane & 1, n0 = lane >> 1, dn = nl >> 1;
-                const char* g = (st ? g1 : g0) + (size_t)n0 * 8;
-                char* d = reinterpret_cast<char*>(A) + st * 8;
-                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 8) cp_async8_full(d + (size_t)AM::at(n) * 16, g);
+                const int st = lane & 1, n0 = lane >> 1;
+                stage_loop<8, 8, 2, AM, NLH, HALF>(reinterpret_cast<char*>(A) + st * 8, (st ? g1 : g0) + (size_t)n0 * 8, n0, half_in, nl);
             } else {
-                const int qd = lane & 3, n0 = lane >> 2, dn = nl >> 2;
-                const char* g = ((qd >> 1) ? g1 : g0) + (size_t)n0 * 8 + (qd & 1) * 4;
-                char* d = reinterpret_cast<char*>(A) + qd * 4;
-                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 8) cp_async4_full(d + (size_t)AM::at(n) * 16, g);
+                const int qd = lane & 3, n0 = lane >> 2;
+                stage_loop<4, 8, 4, AM, NLH, HALF>(reinterpret_cast<char*>(A) + qd * 4, ((qd >> 1) ? g1 : g0) + (size_t)n0 * 8 + (qd & 1) * 4,
+                                                   n0, half_in, nl);
             }
             return;
         }
@@ -418,15 +441,12 @@ __device__ __forceinline__ void prefetch_pair(const Source& s, float4* A, DualSt
         if (a.valid == n_full && b.valid == n_full && g0 + (size_t)half_in * 4 + 4 <= s.pcm_end && g1 + (size_t)half_in * 4 + 4 <= s.pcm_end) {
             a.shift = odd0 ? 16 : 0; b.shift = odd1 ? 16 : 0;
             if (!odd0 && !odd1) {                       // one aligned word per frame pair and stream
-                const int st = lane & 1, n0 = lane >> 1, dn = nl >> 1;
-                const char* g = (st ? g1 : g0) + (size_t)n0 * 4;
-                char* d = reinterpret_cast<char*>(A) + st * 8;
-                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 4) cp_async4_full(d + (size_t)AM::at(n) * 16, g);
+                const int st = lane & 1, n0 = lane >> 1;
+                stage_loop<4, 4, 2, AM, NLH, HALF>(reinterpret_cast<char*>(A) + st * 8, (st ? g1 : g0) + (size_t)n0 * 4, n0, half_in, nl);
             } else {                                    // two words (the funnel shift picks the pair)
-                const int qd = lane & 3, n0 = lane >> 2, dn = nl >> 2;
-                const char* g = ((qd >> 1) ? g1 : g0) + (size_t)n0 * 4 + (qd & 1) * 4;
-                char* d = reinterpret_cast<char*>(A) + qd * 4;
-                for (int n = n0; n < half_in; n += dn, g += (size_t)dn * 4) cp_async4_full(d + (size_t)AM::at(n) * 16, g);
+                const int qd = lane & 3, n0 = lane >> 2;
+                stage_loop<4, 4, 4, AM, NLH, HALF>(reinterpret_cast<char*>(A) + qd * 4, ((qd >> 1) ? g1 : g0) + (size_t)n0 * 4 + (qd & 1) * 4,
+                                                   n0, half_in, nl);
             }
             return;
         }
@@ -448,7 +468,7 @@ struct DualSink {
     }
 };
 
-template <class PV, int KIND>
+template <class PV, int KIND, int NLH>
 __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const RtPlan& PL = P.plan;
@@ -528,7 +548,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
         for (int j = lane; j < M / 2; j += nl) carry[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
         DualStream c0 = stream_of(0, bfirst), c1 = stream_of(1, bfirst);
-        prefetch_pair<KIND, typename PV::MapA>(src, A, c0, c1, HALF_IN, N, lane, nl);
+        prefetch_pair<KIND, typename PV::MapA, NLH, PV::half_in(RtPlan{})>(src, A, c0, c1, HALF_IN, N, lane, nl);
         for (uint32_t b = bfirst; b < b1; ++b) {
             cp_async_wait_all();
             ex.sync();
@@ -543,7 +563,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
             PV::template block<cx2>(ex, PL, T, A, B, carry, ld, sink, [&] {
                 if (b + 1 < b1) {
                     n0 = stream_of(0, b + 1); n1 = stream_of(1, b + 1);
-                    prefetch_pair<KIND, typename PV::MapA>(src, A, n0, n1, HALF_IN, N, lane, nl);
+                    prefetch_pair<KIND, typename PV::MapA, NLH, PV::half_in(RtPlan{})>(src, A, n0, n1, HALF_IN, N, lane, nl);
                 }
             });
             c0 = n0; c1 = n1;
@@ -562,7 +582,10 @@ resample_plan_kernel(const __grid_constant__ WarpParams P) { resample_body<CtVie
 // two-stream kernel; THREADS is the plan's CTA size (BB_K2_CT_PLANS): register budget and warps per group
 template <class PL, int THREADS, int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
-resample_plan2_kernel(const __grid_constant__ WarpParams P) { resample_body_dual<CtView<PL>, KIND>(P); }
+resample_plan2_kernel(const __grid_constant__ WarpParams P) {
+    // expected thread-group size (the staging loops unroll for it; any other size takes their generic form)
+    resample_body_dual<CtView<PL>, KIND, THREADS == 640 ? 160 : 64>(P);
+}
 
 // how the kernels read the PCM: 0 = S16 stereo staged with cp.async, 1 = S16 mono staged, 2 = direct loads
 int source_kind(const void* pcm, int fmt, uint32_t channels) {
@@ -712,9 +735,6 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     P.off_B = a16((size_t)phys_len(PL.N, PL.pad_a) * esz);
     P.off_carry = P.off_B + a16((size_t)phys_len(PL.M, PL.pad_b) * esz);
     P.per_group = P.off_carry + a16((size_t)(PL.M / 2) * esz);
-#ifdef BB_K2W_FAKE_CARRY        // timing experiment only (wrong results): the carry aliases A, one more group fits
-    P.per_group = P.off_carry; P.off_carry = 0;
-#endif
     if (P.tables + P.per_group > kSmemMax) {
         if (!dual) return cudaErrorInvalidConfiguration;
         // does not fit with two streams: one stream per group
