@@ -20,7 +20,7 @@ struct WarpParams {
     uint64_t src_seg, hop, nseg, last_start, rows_total, row_first, seg;
     uint32_t out_len; float* out;
     const float2 *twf, *twi, *WI; const uint4* sidx; const float4 *pq1, *pq2;     // tables in global memory
-    uint32_t nblk, R, items_per_row; uint64_t nitems;
+    uint32_t nblk, R, items_per_row; uint64_t nitems, n_whole;   // items [0, n_whole) are whole rows (pairs); the rest are runs of R blocks
     unsigned long long* counter;
     // shared memory layout (bytes)
     uint32_t off_twi, off_sidx, off_pq1, off_pq2, off_WI, off_items, tables, per_group, off_B, off_carry;
@@ -221,13 +221,14 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
         const unsigned long long item = s_items[group];
         ex.sync();
         if (item >= P.nitems) break;
-        const uint64_t lrow = item / P.items_per_row;
+        uint64_t lrow = item; uint32_t b0 = 0, b1 = P.nblk; bool last_item = true;
+        if (item >= P.n_whole) {
+            const uint64_t j = item - P.n_whole, q = j / P.items_per_row;
+            const uint32_t it = (uint32_t)(j - q * P.items_per_row);
+            lrow = P.n_whole + q; b0 = it * P.R; b1 = min(b0 + P.R, P.nblk); last_item = it + 1 == P.items_per_row;
+        }
         const uint64_t row = P.row_first + lrow;
-        const uint32_t it = (uint32_t)(item - lrow * P.items_per_row);
         float* __restrict__ orow = P.out + row * P.seg;
-        const uint32_t b0 = it * P.R;
-        const uint32_t b1 = min(b0 + P.R, P.nblk);
-        const bool last_item = it + 1 == P.items_per_row;
         const uint32_t o_lo = min(b0 * (uint32_t)M, P.out_len);
         const uint32_t o_hi = last_item ? P.out_len : min(b1 * (uint32_t)M, P.out_len);
         if (row >= P.nseg) {                         // batch-padding row: zeros (processor.rs:239-260)
@@ -513,11 +514,12 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
         const unsigned long long item = s_items[group];
         ex.sync();
         if (item >= P.nitems) break;
-        const uint64_t lpair = item / P.items_per_row;
-        const uint32_t it = (uint32_t)(item - lpair * P.items_per_row);
-        const uint32_t b0 = it * P.R;
-        const uint32_t b1 = min(b0 + P.R, P.nblk);
-        const bool last_item = it + 1 == P.items_per_row;
+        uint64_t lpair = item; uint32_t b0 = 0, b1 = P.nblk; bool last_item = true;
+        if (item >= P.n_whole) {
+            const uint64_t j = item - P.n_whole, q = j / P.items_per_row;
+            const uint32_t it = (uint32_t)(j - q * P.items_per_row);
+            lpair = P.n_whole + q; b0 = it * P.R; b1 = min(b0 + P.R, P.nblk); last_item = it + 1 == P.items_per_row;
+        }
         const uint32_t o_lo = min(b0 * (uint32_t)M, P.out_len);
         const uint32_t o_hi = last_item ? P.out_len : min(b1 * (uint32_t)M, P.out_len);
         uint64_t start[2], take[2]; float* orow[2]; bool active[2];
@@ -752,18 +754,33 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     const size_t smem = P.tables + (size_t)groups * P.per_group;
     const uint64_t units = dual ? (rows_total + 1) / 2 : rows_total;      // rows or row pairs
     const uint64_t total_groups = (uint64_t)sm_count * groups;
-    // blocks per work item: aim for >= 8 items per group, keep the recomputed block a small fraction
-    uint32_t R = P.nblk;
-    const uint64_t want_items = total_groups * 8;
-    if (units < want_items) {
-        uint64_t per_row = (want_items + units - 1) / units;
-        R = (uint32_t)((P.nblk + per_row - 1) / per_row);
-        if (R < 16) R = 16;
-        if (R > P.nblk) R = P.nblk;
+    // Work items, handed out in order by an atomic counter.  While there are at least as many rows (pairs) left as
+    // thread groups, an item is a WHOLE row: equal items, no recomputed block, every group gets the same number.  The
+    // rows that remain are cut into runs of R blocks (each run recomputes the block before it for its carry); R is the
+    // one that minimises the modelled makespan of that last phase, rounds x (R + 1) block times.  (The earlier rule —
+    // about eight equal items per group — left 4800 items for 592 groups on C2: a ninth, nearly empty round.)
+    uint64_t n_whole = (units / total_groups) * total_groups;
+    const uint64_t rem = units - n_whole;
+    uint32_t R = P.nblk, ipr = 1;
+    if (rem > 0) {
+        uint64_t best = ~0ull;
+        for (uint32_t pieces = 1; pieces <= P.nblk; ++pieces) {
+            const uint32_t r = (P.nblk + pieces - 1) / pieces;
+            if (pieces > 1 && r < 8) break;
+            const uint32_t ip = (P.nblk + r - 1) / r;
+            const uint64_t rounds = (rem * ip + total_groups - 1) / total_groups;
+            const uint64_t t = rounds * (r + (ip > 1 ? 1u : 0u));
+            if (t < best) { best = t; R = r; ipr = ip; }
+        }
+    }
+    if (const char* g = std::getenv("BIRDA_K2_ITEM_BLOCKS")) {          // tests: force short runs everywhere
+        const int v = atoi(g);
+        if (v >= 1) { n_whole = 0; R = (uint32_t)v < P.nblk ? (uint32_t)v : P.nblk; ipr = (P.nblk + R - 1) / R; }
     }
     P.R = R;
-    P.items_per_row = (P.nblk + R - 1) / R;
-    P.nitems = units * P.items_per_row;
+    P.items_per_row = ipr;
+    P.n_whole = n_whole;
+    P.nitems = n_whole + (units - n_whole) * ipr;
     cudaError_t e = cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     uint64_t ctas = (P.nitems + groups - 1) / groups;

@@ -49,6 +49,48 @@ def test_c2_full_hour_spot_rows_and_tables(ctx):
     plan.close()
 
 
+def test_c2_full_hour_device_resident_whole_and_split_items(ctx):
+    """C2 from a device-resident buffer = ONE K2 launch over all 2432 rows: the first 1184 row pairs are whole-row work
+    items, the last 32 pairs are cut into short runs with a recomputed carry block.  Rows of both kinds are checked."""
+    import torch
+    base = synth_pcm(5, 60.0, 44_100, 2).reshape(-1, 2)
+    pcm = np.tile(base, (60, 1)); pcm[:: 9967, 1] -= 23
+    pcm = np.ascontiguousarray(pcm).reshape(-1)
+    d = torch.from_numpy(pcm).cuda()
+    plan = b.FrontEndPlan(ctx, 44_100, 2, b.FMT_S16, 48_000, 144_000, 72_000)
+    res = plan.run(d, pad_to_batch=64); ctx.sync()
+    assert (res.nseg, res.rows) == (2400, 2432)
+    rows = [0, 1, 500, 1183, 1184, 2366, 2367, 2368, 2369, 2383, 2390, 2398, 2399]
+    ref = ofe.decode_and_stream(pcm, 2, 44_100, 48_000, 144_000, 72_000, precision="f64", only=rows)
+    assert np.array_equal(res.start_sample, ref.start_sample)
+    out = res.torch()
+    got = out[torch.tensor(rows, device=out.device)].cpu().numpy()
+    assert rel_err(got, ref.segments[rows].astype(np.float64)) <= 1e-5
+    assert not bool(out[2400:].any())
+    plan.close()
+
+
+def test_forced_short_runs_match_whole_rows(ctx, monkeypatch):
+    """Every row cut into runs of 5 blocks (carry recomputed 25 times per row) gives the same samples as whole rows
+    to within the resampler tolerance."""
+    pcm = synth_pcm(6, 20.0, 44_100, 2)
+    import torch
+    d = torch.from_numpy(pcm).cuda()
+    plan = b.FrontEndPlan(ctx, 44_100, 2, b.FMT_S16, 48_000, 144_000, 72_000)
+    monkeypatch.setenv("BIRDA_K2_ITEM_BLOCKS", "129")
+    r = plan.run(d); ctx.sync()
+    whole = r.torch().cpu().numpy().copy()
+    monkeypatch.setenv("BIRDA_K2_ITEM_BLOCKS", "5")
+    r = plan.run(d); ctx.sync()
+    cut = r.torch().cpu().numpy().copy()
+    monkeypatch.delenv("BIRDA_K2_ITEM_BLOCKS")
+    assert whole.shape == cut.shape and whole.shape[0] >= 12
+    assert rel_err(cut, whole.astype(np.float64)) <= 2e-6
+    ref = ofe.decode_and_stream(pcm, 2, 44_100, 48_000, 144_000, 72_000, precision="f64")
+    assert rel_err(cut[: ref.segments.shape[0]], ref.segments.astype(np.float64)) <= 1e-5
+    plan.close()
+
+
 def test_c3_full_hour_perch_spot_rows(ctx):
     """C3: 1 h 48 kHz mono -> 32 kHz, 5 s windows, batch 128 -> 720 windows."""
     import torch
