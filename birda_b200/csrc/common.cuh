@@ -38,6 +38,7 @@ struct ResamplerDev {
     int ct_index = -1;                 // compile-time plan (k2_warp.cuh: BB_K2_CT_PLANS) or -1
     float2 *f_twf = nullptr, *f_twi = nullptr, *f_WI = nullptr;
     uint4* f_sidx = nullptr; float4 *f_pq1 = nullptr, *f_pq2 = nullptr;   // split-pass layout (k2_warp.cuh: build_split_layout)
+    uint32_t *f_ordf = nullptr, *f_ordi = nullptr; uint32_t ordf_len = 0, ordi_len = 0;   // per-stage order tables (build_stage_orders)
     unsigned long long* f_counter = nullptr;
 };
 

@@ -20,6 +20,7 @@ struct WarpParams {
     uint64_t src_seg, hop, nseg, last_start, rows_total, row_first, seg;
     uint32_t out_len; float* out;
     const float2 *twf, *twi, *WI; const uint4* sidx; const float4 *pq1, *pq2;     // tables in global memory
+    const uint32_t *ordf, *ordi; uint32_t ordf_len, ordi_len, off_ordf, off_ordi;
     uint32_t nblk, R, items_per_row; uint64_t nitems, n_whole;   // items [0, n_whole) are whole rows (pairs); the rest are runs of R blocks
     unsigned long long* counter;
     // shared memory layout (bytes)
@@ -190,6 +191,10 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
     for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = P.twf[i];
     for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = P.twi[i];
     for (int i = threadIdx.x; i < PL.split_len; i += NT) { s_sidx[i] = P.sidx[i]; s_pq1[i] = P.pq1[i]; s_pq2[i] = P.pq2[i]; s_WI[i] = P.WI[i]; }
+    uint32_t* s_ordf = reinterpret_cast<uint32_t*>(smem + P.off_ordf);
+    uint32_t* s_ordi = reinterpret_cast<uint32_t*>(smem + P.off_ordi);
+    for (uint32_t i = threadIdx.x; i < P.ordf_len; i += NT) s_ordf[i] = P.ordf[i];
+    for (uint32_t i = threadIdx.x; i < P.ordi_len; i += NT) s_ordi[i] = P.ordi[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5;
@@ -204,7 +209,7 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
     float2* A = reinterpret_cast<float2*>(gbase);
     float2* B = reinterpret_cast<float2*>(gbase + P.off_B);
     float2* carry = reinterpret_cast<float2*>(gbase + P.off_carry);
-    const Tables<float2> T{s_twf, s_twi, s_sidx, s_pq1, s_pq2, s_WI};
+    const Tables<float2> T{s_twf, s_twi, s_sidx, s_pq1, s_pq2, s_WI, P.ordf_len ? s_ordf : nullptr, P.ordi_len ? s_ordi : nullptr};
     const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
 
     Source src;
@@ -484,6 +489,10 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = bc(P.twf[i]);
     for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = bc(P.twi[i]);
     for (int i = threadIdx.x; i < PL.split_len; i += NT) { s_sidx[i] = P.sidx[i]; s_pq1[i] = P.pq1[i]; s_pq2[i] = P.pq2[i]; s_WI[i] = P.WI[i]; }
+    uint32_t* s_ordf = reinterpret_cast<uint32_t*>(smem + P.off_ordf);
+    uint32_t* s_ordi = reinterpret_cast<uint32_t*>(smem + P.off_ordi);
+    for (uint32_t i = threadIdx.x; i < P.ordf_len; i += NT) s_ordf[i] = P.ordf[i];
+    for (uint32_t i = threadIdx.x; i < P.ordi_len; i += NT) s_ordi[i] = P.ordi[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5;
@@ -498,7 +507,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     float4* A = reinterpret_cast<float4*>(gbase);
     float4* B = reinterpret_cast<float4*>(gbase + P.off_B);
     float4* carry = reinterpret_cast<float4*>(gbase + P.off_carry);
-    const Tables<cx2> T{s_twf, s_twi, s_sidx, s_pq1, s_pq2, s_WI};
+    const Tables<cx2> T{s_twf, s_twi, s_sidx, s_pq1, s_pq2, s_WI, P.ordf_len ? s_ordf : nullptr, P.ordi_len ? s_ordi : nullptr};
     const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
 
     Source src;
@@ -640,7 +649,7 @@ bool warp_plan_available(const ResamplerSpec& spec) {
     if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &f, &i)) return false;
     rt_plan_pads(&P);
     const size_t per_group = (size_t)phys_len(P.N, P.pad_a) * 8 + (size_t)phys_len(P.M, P.pad_b) * 8 + (size_t)spec.n_out * 4 + 48;
-    const size_t tables = ((size_t)P.twf_len + P.twi_len) * 8 + (size_t)P.split_len * 56 + 512;
+    const size_t tables = ((size_t)P.twf_len + P.twi_len) * 8 + (size_t)P.split_len * 56 + ((size_t)P.N + P.M) * 4 + 512;
     return per_group + tables < kSmemMax;        // at least one block in flight next to the tables
 }
 
@@ -655,6 +664,10 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
         if (!build_plan_from_radices((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
     } else if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
     if (rs->ct_index >= 0) ct_plan_pads(&P); else rt_plan_pads(&P);
+    // order tables: groups of 8 lanes for the two-stream kernels of compile-time plans (their offsets are compile-time,
+    // the single-stream kernels of those plans ignore the tables), groups of 16 for the runtime-plan kernel
+    std::vector<uint32_t> ordf, ordi;
+    build_stage_orders(&P, rs->ct_index >= 0 ? 8 : 16, rs->ct_index < 0, &ordf, &ordi);
     std::vector<uint16_t> pf(P.N), pi_(P.M);
     build_pos_tables(fwd, inv, P.N, P.M, pf.data(), pi_.data());
     std::vector<float2> Pt(P.nkeep), Qt(P.nkeep), WI(P.M / 2 + 1), twf(P.twf_len), twi(P.twi_len);
@@ -676,6 +689,9 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     if ((e = up(SL.pq1.data(), SL.pq1.size() * 16, (void**)&rs->f_pq1)) != cudaSuccess) return e;
     if ((e = up(SL.pq2.data(), SL.pq2.size() * 16, (void**)&rs->f_pq2)) != cudaSuccess) return e;
     if ((e = up(SL.wi.data(), SL.wi.size() * 8, (void**)&rs->f_WI)) != cudaSuccess) return e;
+    rs->ordf_len = (uint32_t)ordf.size(); rs->ordi_len = (uint32_t)ordi.size();
+    if (!ordf.empty() && (e = up(ordf.data(), ordf.size() * 4, (void**)&rs->f_ordf)) != cudaSuccess) return e;
+    if (!ordi.empty() && (e = up(ordi.data(), ordi.size() * 4, (void**)&rs->f_ordi)) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&rs->f_counter, sizeof(unsigned long long))) != cudaSuccess) return e;
     static_assert(sizeof(RtPlan) <= sizeof(rs->plan_blob), "plan blob too small");
     memcpy(rs->plan_blob, &P, sizeof(P));
@@ -684,9 +700,9 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
 }
 
 void warp_tables_free(ResamplerDev* rs) {
-    void* ptrs[] = {rs->f_twf, rs->f_twi, rs->f_sidx, rs->f_pq1, rs->f_pq2, rs->f_WI, rs->f_counter};
+    void* ptrs[] = {rs->f_twf, rs->f_twi, rs->f_sidx, rs->f_pq1, rs->f_pq2, rs->f_WI, rs->f_counter, rs->f_ordf, rs->f_ordi};
     for (void* p : ptrs) if (p) cudaFree(p);
-    rs->f_twf = rs->f_twi = rs->f_WI = nullptr; rs->f_sidx = nullptr; rs->f_pq1 = rs->f_pq2 = nullptr; rs->f_counter = nullptr;
+    rs->f_twf = rs->f_twi = rs->f_WI = nullptr; rs->f_sidx = nullptr; rs->f_pq1 = rs->f_pq2 = nullptr; rs->f_counter = nullptr; rs->f_ordf = rs->f_ordi = nullptr; rs->ordf_len = rs->ordi_len = 0;
     rs->fast = false;
 }
 
@@ -717,6 +733,7 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     P.out_len = (uint32_t)(resampled_len < seg ? resampled_len : seg);
     P.out = d_out;
     P.twf = rs.f_twf; P.twi = rs.f_twi; P.WI = rs.f_WI; P.sidx = rs.f_sidx; P.pq1 = rs.f_pq1; P.pq2 = rs.f_pq2;
+    P.ordf = rs.f_ordf; P.ordi = rs.f_ordi; P.ordf_len = rs.ordf_len; P.ordi_len = rs.ordi_len;
     P.counter = rs.f_counter;
     P.nblk = (P.out_len + rs.n_out - 1) / rs.n_out;
     if (P.nblk == 0) P.nblk = 1;
@@ -732,7 +749,9 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     P.off_pq1 = P.off_sidx + a16((size_t)PL.split_len * 16);       // split tables have the same layout in both modes
     P.off_pq2 = P.off_pq1 + a16((size_t)PL.split_len * 16);
     P.off_WI = P.off_pq2 + a16((size_t)PL.split_len * 16);
-    P.off_items = P.off_WI + a16((size_t)PL.split_len * 8);
+    P.off_ordf = P.off_WI + a16((size_t)PL.split_len * 8);
+    P.off_ordi = P.off_ordf + a16((size_t)P.ordf_len * 4);
+    P.off_items = P.off_ordi + a16((size_t)P.ordi_len * 4);
     P.tables = P.off_items + a16((size_t)kMaxGroups * 8);
     P.off_B = a16((size_t)phys_len(PL.N, PL.pad_a) * esz);
     P.off_carry = P.off_B + a16((size_t)phys_len(PL.M, PL.pad_b) * esz);

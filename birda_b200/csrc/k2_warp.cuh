@@ -37,6 +37,8 @@ BB_HD constexpr bool tw_table_mode(int radix) { return radix >= BB_K2W_TABLE_RAD
 #define BB_PRAGMA(x) _Pragma(#x)
 #define BB_UNROLL_N(n) BB_PRAGMA(unroll n)
 
+template <class C> struct Mem;
+
 struct RtStage {
     int radix;      // butterfly size
     int span;       // DIF: sub-transform length n_t;  DIT: n_t = m * radix
@@ -47,6 +49,8 @@ struct RtStage {
     int nsb;        // sub-transforms in the stage = nbf / m
     uint32_t magic_nsb;
     int sbfast;     // 1: consecutive lanes walk sub-transforms (stride = span, odd) instead of p (see decompose)
+    int ord_off;    // offset of the stage's order table (build_stage_orders), -1 = default mapping
+    template <class C> BB_HD int ordoff() const { return ord_off; }
     BB_HD int M_() const { return m; }
     BB_HD int SPAN_() const { return span; }
     BB_HD int NBF_() const { return nbf; }
@@ -73,17 +77,49 @@ struct RtStage {
     }
 };
 
-// the same stage with every quantity a compile-time constant (strides become immediate offsets)
-template <int RADIX, int SPAN, int NTOT, int TWOFF>
+// ---- lane -> butterfly mapping of a middle stage and its bank behaviour
+// Default mapping of butterfly q: position p fastest (sub-transform sb = q / m), or sub-transform fastest for short
+// odd-span stages (SBFAST).  A butterfly touches slots e + j*m, e = sb*span + p, one j per instruction, so the lanes
+// served together (8 with 16-byte elements, 16 with 8-byte ones: `group`) collide exactly when their e share a
+// residue mod `group`.  stage_default_conflicts counts the extra wavefronts of one pass over the stage; stages that
+// lose more than 10 % that way read their (e, p) from a host-built order table instead (build_stage_orders).
+BB_HD constexpr bool stage_sbfast(int span, int m, int ntot) { return m < 16 && (span % 2) == 1 && ntot / span >= 8; }
+BB_HD constexpr int stage_default_conflicts(int span, int m, int ntot, int group, bool pad) {
+    const int radix = span / m, nbf = ntot / radix, nsb = ntot / span;
+    const bool sbf = stage_sbfast(span, m, ntot);
+    int cost = 0;
+    for (int q0 = 0; q0 < nbf; q0 += group) {
+        int cnt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+        for (int q = q0; q < q0 + group && q < nbf; ++q) {
+            int sb = 0, p = 0;
+            if (sbf) { p = q / nsb; sb = q - p * nsb; } else { sb = q / m; p = q - sb * m; }
+            int e = sb * span + p;
+            if (pad) e += e >> 3;
+            const int r = ++cnt[e % group];
+            mx = r > mx ? r : mx;
+        }
+        cost += mx - 1;
+    }
+    return cost;
+}
+BB_HD constexpr bool stage_wants_order(int span, int m, int ntot, int group, bool pad) {
+    const int nbf = ntot / (span / m);
+    return stage_default_conflicts(span, m, ntot, group, pad) * 10 * group > nbf;
+}
+
+// the same stage with every quantity a compile-time constant (strides become immediate offsets).
+// ORDOFF: offset of the stage's order table for the two-stream element type (16-byte slots), -1 = default mapping
+template <int RADIX, int SPAN, int NTOT, int TWOFF, int ORDOFF = -1>
 struct CtStage {
     static constexpr int radix = RADIX;
     static BB_HD constexpr int M_() { return SPAN / RADIX; }
     static BB_HD constexpr int SPAN_() { return SPAN; }
     static BB_HD constexpr int NBF_() { return NTOT / RADIX; }
     static BB_HD constexpr int TWOFF_() { return TWOFF; }
+    template <class C> static BB_HD constexpr int ordoff() { return sizeof(typename Mem<C>::T) == 16 ? ORDOFF : -1; }
     static BB_HD constexpr int div(int q) { return q / (SPAN / RADIX); }
     static constexpr int NSB = NTOT / SPAN;
-    static constexpr bool SBFAST = (SPAN / RADIX) < 16 && (SPAN % 2) == 1 && NSB >= 8;
+    static constexpr bool SBFAST = stage_sbfast(SPAN, SPAN / RADIX, NTOT);
     static BB_HD void decompose(int q, int& sb, int& p) {
         if (SBFAST) { p = q / NSB; sb = q - p * NSB; }
         else { sb = q / (SPAN / RADIX); p = q - sb * (SPAN / RADIX); }
@@ -138,13 +174,15 @@ template <int R, class C> BB_HD void apply_twiddles(C (&a)[R], const typename Me
 
 // ---- forward DIF stage, in place
 template <int R, class C, class AM = MapId, class S>
-BB_HD void dif_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl) {
+BB_HD void dif_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl,
+                     const uint32_t* __restrict__ order = nullptr) {
     const int m = s.M_();
+    const int ooff = order != nullptr ? s.template ordoff<C>() : -1;
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < s.NBF_(); q += nl) {
-        int sb, p;
-        s.decompose(q, sb, p);
-        const int e = sb * s.SPAN_() + p;
+        int e, p;
+        if (ooff >= 0) { const uint32_t w = order[ooff + q]; e = (int)(w & 0xffffu); p = (int)(w >> 16); }
+        else { int sb; s.decompose(q, sb, p); e = sb * s.SPAN_() + p; }
         C a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(buf + AM::at(e + j * m));
@@ -177,13 +215,15 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 
 // ---- inverse DIT stage, in place
 template <int R, class C, class AM = MapId, class S>
-BB_HD void dit_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl) {
+BB_HD void dit_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl,
+                     const uint32_t* __restrict__ order = nullptr) {
     const int m = s.M_();
+    const int ooff = order != nullptr ? s.template ordoff<C>() : -1;
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int q = lane; q < s.NBF_(); q += nl) {
-        int sb, p;
-        s.decompose(q, sb, p);
-        const int e = sb * s.SPAN_() + p;
+        int e, p;
+        if (ooff >= 0) { const uint32_t w = order[ooff + q]; e = (int)(w & 0xffffu); p = (int)(w >> 16); }
+        else { int sb; s.decompose(q, sb, p); e = sb * s.SPAN_() + p; }
         C a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = Mem<C>::ld(buf + AM::at(e + j * m));
@@ -229,6 +269,7 @@ template <class C> struct Tables {
     const uint4* sidx;                       // [split_len]
     const float4* pq1; const float4* pq2;    // [split_len] (P[k], Q[k]) and (P[k2], Q[k2]); broadcast to the stream(s) at load time
     const float2* WI;                        // [split_len] exp(+i pi k / M)
+    const uint32_t* order_f; const uint32_t* order_i;   // per-stage order tables (e | p << 16), may be null
 };
 
 // ---- fused split / filter / re-bin / inverse pack:  A (digit-reversed forward result) -> B
@@ -298,7 +339,7 @@ BB_HD void forward_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typ
         BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R, C, AM>(A, T.twf, P.f[0], P.half_in, ld, lane, nl)))
     });
     for (int t = 1; t < P.nf; ++t)
-        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R, C, AM>(A, T.twf, P.f[t], lane, nl))) });
+        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R, C, AM>(A, T.twf, P.f[t], lane, nl, T.order_f))) });
     before_split();
     ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.split_len, lane, nl); });
 }
@@ -307,7 +348,7 @@ template <class C, class AM = MapId, class Exec, class Sink>
 BB_HD void inverse_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry,
                         const Sink& sink) {
     for (int t = 0; t + 1 < P.ni; ++t)
-        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R, C, AM>(B, T.twi, P.i[t], lane, nl))) });
+        ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R, C, AM>(B, T.twi, P.i[t], lane, nl, T.order_i))) });
     ex.each([&](int lane, int nl) {
         BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R, C, AM>(B, T.twi, P.i[P.ni - 1], carry, sink, lane, nl)))
     });
@@ -366,8 +407,23 @@ struct CtPlan {
         for (int u = 1; u < t; ++u) off += tw_entries(INV_::at(u), INV_::prod_upto(u));
         return off;
     }
-    template <int T> using FwdStage = CtStage<FWD::at(T), fwd_span(T), N, fwd_twoff(T)>;
-    template <int T> using InvStage = CtStage<INV_::at(T), inv_span(T), M, inv_twoff(T)>;
+    // order tables of the two-stream kernel (16-byte slots: groups of 8 lanes); same rule as build_stage_orders
+    static constexpr bool fwd_wants(int t) { return t >= 1 && stage_wants_order(fwd_span(t), fwd_span(t) / FWD::at(t), N, 8, PAD_A); }
+    static constexpr bool inv_wants(int t) { return t + 1 < INV_::count && stage_wants_order(inv_span(t), inv_span(t) / INV_::at(t), M, 8, PAD_B); }
+    static constexpr int fwd_ordoff(int t) {
+        if (!fwd_wants(t)) return -1;
+        int off = 0;
+        for (int u = 1; u < t; ++u) if (fwd_wants(u)) off += N / FWD::at(u);
+        return off;
+    }
+    static constexpr int inv_ordoff(int t) {
+        if (!inv_wants(t)) return -1;
+        int off = 0;
+        for (int u = 0; u < t; ++u) if (inv_wants(u)) off += M / INV_::at(u);
+        return off;
+    }
+    template <int T> using FwdStage = CtStage<FWD::at(T), fwd_span(T), N, fwd_twoff(T), fwd_ordoff(T)>;
+    template <int T> using InvStage = CtStage<INV_::at(T), inv_span(T), M, inv_twoff(T), inv_ordoff(T)>;
     static_assert(INV_::at(INV_::count - 1) % 2 == 0, "last inverse radix must be even");
 };
 
@@ -377,20 +433,20 @@ template <class L, class F> BB_HD auto loader_pick(const L& l, F&& f, int) -> de
 template <class L, class F> BB_HD void loader_pick(const L& l, F&& f, long) { f(l); }
 
 template <class PL, class C, class Exec, int T> struct CtFwdRest {
-    static BB_HD void run(const Exec& ex, typename Mem<C>::T* A, const typename Mem<C>::T* twf) {
+    static BB_HD void run(const Exec& ex, typename Mem<C>::T* A, const typename Mem<C>::T* twf, const uint32_t* order) {
         if constexpr (T < PL::Fwd::count) {
             using S = typename PL::template FwdStage<T>;
-            ex.each([&](int lane, int nl) { dif_stage<S::radix, C, typename PL::MapA>(A, twf, S{}, lane, nl); });
-            CtFwdRest<PL, C, Exec, T + 1>::run(ex, A, twf);
+            ex.each([&](int lane, int nl) { dif_stage<S::radix, C, typename PL::MapA>(A, twf, S{}, lane, nl, order); });
+            CtFwdRest<PL, C, Exec, T + 1>::run(ex, A, twf, order);
         }
     }
 };
 template <class PL, class C, class Exec, int T> struct CtInvMid {
-    static BB_HD void run(const Exec& ex, typename Mem<C>::T* B, const typename Mem<C>::T* twi) {
+    static BB_HD void run(const Exec& ex, typename Mem<C>::T* B, const typename Mem<C>::T* twi, const uint32_t* order) {
         if constexpr (T + 1 < PL::Inv::count) {
             using S = typename PL::template InvStage<T>;
-            ex.each([&](int lane, int nl) { dit_stage<S::radix, C, typename PL::MapB>(B, twi, S{}, lane, nl); });
-            CtInvMid<PL, C, Exec, T + 1>::run(ex, B, twi);
+            ex.each([&](int lane, int nl) { dit_stage<S::radix, C, typename PL::MapB>(B, twi, S{}, lane, nl, order); });
+            CtInvMid<PL, C, Exec, T + 1>::run(ex, B, twi, order);
         }
     }
 };
@@ -402,13 +458,13 @@ BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::
     loader_pick(ld, [&](const auto& l) {
         ex.each([&](int lane, int nl) { dif_first<S0::radix, C, typename PL::MapA>(A, T.twf, S0{}, PL::HALF_IN, l, lane, nl); });
     }, 0);
-    CtFwdRest<PL, C, Exec, 1>::run(ex, A, T.twf);
+    CtFwdRest<PL, C, Exec, 1>::run(ex, A, T.twf, T.order_f);
     before_split();
     ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::M / 2 + 1, lane, nl); });
 }
 template <class PL, class C, class Exec, class Sink>
 BB_HD void inverse_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry, const Sink& sink) {
-    CtInvMid<PL, C, Exec, 0>::run(ex, B, T.twi);
+    CtInvMid<PL, C, Exec, 0>::run(ex, B, T.twi, T.order_i);
     using SL = typename PL::template InvStage<PL::Inv::count - 1>;
     ex.each([&](int lane, int nl) { dit_last<SL::radix, C, typename PL::MapB>(B, T.twi, SL{}, carry, sink, lane, nl); });
 }
@@ -508,7 +564,7 @@ inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const st
         if (s.tw_off >= 0) off += tw_table_mode(s.radix) ? s.m * (s.radix - 1) : s.m;
         s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
         s.nsb = N / s.span; s.magic_nsb = s.nsb <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.nsb - 1) / s.nsb);
-        s.sbfast = (s.m < 16 && (s.span % 2) == 1 && s.nsb >= 8) ? 1 : 0;
+        s.sbfast = (s.m < 16 && (s.span % 2) == 1 && s.nsb >= 8) ? 1 : 0; s.ord_off = -1;
         span = s.m;
     }
     P->twf_len = off > 0 ? off : 1;
@@ -520,7 +576,7 @@ inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const st
         if (s.tw_off >= 0) off += tw_table_mode(s.radix) ? s.m * (s.radix - 1) : s.m;
         s.magic = s.m <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.m - 1) / s.m);
         s.nsb = M / s.span; s.magic_nsb = s.nsb <= 1 ? 0u : (uint32_t)(((1ull << 32) + s.nsb - 1) / s.nsb);
-        s.sbfast = (s.m < 16 && (s.span % 2) == 1 && s.nsb >= 8) ? 1 : 0;
+        s.sbfast = (s.m < 16 && (s.span % 2) == 1 && s.nsb >= 8) ? 1 : 0; s.ord_off = -1;
         prev = s.span;
     }
     P->twi_len = off > 0 ? off : 1;
@@ -572,6 +628,57 @@ inline void build_pos_tables(const std::vector<int>& fwd, const std::vector<int>
             pos += d * prev;
         }
         pos_i[n] = (uint16_t)pos;
+    }
+}
+
+// ---- per-stage order tables
+// For every middle stage whose default mapping loses more than 10 % to bank conflicts (stage_wants_order), the
+// butterflies are regrouped so that the lanes served together start at distinct residues mod `group` (and read distinct
+// twiddle residues where possible).  Entry = e | p << 16 with e = sb*span + p (logical slot) and p the twiddle index.
+// Offsets follow CtPlan::fwd_ordoff / inv_ordoff; `set_offsets` also records them in the plan (runtime-plan kernels).
+inline void build_stage_orders(RtPlan* P, int group, bool set_offsets, std::vector<uint32_t>* of, std::vector<uint32_t>* oi) {
+    auto build = [&](RtStage& s, int ntot, bool pad, std::vector<uint32_t>* out) {
+        const int nbf = s.nbf, G = group;
+        std::vector<int> e(nbf), p(nbf), r0(nbf), r1(nbf);
+        for (int q = 0; q < nbf; ++q) {
+            int sb, pp; s.decompose(q, sb, pp);
+            e[q] = sb * s.span + pp; p[q] = pp;
+            const int phys = pad ? MapPad8::at(e[q]) : e[q];
+            r0[q] = phys % G; r1[q] = pp % G;
+        }
+        (void)ntot;
+        std::vector<char> used(nbf, 0);
+        std::vector<int> order; order.reserve(nbf);
+        int left = nbf;
+        while (left > 0) {
+            bool s0[16] = {false}, s1[16] = {false};
+            for (int n = 0; n < G && left > 0; ++n) {
+                int best = -1, bc = 99;
+                for (int q = 0; q < nbf && bc > 0; ++q) {
+                    if (used[q]) continue;
+                    const int c = (s0[r0[q]] ? 4 : 0) + (s1[r1[q]] ? 1 : 0);      // data conflicts cost R accesses, twiddle ones 1
+                    if (c < bc) { bc = c; best = q; }
+                }
+                used[best] = 1; --left; order.push_back(best);
+                s0[r0[best]] = true; s1[r1[best]] = true;
+            }
+        }
+        const int off = (int)out->size();
+        for (int q : order) out->push_back((uint32_t)e[q] | ((uint32_t)p[q] << 16));
+        return off;
+    };
+    of->clear(); oi->clear();
+    for (int t = 1; t < P->nf; ++t) {
+        RtStage& s = P->f[t];
+        const bool want = stage_wants_order(s.span, s.m, P->N, group, P->pad_a != 0);
+        const int off = want ? build(s, P->N, P->pad_a != 0, of) : -1;
+        if (set_offsets) s.ord_off = off;
+    }
+    for (int t = 0; t + 1 < P->ni; ++t) {
+        RtStage& s = P->i[t];
+        const bool want = stage_wants_order(s.span, s.m, P->M, group, P->pad_b != 0);
+        const int off = want ? build(s, P->M, P->pad_b != 0, oi) : -1;
+        if (set_offsets) s.ord_off = off;
     }
 }
 

@@ -33,6 +33,9 @@ static int check_impl(int N, int M, int nl) {
         if (!build_plan_from_radices(N, M, NKEEP, &P, &fwd, &inv)) { printf("bad ct plan\n"); return 1; }
     } else if (!build_plan(N, M, NKEEP, &P, &fwd, &inv)) { printf("N=%d M=%d: no plan (generic kernel)\n", N, M); return 0; }
     if constexpr (kCt) ct_plan_pads(&P); else rt_plan_pads(&P);
+    std::vector<uint32_t> ordf, ordi;
+    build_stage_orders(&P, NS == 2 ? 8 : 16, !kCt, &ordf, &ordi);
+    if (kCt && NS == 1) { ordf.clear(); ordi.clear(); }      // single-stream kernels of compile-time plans use the default mapping
     std::vector<uint16_t> pos_f(N), pos_i(M);
     build_pos_tables(fwd, inv, N, M, pos_f.data(), pos_i.data());
     srand(1234 + N);
@@ -48,7 +51,8 @@ static int check_impl(int N, int M, int nl) {
     auto twf_e = expand_table<C>(twf), twi_e = expand_table<C>(twi);
     SplitLayout SL;
     build_split_layout(N, M, NKEEP, pos_f.data(), pos_i.data(), Pt.data(), Qt.data(), WI.data(), NS == 2 ? 8 : 16, &SL, P.pad_a, P.pad_b);
-    Tables<C> T{twf_e.data(), twi_e.data(), SL.sidx.data(), SL.pq1.data(), SL.pq2.data(), SL.wi.data()};
+    Tables<C> T{twf_e.data(), twi_e.data(), SL.sidx.data(), SL.pq1.data(), SL.pq2.data(), SL.wi.data(),
+                ordf.empty() ? nullptr : ordf.data(), ordi.empty() ? nullptr : ordi.data()};
 
     const int NB = 3;
     std::vector<float> x(NB * N), x2(NB * N);
@@ -98,7 +102,7 @@ static int check_impl(int N, int M, int nl) {
     for (int r : fwd) printf(" %d", r);
     printf(" ] inv[");
     for (int r : inv) printf(" %d", r);
-    printf(" ] pad %d%d split conflicts %d  rel err %.3e\n", P.pad_a, P.pad_b, SL.extra_wavefronts, worst);
+    printf(" ] pad %d%d orders %zu+%zu split conflicts %d  rel err %.3e\n", P.pad_a, P.pad_b, ordf.size(), ordi.size(), SL.extra_wavefronts, worst);
     return worst < 5e-6 ? 0 : 1;
 }
 
