@@ -96,6 +96,7 @@ SIGNATURES = {
     "bb_pipeline_create": (C.c_int32, [vp, C.POINTER(PipelineCfg), CLASSIFY_FN, vp, C.POINTER(vp)]),
     "bb_pipeline_destroy": (None, [vp]),
     "bb_pipeline_last_error": (C.c_char_p, [vp]),
+    "bb_pipeline_plans_created": (C.c_uint64, [vp]),
     "bb_pipeline_process_pcm": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(DetectionC),
                                             C.c_uint64, u64p, u64p, u32p]),
     "bb_pipeline_process_wav": (C.c_int32, [vp, C.c_char_p, C.c_uint64, C.POINTER(DetectionC), C.c_uint64, u64p, u64p, u32p]),

@@ -22,8 +22,15 @@ struct bb_pipeline {
     bb_pipeline_cfg cfg{};
     bb_classify_fn classify = nullptr;
     void* user = nullptr;
-    bb_plan* plan = nullptr;
+    bb_plan* plan = nullptr;                  // the plan of the file being processed (owned by `cache`)
     uint32_t plan_rate = 0, plan_channels = 0; int plan_fmt = 0;
+    // A directory mixes sample rates and channel counts (BASELINE config 5): plans are kept per (rate, channels,
+    // format), least recently used evicted, so a file only pays for plan creation (resampler tables, ~50 ms) the
+    // first time its kind is seen.
+    struct Cached { bb_plan* plan; uint32_t rate, channels; int fmt; uint64_t last_use; };
+    std::vector<Cached> cache;
+    uint64_t use_clock = 0;
+    uint64_t plans_created = 0;
     void* pinned = nullptr; uint64_t pinned_bytes = 0;
     std::vector<uint32_t> h_index; std::vector<float> h_conf; std::vector<uint32_t> h_count;
     std::vector<float> st, et; std::vector<uint64_t> ss;
@@ -34,15 +41,32 @@ namespace {
 
 int fail(bb_pipeline* p, int code, const std::string& m) { if (p) p->error = m; bb::set_tls_error(m); return code; }
 
+constexpr size_t kPlanCache = 8;
+
 int ensure_plan(bb_pipeline* p, uint32_t rate, uint32_t channels, int fmt) {
-    if (p->plan && p->plan_rate == rate && p->plan_channels == channels && p->plan_fmt == fmt) return BB_OK;
-    if (p->plan) { bb_plan_destroy(p->plan); p->plan = nullptr; }
+    ++p->use_clock;
+    for (auto& c : p->cache)
+        if (c.rate == rate && c.channels == channels && c.fmt == fmt) {
+            c.last_use = p->use_clock;
+            p->plan = c.plan; p->plan_rate = rate; p->plan_channels = channels; p->plan_fmt = fmt;
+            return BB_OK;
+        }
+    if (p->cache.size() >= kPlanCache) {
+        size_t lru = 0;
+        for (size_t i = 1; i < p->cache.size(); ++i) if (p->cache[i].last_use < p->cache[lru].last_use) lru = i;
+        bb_plan_destroy(p->cache[lru].plan);
+        p->cache.erase(p->cache.begin() + (long)lru);
+    }
+    p->plan = nullptr;
     const uint32_t target = p->cfg.bat_mode ? rate : p->cfg.target_rate;            // processor.rs:464-475
     uint64_t seg = 0, ovl = 0;
     bb_rule_segment_samples(p->cfg.segment_duration, p->cfg.overlap, target, p->cfg.bat_mode, &seg, &ovl);
-    int rc = bb_plan_create(p->ctx, rate, channels, (bb_sample_fmt)fmt, target, seg, ovl, &p->plan);
+    bb_plan* plan = nullptr;
+    int rc = bb_plan_create(p->ctx, rate, channels, (bb_sample_fmt)fmt, target, seg, ovl, &plan);
     if (rc != BB_OK) return fail(p, rc, bb_last_error(p->ctx));
-    p->plan_rate = rate; p->plan_channels = channels; p->plan_fmt = fmt;
+    p->cache.push_back({plan, rate, channels, fmt, p->use_clock});
+    ++p->plans_created;
+    p->plan = plan; p->plan_rate = rate; p->plan_channels = channels; p->plan_fmt = fmt;
     return BB_OK;
 }
 
@@ -121,12 +145,13 @@ int32_t bb_pipeline_create(bb_ctx* ctx, const bb_pipeline_cfg* cfg, bb_classify_
 
 void bb_pipeline_destroy(bb_pipeline* p) {
     if (!p) return;
-    if (p->plan) bb_plan_destroy(p->plan);
+    for (auto& c : p->cache) bb_plan_destroy(c.plan);
     if (p->pinned) bb_host_free(p->pinned);
     delete p;
 }
 
 const char* bb_pipeline_last_error(const bb_pipeline* p) { return p ? p->error.c_str() : ""; }
+uint64_t bb_pipeline_plans_created(const bb_pipeline* p) { return p ? p->plans_created : 0; }
 
 int32_t bb_pipeline_process_pcm(bb_pipeline* p, const void* pcm, uint64_t frames, uint32_t src_rate, uint32_t channels,
                                 int32_t fmt, bb_detection* out, uint64_t capacity, uint64_t* n_detections,

@@ -208,6 +208,12 @@ class NativePipeline:
         return self._collect(lambda buf, cap, nd, ns, bu: _lib.lib.bb_pipeline_process_wav(
             self._h, path.encode(), piece_frames, buf, cap, nd, ns, bu))
 
+    @property
+    def plans_created(self) -> int:
+        """Front-end plans built so far (they are cached per source rate / channels / format)."""
+        from . import _lib
+        return int(_lib.lib.bb_pipeline_plans_created(self._h))
+
     def close(self):
         from . import _lib
         if self._h:

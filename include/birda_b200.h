@@ -256,6 +256,9 @@ typedef struct {                    /* Detection fields the writers need (src/ou
 int32_t     bb_pipeline_create(bb_ctx*, const bb_pipeline_cfg*, bb_classify_fn, void* user, bb_pipeline** out);
 void        bb_pipeline_destroy(bb_pipeline*);
 const char* bb_pipeline_last_error(const bb_pipeline*);
+/* front-end plans are cached per (source rate, channels, format), 8 kinds, least recently used evicted; this counts
+ * how many were built so far (a mixed-rate directory builds each kind once) */
+uint64_t    bb_pipeline_plans_created(const bb_pipeline*);
 /* Whole decoded file in host memory.  Detections come back sorted (start_time asc, confidence desc:
  * processor.rs:178-187); BB_ERR_CAPACITY reports the needed count in *n_detections. */
 int32_t bb_pipeline_process_pcm(bb_pipeline*, const void* pcm, uint64_t frames, uint32_t src_rate, uint32_t channels,

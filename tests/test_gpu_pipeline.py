@@ -121,3 +121,38 @@ def test_native_cpp_pipeline_equals_python_mirror(tmp_path):
     r2 = nat.process_wav(p, piece_frames=44_100 * 9)
     assert r2.segments == py.segments and key(r2) == key(py)
     nat.close(); ctx.close()
+
+
+def test_native_pipeline_mixed_rate_directory_reuses_plans():
+    """BASELINE config 5 in miniature: files cycling over rates and channel counts through ONE native pipeline.
+    Every kind of file builds its plan once; results equal a fresh pipeline per file."""
+    import time
+
+    import torch
+    from birda_b200.pipeline import NativePipeline
+    C = 265
+    ctx = b.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    clf = StandInClassifier(144_000, C)
+    cfg = ProcessingConfig(target_rate=48_000, segment_duration=3.0, overlap=0.0, batch_size=4, min_confidence=0.1)
+    kinds = [(16_000, 1), (22_050, 2), (32_000, 1), (44_100, 2), (48_000, 1), (96_000, 2)]
+    files = [(sr, ch, synth_pcm(200 + i, 10.0, sr, ch)) for i, (sr, ch) in enumerate(kinds * 3)]
+    key = lambda r: [(d.segment, d.index, round(d.confidence, 6), d.start_time, d.end_time) for d in r.detections]
+    nat = NativePipeline(ctx, cfg, clf)
+    t_first, t_again, results = 0.0, 0.0, []
+    for i, (sr, ch, pcm) in enumerate(files):
+        t0 = time.perf_counter()
+        results.append(nat.process_pcm(pcm, ch, sr, b.FMT_S16))
+        dt = time.perf_counter() - t0
+        if i < len(kinds):
+            t_first += dt
+        else:
+            t_again += dt / 2
+    assert nat.plans_created == len(kinds)                     # 18 files, 6 kinds, 6 plans
+    assert t_again < t_first                                   # later passes do not pay for plan creation
+    for i in (0, 3, 7, 11, 17):                                # same detections as a pipeline that sees only this file
+        sr, ch, pcm = files[i]
+        one = NativePipeline(ctx, cfg, clf)
+        r = one.process_pcm(pcm, ch, sr, b.FMT_S16)
+        assert r.segments == results[i].segments == 4 and key(r) == key(results[i])
+        one.close()
+    nat.close(); ctx.close()
