@@ -1,4 +1,9 @@
-// K2 warp-per-block resampler kernel (runtime plans; design notes in k2_warp.cuh) and launcher.
+// K2 — convert + downmix + window gather + per-window block-FFT resample + pack (src/audio/resample.rs:10-105 over
+// src/pipeline/processor.rs:61-100 and src/audio/decode.rs:150-202, 353-411), the device kernels and their launcher.
+// The transform core is k2_warp.cuh; here: PCM staging (cp.async into the forward buffer's own slots), loaders with
+// the reference's exact sample conversion, the work-item loop (atomic counter), sinks, and three kernels over the
+// core — resample_plan2_kernel (compile-time plan, two windows per thread group, packed f32x2 math: the fast path),
+// resample_plan_kernel (compile-time plan, one window) and resample_warp_kernel (runtime plan, any supported rate pair).
 #include "common.cuh"
 #include "k2_warp.cuh"
 #include <cstdlib>

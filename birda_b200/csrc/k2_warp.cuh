@@ -1,18 +1,21 @@
-// K2 warp-per-block resampler core with RUNTIME plans (product code).
+// K2 resampler core (product code): everything the per-window block-FFT resampler does between the staged PCM of a
+// block and its output samples, written once for the device kernels (k2_warp.cu) and for the host self check
+// (tests/host_k2_check.cu runs the same templates lane by lane on the CPU).
 //
-// One warp owns a run of consecutive resampler blocks of one window:
-//   * forward half-length complex FFT in place (decimation in frequency: natural order in,
-//     digit-reversed out) in buffer A; inverse in place (decimation in time: digit-reversed in,
-//     natural order out) in buffer B; the fused split / filter / re-bin / inverse-pack pass
-//     between them absorbs both permutations through two small index tables;
-//   * radices and strides come from a small stage table, so ONE code body per (radix,
-//     direction) serves every stage and every rate pair — the kernel stays a few thousand
-//     instructions and lives in the instruction cache (the fully unrolled compile-time-plan
-//     variant was 190 KB of SASS and stalled 29 % of the time on instruction fetch);
-//   * twiddles: one conflict-free table read (w^1) per butterfly plus an in-register power chain;
-//   * the overlap-add carry is per-warp shared memory; the last inverse stage adds it and stores
-//     straight to the output tensor.
-// Everything is __host__ __device__ so tests/host_k2_check.cu runs the same code on the CPU.
+// A thread group (1-6 warps) owns a run of consecutive resampler blocks of one window — or of TWO adjacent windows in
+// lockstep (element type cx2: float4 slots, packed f32x2 math):
+//   * forward half-length complex FFT in place (decimation in frequency: natural order in, digit-reversed out) in
+//     buffer A; inverse in place (decimation in time: digit-reversed in, natural order out) in buffer B;
+//   * the fused split / filter / re-bin / inverse-pack pass between them is driven by a host-built layout
+//     (build_split_layout): per (k, M-k) pair the six positions it touches, flags, and the filter tables in visiting
+//     order, the order chosen to keep the scattered accesses off each other's banks;
+//   * stages come from a small stage table (RtPlan, one code body per radix and direction: the kernel stays in the
+//     instruction cache) or from compile-time plans (CtPlan: strides are immediates);
+//   * buffers of power-of-two-like transforms use a padded address map (MapPad8), middle stages whose default
+//     lane -> butterfly mapping conflicts read an order table (build_stage_orders);
+//   * twiddles: one conflict-free table read (w^1) per butterfly plus an in-register power chain, full tables for the
+//     big radices;
+//   * the overlap-add carry is per-group shared memory; the last inverse stage adds it and hands the samples to a sink.
 #pragma once
 #include <cmath>
 #include <cstdint>
