@@ -78,6 +78,27 @@ def test_melspec_many_rows_chunked(ctx):
     assert (np.abs(got - ref) / scale).max() <= REL_TOL
 
 
+@pytest.mark.parametrize("n_fft,hop,samples,n_frames,rows", [
+    (2048, 277, 47_999, 190, 3),     # odd hop and odd row length: unaligned frame starts, ragged tail, frames wholly past the end
+    (1024, 1, 3_000, 64, 1),         # hop 1, a single short row
+    (256, 100, 5_000, 70, 2),        # single-stream runtime-plan STFT kernel (n_fft without a two-stream plan), frames past the end
+    (4096, 512, 20_000, 9, 5),       # largest frame length
+])
+def test_melspec_edge_shapes(ctx, n_fft, hop, samples, n_frames, rows):
+    rate = 48_000
+    rng = np.random.default_rng(n_fft + hop)
+    seg = (rng.standard_normal((rows, samples)) * 0.2).astype(np.float32)
+    w, mw = om.hann(n_fft), om.mel_filterbank(32, n_fft, rate, 300.0, 20_000.0)
+    got, _ = run_gpu(ctx, seg, n_fft, hop, n_frames, w, mw)
+    ref = om.melspec(seg, n_fft, hop, n_frames, w, mw)
+    assert np.isfinite(got).all()
+    scale = np.abs(ref).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(got - ref) / scale).max() <= REL_TOL
+    past = [t for t in range(n_frames) if t * hop >= samples]
+    if past:
+        assert not got[:, :, past].any()          # frames that start past the end of the row are silence
+
+
 def test_melspec_errors(ctx):
     w, mw = om.hann(1024), om.mel_filterbank(64, 1024, 48_000, 0.0, 24000.0)
     with pytest.raises(b.BirdaError):
