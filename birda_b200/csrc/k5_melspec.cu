@@ -2,7 +2,7 @@
 // mel-filterbank kernel whose mel projection runs on tcgen05 tensor cores").
 //
 //   packed windows [rows, samples] f32 (what K1 / K2 wrote)
-//     -> K5a  stft_power_kernel : frame t = samples [t*hop, t*hop + n_fft) * window, real FFT of length n_fft as a
+//     -> K5a  stft_power2_kernel: frame t = samples [t*hop, t*hop + n_fft) * window, real FFT of length n_fft as a
 //                                 half-length complex FFT in shared memory (the K2 butterflies and stage tables),
 //                                 |X|^power of the bins the mel filters touch -> P [frames, Kpad] f32 (L2-sized chunks)
 //     -> K5b  mel_gemm_kernel   : D[frame, mel] = sum_k P[frame, k] * W[mel, k] on the 5th-gen tensor cores
@@ -38,8 +38,7 @@ namespace {
 using namespace bb::k2w;
 
 // ------------------------------------------------------------------------------------------ K5a
-constexpr int kFftThreads = 256;         // 4 groups of 2 warps; a group owns one frame at a time
-constexpr int kFftGroupWarps = 2;
+constexpr int kFftGroupWarps = 2;        // warps per thread group
 
 struct FftExec {
     int glane, nl, bar_id;
@@ -71,69 +70,7 @@ struct StftParams {
     uint32_t off_posf, off_wk, off_win, tables, per_group;
 };
 
-__global__ void __launch_bounds__(kFftThreads)
-stft_power_kernel(const __grid_constant__ StftParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const RtPlan& PL = p.plan;
-    const int N = PL.N;
-    float2* s_twf = reinterpret_cast<float2*>(smem);
-    uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + p.off_posf);
-    float2* s_wk = reinterpret_cast<float2*>(smem + p.off_wk);
-    float* s_win = reinterpret_cast<float*>(smem + p.off_win);
-    for (int i = threadIdx.x; i < PL.twf_len; i += kFftThreads) s_twf[i] = p.twf[i];
-    for (int i = threadIdx.x; i < N; i += kFftThreads) s_posf[i] = p.posf[i];
-    for (int i = threadIdx.x; i <= N; i += kFftThreads) s_wk[i] = p.wk[i];
-    for (int i = threadIdx.x; i < (int)p.n_fft; i += kFftThreads) s_win[i] = p.window[i];
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, group = warp / kFftGroupWarps;
-    constexpr int kGroups = kFftThreads / 32 / kFftGroupWarps;
-    FftExec ex;
-    ex.nl = kFftGroupWarps * 32;
-    ex.glane = (warp - group * kFftGroupWarps) * 32 + (int)(threadIdx.x & 31);
-    ex.bar_id = 1 + group;
-    const int lane = ex.glane, nl = ex.nl;
-    float2* A = reinterpret_cast<float2*>(smem + p.tables + (size_t)group * p.per_group);
-
-    for (uint64_t fi = (uint64_t)blockIdx.x * kGroups + group; fi < p.nframes; fi += (uint64_t)gridDim.x * kGroups) {
-        const uint64_t f = p.frame0 + fi;
-        const uint64_t row = f / p.n_frames;
-        const uint32_t t = (uint32_t)(f - row * p.n_frames);
-        const float* __restrict__ xr = p.x + row * p.samples;
-        const uint32_t s0 = t * p.hop;
-        // z[n] = x[s0 + 2n] w[2n] + i x[s0 + 2n + 1] w[2n + 1], zero past the end of the window
-        auto ld = [&](int n) -> float2 {
-            const uint32_t i0 = s0 + 2u * (uint32_t)n;
-            const float a = i0 < p.samples ? __ldg(xr + i0) : 0.f;
-            const float b = i0 + 1u < p.samples ? __ldg(xr + i0 + 1u) : 0.f;
-            return make_float2(a * s_win[2 * n], b * s_win[2 * n + 1]);
-        };
-        ex.each([&](int l, int n_l) { BB_K2W_RADIX_SWITCH(PL.f[0].radix, (dif_first<R, float2>(A, s_twf, PL.f[0], PL.half_in, ld, l, n_l))) });
-        for (int st = 1; st < PL.nf; ++st)
-            ex.each([&](int l, int n_l) { BB_K2W_RADIX_SWITCH(PL.f[st].radix, (dif_stage<R, float2>(A, s_twf, PL.f[st], l, n_l))) });
-        // bins of the mel support: X[k] = (Z[k] + conj Z[N-k]) / 2 - (i/2) exp(-i pi k / N) (Z[k] - conj Z[N-k])
-        float* __restrict__ Pf = p.P + fi * (2ull * p.kpad);
-        for (uint32_t j = lane; j < p.kpad; j += nl) {
-            float v = 0.f;
-            if (j < p.nb) {
-                const int k = (int)(p.bin_lo + j);
-                const float2 zk = A[s_posf[k == N ? 0 : k]], zq = A[s_posf[k == 0 ? 0 : N - k]];
-                const float2 zn = make_float2(zq.x, -zq.y);
-                const float er = 0.5f * (zk.x + zn.x), ei = 0.5f * (zk.y + zn.y);
-                const float dr = 0.5f * (zk.x - zn.x), di = 0.5f * (zk.y - zn.y);
-                const float2 w = s_wk[k];
-                // -i w d = (w.y dr + w.x di) + i (w.y di - w.x dr)
-                const float xr_ = er + (w.y * dr + w.x * di), xi_ = ei + (w.y * di - w.x * dr);
-                const float pw = xr_ * xr_ + xi_ * xi_;
-                v = p.power == 2.0f ? pw : (p.power == 1.0f ? sqrtf(pw) : powf(pw, 0.5f * p.power));
-            }
-            store_split(Pf, j, v);
-        }
-        ex.sync();                       // A is rewritten by the next frame's first stage
-    }
-}
-
-// Two-stream variant for the common frame lengths: a group transforms TWO frames at once, every element is a float4
+// A thread group transforms TWO frames at once (all power-of-two frame lengths 256..4096): every element is a float4
 // (re0, re1, im0, im1) and every butterfly instruction a packed f32x2 op (the K2 trick), stage constants are
 // compile-time.  6 groups of 2 warps per CTA: 64 lanes = the butterfly count of the radix-16 stage of N = 1024.
 constexpr int kFft2Threads = 384;
@@ -162,14 +99,15 @@ stft_power2_kernel(const __grid_constant__ StftParams p) {
     uint16_t* s_posf = reinterpret_cast<uint16_t*>(smem + p.off_posf);
     float2* s_wk = reinterpret_cast<float2*>(smem + p.off_wk);
     float2* s_win = reinterpret_cast<float2*>(smem + p.off_win);
-    for (int i = threadIdx.x; i < RP.twf_len; i += kFft2Threads) { const float2 w = p.twf[i]; s_twf[i] = make_float4(w.x, w.x, w.y, w.y); }
-    for (int i = threadIdx.x; i < N; i += kFft2Threads) s_posf[i] = p.posf[i];
-    for (int i = threadIdx.x; i <= N; i += kFft2Threads) s_wk[i] = p.wk[i];
-    for (int i = threadIdx.x; i < N; i += kFft2Threads) s_win[i] = make_float2(p.window[2 * i], p.window[2 * i + 1]);
+    const int NT = blockDim.x;                   // 64 threads per group; as many groups as fit next to the tables (<= 6)
+    for (int i = threadIdx.x; i < RP.twf_len; i += NT) { const float2 w = p.twf[i]; s_twf[i] = make_float4(w.x, w.x, w.y, w.y); }
+    for (int i = threadIdx.x; i < N; i += NT) s_posf[i] = p.posf[i];
+    for (int i = threadIdx.x; i <= N; i += NT) s_wk[i] = p.wk[i];
+    for (int i = threadIdx.x; i < N; i += NT) s_win[i] = make_float2(p.window[2 * i], p.window[2 * i + 1]);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, group = warp / kFftGroupWarps;
-    constexpr int kGroups = kFft2Threads / 32 / kFftGroupWarps;
+    const int kGroups = (int)blockDim.x / 32 / kFftGroupWarps;
     FftExec ex;
     ex.nl = kFftGroupWarps * 32;
     ex.glane = (warp - group * kFftGroupWarps) * 32 + (int)(threadIdx.x & 31);
@@ -523,13 +461,6 @@ int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, ui
     sp.P = m->d_P; sp.samples = samples; sp.hop = cfg.hop; sp.n_frames = cfg.n_frames; sp.n_fft = cfg.n_fft;
     sp.bin_lo = m->bin_lo; sp.nb = m->nb; sp.kpad = m->kpad; sp.power = cfg.power;
     auto a16 = [](size_t x) { return (uint32_t)((x + 15) & ~(size_t)15); };
-    sp.off_posf = a16((size_t)m->plan.twf_len * 8);
-    sp.off_wk = sp.off_posf + a16((size_t)m->N * 2);
-    sp.off_win = sp.off_wk + a16((size_t)(m->N + 1) * 8);
-    sp.tables = sp.off_win + a16((size_t)cfg.n_fft * 4);
-    sp.per_group = a16((size_t)m->N * 8);
-    const size_t fft_smem = sp.tables + (size_t)(kFftThreads / 32 / kFftGroupWarps) * sp.per_group;
-    BB_CUDA_OK(c, cudaFuncSetAttribute(stft_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem));
     GemmParams gp{};
     gp.P = m->d_P; gp.W = m->d_w; gp.out = d_out;
     gp.kpad = m->kpad; gp.n_mels = cfg.n_mels; gp.n_frames = cfg.n_frames;
@@ -547,28 +478,30 @@ int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, ui
         const uint64_t nr = rows - r0 < rows_per_chunk ? rows - r0 : rows_per_chunk;
         const uint64_t nframes = nr * cfg.n_frames;
         sp.frame0 = r0 * cfg.n_frames; sp.nframes = nframes;
-        if (m->N == 1024 || m->N == 512) {
+        {
             StftParams s2 = sp;
             s2.off_posf = a16((size_t)m->plan.twf_len * 16);
             s2.off_wk = s2.off_posf + a16((size_t)m->N * 2);
             s2.off_win = s2.off_wk + a16((size_t)(m->N + 1) * 8);
             s2.tables = s2.off_win + a16((size_t)cfg.n_fft * 4);
             s2.per_group = a16((size_t)(m->N + m->N / 8) * 16);      // MapPad8: one slot of padding after every eight
-            constexpr int groups2 = kFft2Threads / 32 / kFftGroupWarps;
+            int groups2 = (int)((227 * 1024 - s2.tables) / s2.per_group);
+            if (groups2 > kFft2Threads / 32 / kFftGroupWarps) groups2 = kFft2Threads / 32 / kFftGroupWarps;
+            if (groups2 < 1) BB_SET_ERR(c, BB_ERR_INTERNAL, "STFT tables do not fit in shared memory");
+            const unsigned threads2 = (unsigned)groups2 * 32 * kFftGroupWarps;
             const size_t smem2 = s2.tables + (size_t)groups2 * s2.per_group;
             const uint64_t want2 = ((nframes + 1) / 2 + groups2 - 1) / groups2;
             const unsigned grid2 = (unsigned)(want2 < (uint64_t)c->sm_count ? want2 : (uint64_t)c->sm_count);
-            if (m->N == 1024) {
-                BB_CUDA_OK(c, cudaFuncSetAttribute(stft_power2_kernel<RSeq<16, 8, 8>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                stft_power2_kernel<RSeq<16, 8, 8>><<<grid2, kFft2Threads, smem2, c->stream>>>(s2);
-            } else {
-                BB_CUDA_OK(c, cudaFuncSetAttribute(stft_power2_kernel<RSeq<8, 8, 8>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                stft_power2_kernel<RSeq<8, 8, 8>><<<grid2, kFft2Threads, smem2, c->stream>>>(s2);
-            }
-        } else {
-            const uint64_t want = (nframes + 3) / 4;
-            const unsigned grid = (unsigned)(want < (uint64_t)c->sm_count * 4 ? want : (uint64_t)c->sm_count * 4);
-            stft_power_kernel<<<grid, kFftThreads, fft_smem, c->stream>>>(sp);
+#define BB_STFT2(...)                                                                                                              \
+            { BB_CUDA_OK(c, cudaFuncSetAttribute(stft_power2_kernel<RSeq<__VA_ARGS__>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+              stft_power2_kernel<RSeq<__VA_ARGS__>><<<grid2, threads2, smem2, c->stream>>>(s2); }
+            // radices as choose_radices picks them for these lengths (the plan's tables are laid out for them)
+            if (m->N == 2048) BB_STFT2(16, 16, 8)
+            else if (m->N == 1024) BB_STFT2(16, 8, 8)
+            else if (m->N == 512) BB_STFT2(8, 8, 8)
+            else if (m->N == 256) BB_STFT2(16, 16)
+            else BB_STFT2(16, 8)
+#undef BB_STFT2
         }
         gp.frame0 = sp.frame0; gp.nframes = nframes;
         mel_gemm_kernel<<<(unsigned)((nframes + kBM - 1) / kBM), kGemmThreads, gemm_smem, c->stream>>>(gp);
