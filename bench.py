@@ -48,6 +48,17 @@ def k2_traffic_bytes():
         return None
 
 
+def k2_smem_pipe_pct():
+    """Shared-memory pipe utilisation of the dominant kernel from the committed ncu summary (what actually binds K2)."""
+    import re
+    try:
+        txt = open(os.path.join(ROOT, "profiles", "r01_final_k2_c2_1h.txt")).read()
+        m = re.search(r"l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum\.pct_of_peak_sustained_elapsed\s+([0-9.]+)", txt)
+        return float(m.group(1)) if m else None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -383,6 +394,7 @@ def run_gpu(args):
                          "frac": ach / peak, "traffic": k2_traffic_bytes(), "algorithmic_bytes": ALGO_BYTES_FRONT,
                          "peak_source": peak_src,
                          "note": "K2 is FP32/shared-memory bound, not HBM bound (SURVEY 7.3 item 2)",
+                         "shared_memory_pipe_pct_ncu": k2_smem_pipe_pct(),
                          "fp32": {"achieved_tflops": ALGO_FLOPS_FRONT / (ms_front / 1e3) / 1e12, "peak_tflops": 74.5,
                                   "frac": ALGO_FLOPS_FRONT / (ms_front / 1e3) / 1e12 / 74.5}},
             "cpu_baseline": {"value": cpu_v, "unit": "audio-h/s", "cores": cores, "kind": "port",
