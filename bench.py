@@ -183,7 +183,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1        # the threads this process may actually use
     nseg = 200                                   # 5 min of audio per worker per step
     vals = []
     for i in range(args.warmup + args.steps):
@@ -375,7 +375,7 @@ def run_gpu(args):
         e2e = args.steps * hours * world / (ms_e2e / 1e3)
         peak, peak_src = measured_peaks()
         ach = ALGO_BYTES_FRONT / (ms_front / 1e3) / 1e9
-        cores = os.cpu_count() or 1
+        cores = len(os.sched_getaffinity(0)) or 1        # the threads this process may actually use
         cpu_v, cpu_wall, _ = cpu_arm(cores, 200, seed=7)      # 5 min of audio per core, a few seconds
         line = {
             "metric": "audio-hours/sec", "value": value, "unit": "audio-h/s", "n_gpus": world, "steps": args.steps,
