@@ -26,7 +26,7 @@ struct WarpParams {
     uint32_t out_len; float* out;
     const float2 *twf, *twi, *WI; const uint4* sidx; const float4 *pq1, *pq2;     // tables in global memory
     const uint32_t *ordf, *ordi; uint32_t ordf_len, ordi_len, off_ordf, off_ordi;
-    uint32_t nblk, R, items_per_row, R1, parts1; uint64_t nitems, n1_items, n1_rows;   // phase 1: n1_rows rows in parts1 runs of R1 blocks each (n1_items items); phase 2: runs of R blocks
+    WorkItems wi; uint32_t nblk; uint64_t nitems;     // work-item plan (k2_warp.cuh: plan_work_items)
     unsigned long long* counter;
     // shared memory layout (bytes)
     uint32_t off_twi, off_sidx, off_pq1, off_pq2, off_WI, off_items, tables, per_group, off_B, off_carry;
@@ -232,15 +232,7 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
         ex.sync();
         if (item >= P.nitems) break;
         uint64_t lrow; uint32_t b0, b1; bool last_item;
-        if (item < P.n1_items) {
-            lrow = item / P.parts1;
-            const uint32_t it = (uint32_t)(item - lrow * P.parts1);
-            b0 = it * P.R1; b1 = min(b0 + P.R1, P.nblk); last_item = it + 1 == P.parts1;
-        } else {
-            const uint64_t j = item - P.n1_items, q = j / P.items_per_row;
-            const uint32_t it = (uint32_t)(j - q * P.items_per_row);
-            lrow = P.n1_rows + q; b0 = it * P.R; b1 = min(b0 + P.R, P.nblk); last_item = it + 1 == P.items_per_row;
-        }
+        decode_work_item(P.wi, item, lrow, b0, b1, last_item);
         const uint64_t row = P.row_first + lrow;
         float* __restrict__ orow = P.out + row * P.seg;
         const uint32_t o_lo = min(b0 * (uint32_t)M, P.out_len);
@@ -533,15 +525,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
         ex.sync();
         if (item >= P.nitems) break;
         uint64_t lpair; uint32_t b0, b1; bool last_item;
-        if (item < P.n1_items) {
-            lpair = item / P.parts1;
-            const uint32_t it = (uint32_t)(item - lpair * P.parts1);
-            b0 = it * P.R1; b1 = min(b0 + P.R1, P.nblk); last_item = it + 1 == P.parts1;
-        } else {
-            const uint64_t j = item - P.n1_items, q = j / P.items_per_row;
-            const uint32_t it = (uint32_t)(j - q * P.items_per_row);
-            lpair = P.n1_rows + q; b0 = it * P.R; b1 = min(b0 + P.R, P.nblk); last_item = it + 1 == P.items_per_row;
-        }
+        decode_work_item(P.wi, item, lpair, b0, b1, last_item);
         const uint32_t o_lo = min(b0 * (uint32_t)M, P.out_len);
         const uint32_t o_hi = last_item ? P.out_len : min(b1 * (uint32_t)M, P.out_len);
         uint64_t start[2], take[2]; float* orow[2]; bool active[2];
@@ -786,40 +770,10 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     const size_t smem = P.tables + (size_t)groups * P.per_group;
     const uint64_t units = dual ? (rows_total + 1) / 2 : rows_total;      // rows or row pairs
     const uint64_t total_groups = (uint64_t)sm_count * groups;
-    // Work items, handed out in order by an atomic counter.  Phase 1: while there are at least as many rows (pairs)
-    // left as thread groups, every group gets the same number of rows — equal items, (almost) nothing recomputed.
-    // With overlapping windows a row is cut in two halves: the second half of window w and the first half of window
-    // w + 1 read the same PCM, and as half-row items they run at the same time on different groups, so the second
-    // reader hits L2 (whole-row items doubled the DRAM reads: 1.26 GB instead of 0.68 GB per C2 audio-hour).
-    // Phase 2: the remaining rows are cut into runs of R blocks (each run recomputes the block before it for its
-    // carry); R minimises the modelled makespan of that phase, rounds x (R + 1) block times.  (The earlier rule —
-    // about eight equal items per group — left 4800 items for 592 groups on C2: a ninth, nearly empty round.)
-    uint64_t n1_rows = (units / total_groups) * total_groups;
-    uint32_t parts1 = (hop < src_seg && P.nblk >= 32) ? 2u : 1u;
-    const uint64_t rem = units - n1_rows;
-    uint32_t R = P.nblk, ipr = 1;
-    if (rem > 0) {
-        uint64_t best = ~0ull;
-        for (uint32_t pieces = 1; pieces <= P.nblk; ++pieces) {
-            const uint32_t r = (P.nblk + pieces - 1) / pieces;
-            if (pieces > 1 && r < 8) break;
-            const uint32_t ip = (P.nblk + r - 1) / r;
-            const uint64_t rounds = (rem * ip + total_groups - 1) / total_groups;
-            const uint64_t t = rounds * (r + (ip > 1 ? 1u : 0u));
-            if (t < best) { best = t; R = r; ipr = ip; }
-        }
-    }
-    if (const char* g = std::getenv("BIRDA_K2_ITEM_BLOCKS")) {          // tests: force runs of this many blocks everywhere
-        const int v = atoi(g);
-        if (v >= 1) { n1_rows = 0; R = (uint32_t)v < P.nblk ? (uint32_t)v : P.nblk; ipr = (P.nblk + R - 1) / R; }
-    }
-    P.R = R;
-    P.items_per_row = ipr;
-    P.parts1 = parts1;
-    P.R1 = (P.nblk + parts1 - 1) / parts1;
-    P.n1_rows = n1_rows;
-    P.n1_items = n1_rows * parts1;
-    P.nitems = P.n1_items + (units - n1_rows) * ipr;
+    int force_blocks = 0;
+    if (const char* g = std::getenv("BIRDA_K2_ITEM_BLOCKS")) force_blocks = atoi(g);       // tests: runs of this many blocks everywhere
+    P.wi = plan_work_items(units, total_groups, P.nblk, hop < src_seg, force_blocks);
+    P.nitems = P.wi.nitems;
     cudaError_t e = cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     uint64_t ctas = (P.nitems + groups - 1) / groups;

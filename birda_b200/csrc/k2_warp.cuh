@@ -366,6 +366,58 @@ BB_HD void process_block(const Exec& ex, const RtPlan& P, const Tables<C>& T, ty
 }
 
 
+// ------------------------------------------------------------------ work items
+// The kernels hand out work items in order through an atomic counter.  Phase 1: while there are at least as many rows
+// (row pairs in two-stream mode) left as thread groups, every group gets the same number of rows — equal items,
+// (almost) nothing recomputed.  With overlapping windows a row is cut in two halves: the second half of window w and
+// the first half of window w + 1 read the same PCM, and as half-row items they run at the same time on different groups,
+// so the second reader hits L2 (whole-row items doubled the DRAM reads of C2).  Phase 2: the remaining rows are cut
+// into runs of R blocks (each run recomputes the block before it for its carry); R minimises the modelled makespan of
+// that phase, rounds x (R + 1) block times.
+struct WorkItems {
+    uint32_t nblk, R, items_per_row, R1, parts1;
+    uint64_t nitems, n1_items, n1_rows;
+};
+inline WorkItems plan_work_items(uint64_t units, uint64_t groups, uint32_t nblk, bool overlapping, int force_blocks = 0) {
+    WorkItems w{};
+    w.nblk = nblk;
+    uint64_t n1_rows = groups ? (units / groups) * groups : 0;
+    w.parts1 = (overlapping && nblk >= 32) ? 2u : 1u;
+    const uint64_t rem = units - n1_rows;
+    uint32_t R = nblk, ipr = 1;
+    if (rem > 0) {
+        uint64_t best = ~0ull;
+        for (uint32_t pieces = 1; pieces <= nblk; ++pieces) {
+            const uint32_t r = (nblk + pieces - 1) / pieces;
+            if (pieces > 1 && r < 8) break;
+            const uint32_t ip = (nblk + r - 1) / r;
+            const uint64_t rounds = (rem * ip + groups - 1) / groups;
+            const uint64_t t = rounds * (r + (ip > 1 ? 1u : 0u));
+            if (t < best) { best = t; R = r; ipr = ip; }
+        }
+    }
+    if (force_blocks >= 1) {                       // tests: runs of this many blocks everywhere
+        n1_rows = 0; R = (uint32_t)force_blocks < nblk ? (uint32_t)force_blocks : nblk; ipr = (nblk + R - 1) / R;
+    }
+    w.R = R; w.items_per_row = ipr;
+    w.R1 = (nblk + w.parts1 - 1) / w.parts1;
+    w.n1_rows = n1_rows; w.n1_items = n1_rows * w.parts1;
+    w.nitems = w.n1_items + (units - n1_rows) * ipr;
+    return w;
+}
+// item -> (row, [b0, b1), last run of its row)
+BB_HD void decode_work_item(const WorkItems& w, uint64_t item, uint64_t& row, uint32_t& b0, uint32_t& b1, bool& last) {
+    if (item < w.n1_items) {
+        row = item / w.parts1;
+        const uint32_t it = (uint32_t)(item - row * w.parts1);
+        b0 = it * w.R1; b1 = b0 + w.R1 < w.nblk ? b0 + w.R1 : w.nblk; last = it + 1 == w.parts1;
+    } else {
+        const uint64_t j = item - w.n1_items, q = j / w.items_per_row;
+        const uint32_t it = (uint32_t)(j - q * w.items_per_row);
+        row = w.n1_rows + q; b0 = it * w.R; b1 = b0 + w.R < w.nblk ? b0 + w.R : w.nblk; last = it + 1 == w.items_per_row;
+    }
+}
+
 // ------------------------------------------------------------------ compile-time plans
 template <int... Rs> struct RSeq {
     static constexpr int count = sizeof...(Rs);

@@ -106,8 +106,33 @@ static int check_impl(int N, int M, int nl) {
     return worst < 5e-6 ? 0 : 1;
 }
 
-int main() {
+// every (row, block) is covered exactly once by the work items, runs are contiguous and end flags are right
+static int check_work_items() {
     int bad = 0;
+    const uint64_t units_l[] = {1, 2, 7, 75, 100, 360, 591, 592, 593, 1200, 1216, 5000};
+    const uint64_t groups_l[] = {1, 148, 592, 888, 1776};
+    const uint32_t nblk_l[] = {1, 7, 31, 32, 129, 234, 282};
+    for (uint64_t units : units_l) for (uint64_t groups : groups_l) for (uint32_t nblk : nblk_l) for (int ov = 0; ov < 2; ++ov) for (int force : {0, 5}) {
+        const WorkItems w = plan_work_items(units, groups, nblk, ov != 0, force);
+        std::vector<uint32_t> next(units, 0); std::vector<char> ended(units, 0);
+        uint64_t prev_row = 0;
+        for (uint64_t item = 0; item < w.nitems; ++item) {
+            uint64_t row; uint32_t b0, b1; bool last;
+            decode_work_item(w, item, row, b0, b1, last);
+            if (row >= units || row < prev_row || b0 != next[row] || b1 <= b0 || b1 > nblk || ended[row]) { ++bad; break; }
+            next[row] = b1; prev_row = row;
+            if (last != (b1 == nblk)) { ++bad; break; }
+            if (last) ended[row] = 1;
+        }
+        for (uint64_t r = 0; r < units; ++r) if (next[r] != nblk || !ended[r]) { ++bad; break; }
+        if (force == 0 && groups > 1 && units >= groups && (w.n1_rows % groups != 0 || w.n1_rows + groups <= units)) ++bad;   // phase 1 = whole rounds
+    }
+    printf("work items: %s\n", bad ? "FAILED" : "every (row, block) covered once");
+    return bad;
+}
+
+int main() {
+    int bad = check_work_items();
     const int cases[][2] = {{1029, 1120}, {1029, 2240}, {1026, 684}, {1024, 512}, {1024, 1536}, {1024, 3072},
                             {1323, 960}, {1323, 1920}, {1024, 2048}, {1026, 342}, {1029, 560}, {1125, 216}, {1024, 256}};
     for (auto& c : cases) for (int nl : {32, 64}) bad += check_impl<void, float2>(c[0], c[1], nl);
