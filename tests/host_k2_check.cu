@@ -103,7 +103,12 @@ static int check_impl(int N, int M, int nl) {
     printf(" ] inv[");
     for (int r : inv) printf(" %d", r);
     printf(" ] pad %d%d orders %zu+%zu split conflicts %d  rel err %.3e\n", P.pad_a, P.pad_b, ordf.size(), ordi.size(), SL.extra_wavefronts, worst);
-    return worst < 5e-6 ? 0 : 1;
+    // the split layout must keep the scattered accesses mostly off each other's banks: at most a third more wavefronts
+    // than the conflict-free count (6 scattered accesses per lane group) for the two-stream compile-time plans
+    const int ideal = 6 * ((M / 2 + 1 + (NS == 2 ? 8 : 16) - 1) / (NS == 2 ? 8 : 16));
+    const bool layout_ok = !(kCt && NS == 2) || SL.extra_wavefronts * 3 <= ideal;
+    if (!layout_ok) printf("split layout too conflicted: %d extra of %d\n", SL.extra_wavefronts, ideal);
+    return (worst < 5e-6 && layout_ok) ? 0 : 1;
 }
 
 // every (row, block) is covered exactly once by the work items, runs are contiguous and end flags are right
