@@ -96,12 +96,21 @@ class FilePipeline:
         res = ProcessResult(segments=segs.nseg, effective_batch_size=B)
         if segs.nseg == 0:
             return res
+        # the classifier runs on torch's current stream: when the context owns a different (non-blocking) stream the
+        # two must be ordered by hand — packed windows finished before the classifier reads them, scores finished
+        # before the post kernel reads them (a Rust host with ORT on the ctx stream needs neither)
+        differs = ctx_stream_differs(self.ctx)
+        if differs:
+            self.ctx.sync()
         x = segs.torch()
         post = PostConfig(cfg.activation, cfg.min_confidence, cfg.top_k, cfg.range_threshold, cfg.keep_unmatched, cfg.rerank)
         dets: List[Detection] = []
         for first in range(0, segs.nseg, B):
             valid = min(B, segs.nseg - first)
             scores = self.classifier(x[first:first + B])                                        # [B, C] on the device
+            if differs:
+                import torch
+                torch.cuda.current_stream().synchronize()
             Bc, C = int(scores.shape[0]), int(scores.shape[1])
             idx, conf, cnt = self.ctx.post_run(scores.data_ptr(), Bc, C, valid, post, cfg.d_mask, cfg.d_species_keep)
             res.batches += 1
@@ -149,12 +158,16 @@ class NativePipeline:
         def _cb(user, d_segments, rows, samples, d_scores, classes):
             try:
                 import torch
+                differs = ctx_stream_differs(ctx)
+                if differs:                            # the packed windows are written on the ctx stream
+                    ctx.sync()
                 x = torch.as_tensor(_DevView(d_segments, (rows, samples)), device=f"cuda:{ctx.device}")
                 s = self.classifier(x).contiguous().float()
                 self._scores = s                       # keep alive until the next call
                 d_scores[0] = s.data_ptr()
                 classes[0] = int(s.shape[1])
-                torch.cuda.current_stream().synchronize() if ctx_stream_differs(ctx) else None
+                if differs:                            # ... and the post kernel reads the scores on it
+                    torch.cuda.current_stream().synchronize()
                 return 0
             except Exception as e:                      # never let an exception cross the C boundary
                 self._error = e

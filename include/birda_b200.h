@@ -229,7 +229,9 @@ int32_t bb_wav_read(const char* path, const bb_wav_info* info, uint64_t first_fr
  * Per-file pipeline (C++ host code in the library): the reference's process_file loop
  * (src/pipeline/processor.rs:418-796) with the front end and the post step on the GPU and the
  * classifier as a callback.  In birda the callback is BirdClassifier::predict_batch_device (ONNX
- * Runtime with IoBinding on the ctx stream); it must leave `*d_scores` = device [batch_rows, classes]
+ * Runtime with IoBinding on the ctx stream); `d_segments` is written, and `*d_scores` is read, on the ctx stream
+ * (bb_ctx_stream): a callback that computes on another stream must order itself against it.  It must leave
+ * `*d_scores` = device [batch_rows, classes]
  * f32 valid until the next call.  Return 0 on success (anything else -> BB_ERR_INTERNAL, as
  * Error::Inference).
  * ---------------------------------------------------------------------------------------- */
