@@ -22,6 +22,7 @@ def run_gpu(ctx, seg, n_fft, hop, n_frames, window, mw, **kw):
     import torch
     d = torch.from_numpy(seg).cuda()
     out = torch.full((seg.shape[0], mw.shape[0], n_frames), float("nan"), device="cuda")
+    torch.cuda.synchronize()          # the fill runs on torch's stream, the kernels on the context's own stream
     ms = b.MelSpec(ctx, n_fft, hop, n_frames, window, mw, **kw)
     ms.run(d.data_ptr(), seg.shape[0], seg.shape[1], out.data_ptr())
     ctx.sync()
