@@ -54,6 +54,11 @@ class DetectionC(C.Structure):
                 ("start_time", C.c_float), ("end_time", C.c_float)]
 
 
+class PoolResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("device", C.c_int32), ("n_detections", C.c_uint64), ("n_segments", C.c_uint64),
+                ("batch_used", C.c_uint32), ("detections", C.POINTER(DetectionC)), ("error", C.c_char * 200)]
+
+
 CLASSIFY_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32))
 
 
@@ -97,9 +102,14 @@ SIGNATURES = {
     "bb_pipeline_destroy": (None, [vp]),
     "bb_pipeline_last_error": (C.c_char_p, [vp]),
     "bb_pipeline_plans_created": (C.c_uint64, [vp]),
+    "bb_pipeline_set_sync_before_classify": (None, [vp, C.c_int32]),
     "bb_pipeline_process_pcm": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(DetectionC),
                                             C.c_uint64, u64p, u64p, u32p]),
     "bb_pipeline_process_wav": (C.c_int32, [vp, C.c_char_p, C.c_uint64, C.POINTER(DetectionC), C.c_uint64, u64p, u64p, u32p]),
+    "bb_pool_create": (C.c_int32, [C.POINTER(C.c_int32), C.c_uint32, C.POINTER(PipelineCfg), CLASSIFY_FN, C.POINTER(vp), C.POINTER(vp)]),
+    "bb_pool_destroy": (None, [vp]),
+    "bb_pool_process_wavs": (C.c_int32, [vp, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(PoolResult)]),
+    "bb_pool_free_results": (None, [C.POINTER(PoolResult), C.c_uint32]),
     "bb_dense_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_int32, vp]),
     "bb_melspec_create": (C.c_int32, [vp, C.POINTER(MelSpecCfg), f32p, f32p, C.POINTER(vp)]),
     "bb_melspec_destroy": (None, [vp]),

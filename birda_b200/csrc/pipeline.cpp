@@ -31,6 +31,7 @@ struct bb_pipeline {
     std::vector<Cached> cache;
     uint64_t use_clock = 0;
     uint64_t plans_created = 0;
+    bool sync_before_classify = false;        // bb_pipeline_set_sync_before_classify
     void* pinned = nullptr; uint64_t pinned_bytes = 0;
     std::vector<uint32_t> h_index; std::vector<float> h_conf; std::vector<uint32_t> h_count;
     std::vector<float> st, et; std::vector<uint64_t> ss;
@@ -93,6 +94,7 @@ int run_piece(bb_pipeline* p, const void* pcm, uint64_t frames, uint64_t first_s
     for (uint64_t first = 0; first < nseg; first += B) {
         const uint32_t valid = (uint32_t)std::min<uint64_t>(B, nseg - first);
         const float* d_scores = nullptr; uint32_t classes = 0;
+        if (p->sync_before_classify && bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));
         rc = p->classify(p->user, d_seg + first * seg_samples, B, (uint32_t)seg_samples, &d_scores, &classes);
         if (rc != 0 || !d_scores || classes == 0) return fail(p, BB_ERR_INTERNAL, "classifier callback failed");   // Error::Inference
         rc = bb_post_run(p->ctx, d_scores, B, classes, valid, &p->cfg.post, p->cfg.d_mask, p->cfg.d_species_keep,
@@ -152,6 +154,7 @@ void bb_pipeline_destroy(bb_pipeline* p) {
 
 const char* bb_pipeline_last_error(const bb_pipeline* p) { return p ? p->error.c_str() : ""; }
 uint64_t bb_pipeline_plans_created(const bb_pipeline* p) { return p ? p->plans_created : 0; }
+void bb_pipeline_set_sync_before_classify(bb_pipeline* p, int32_t on) { if (p) p->sync_before_classify = on != 0; }
 
 int32_t bb_pipeline_process_pcm(bb_pipeline* p, const void* pcm, uint64_t frames, uint32_t src_rate, uint32_t channels,
                                 int32_t fmt, bb_detection* out, uint64_t capacity, uint64_t* n_detections,

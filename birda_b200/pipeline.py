@@ -234,6 +234,85 @@ class NativePipeline:
             self._h = None
 
 
+class NativePool:
+    """The C++ multi-GPU directory runner (csrc/pool.cpp: bb_pool_*): one worker thread + context + pipeline per entry of
+    ``devices``, WAV files handed out longest first.  ``classifiers[i]`` serves ``devices[i]`` and is called from that
+    worker's thread (after the context's stream was synchronised); it must return scores whose computation is finished."""
+
+    def __init__(self, devices: List[int], cfgs: List[ProcessingConfig], classifiers: List[Callable]):
+        import ctypes as C
+
+        from . import _lib
+        assert len(devices) == len(cfgs) == len(classifiers) and devices
+        self.devices, self.cfgs, self.classifiers = list(devices), list(cfgs), list(classifiers)
+        self._scores = [None] * len(devices)
+        self._errors: list = []
+
+        def _cb(user, d_segments, rows, samples, d_scores, classes):
+            try:
+                import torch
+                i = int(user or 0) - 1                 # users[i] = i + 1 (a null user pointer would read as None)
+                dev = self.devices[i]
+                with torch.cuda.device(dev):
+                    x = torch.as_tensor(_DevView(d_segments, (rows, samples)), device=f"cuda:{dev}")
+                    s = self.classifiers[i](x).contiguous().float()
+                    torch.cuda.current_stream().synchronize()
+                self._scores[i] = s                    # keep alive until this worker's next call
+                d_scores[0] = s.data_ptr()
+                classes[0] = int(s.shape[1])
+                return 0
+            except Exception as e:                      # never let an exception cross the C boundary
+                self._errors.append(e)
+                return 1
+
+        self._cb = _lib.CLASSIFY_FN(_cb)
+        n = len(devices)
+        c_cfgs = (_lib.PipelineCfg * n)(*[
+            _lib.PipelineCfg(c.target_rate, c.segment_duration, c.overlap, c.batch_size, int(c.bat_mode),
+                             PostConfig(c.activation, c.min_confidence, c.top_k, c.range_threshold, c.keep_unmatched, c.rerank).to_c(),
+                             c.d_mask, c.d_species_keep) for c in cfgs])
+        users = (C.c_void_p * n)(*[C.c_void_p(i + 1) for i in range(n)])
+        devs = (C.c_int32 * n)(*devices)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib.bb_pool_create(devs, n, c_cfgs, self._cb, users, C.byref(self._h)))
+
+    def process_wavs(self, paths: List[str]) -> List[ProcessResult]:
+        import ctypes as C
+
+        from . import _lib
+        n = len(paths)
+        arr = (C.c_char_p * n)(*[p.encode() for p in paths])
+        res = (_lib.PoolResult * n)()
+        rc = _lib.lib.bb_pool_process_wavs(self._h, arr, n, res)
+        out = []
+        try:
+            for i in range(n):
+                r = res[i]
+                if r.status != 0:
+                    if self._errors:
+                        raise self._errors[0]
+                    raise _lib.BirdaError(int(r.status), f"{paths[i]}: {r.error.decode('utf-8', 'replace')}")
+                pr = ProcessResult(segments=int(r.n_segments), effective_batch_size=int(r.batch_used))
+                pr.device = int(r.device)
+                labels = self.cfgs[0].labels
+                for j in range(int(r.n_detections)):
+                    d = r.detections[j]
+                    sci, com = split_label(labels[d.index]) if labels is not None else (str(d.index), str(d.index))
+                    pr.detections.append(Detection(sci, com, float(d.confidence), float(d.start_time), float(d.end_time), int(d.index), int(d.segment)))
+                pr.batches = -(-pr.segments // max(pr.effective_batch_size, 1))
+                out.append(pr)
+        finally:
+            _lib.lib.bb_pool_free_results(res, n)
+        assert rc == 0
+        return out
+
+    def close(self):
+        from . import _lib
+        if self._h:
+            _lib.lib.bb_pool_destroy(self._h)
+            self._h = None
+
+
 def ctx_stream_differs(ctx: Context) -> bool:
     """True when the context runs on its own stream: the classifier's torch work (current stream) must be
     finished before the library's post kernel reads the scores."""

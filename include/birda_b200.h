@@ -261,6 +261,9 @@ const char* bb_pipeline_last_error(const bb_pipeline*);
 /* front-end plans are cached per (source rate, channels, format), 8 kinds, least recently used evicted; this counts
  * how many were built so far (a mixed-rate directory builds each kind once) */
 uint64_t    bb_pipeline_plans_created(const bb_pipeline*);
+/* for classifiers that do not run on the ctx stream: synchronise it before every callback (the callback then has to
+ * finish its own work before it returns).  Off by default; bb_pool turns it on. */
+void        bb_pipeline_set_sync_before_classify(bb_pipeline*, int32_t on);
 /* Whole decoded file in host memory.  Detections come back sorted (start_time asc, confidence desc:
  * processor.rs:178-187); BB_ERR_CAPACITY reports the needed count in *n_detections. */
 int32_t bb_pipeline_process_pcm(bb_pipeline*, const void* pcm, uint64_t frames, uint32_t src_rate, uint32_t channels,
@@ -269,6 +272,30 @@ int32_t bb_pipeline_process_pcm(bb_pipeline*, const void* pcm, uint64_t frames, 
 /* WAV / RF64 file streamed through a pinned staging buffer in pieces of ~piece_frames (0 = default). */
 int32_t bb_pipeline_process_wav(bb_pipeline*, const char* path, uint64_t piece_frames, bb_detection* out, uint64_t capacity,
                                 uint64_t* n_detections, uint64_t* n_segments, uint32_t* batch_used);
+
+/* ------------------------------------------------------------------------------------------
+ * Directory batches across the GPUs of one box (csrc/pool.cpp): a host work queue of WAV files, longest first, one worker
+ * thread + context + bb_pipeline per GPU, no collective (files are independent: src/lib.rs:694-796).
+ * `cfgs[i]` / `users[i]` belong to `devices[i]` (device pointers such as d_mask live on that device); the classifier
+ * callback is called from the worker thread of its device, after the context's stream has been synchronised, and must
+ * finish its own device work before it returns.  Results come back per file, each list sorted the
+ * reference's way; `detections` is owned by the library until bb_pool_free_results.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bb_pool bb_pool;
+typedef struct {
+    int32_t  status;                /* BB_OK or the BB_ERR_* of this file (the batch goes on: src/lib.rs:776-796)  */
+    int32_t  device;                /* GPU that processed the file                                                 */
+    uint64_t n_detections, n_segments;
+    uint32_t batch_used;
+    bb_detection* detections;
+    char     error[200];
+} bb_pool_result;
+int32_t bb_pool_create(const int32_t* devices, uint32_t n_devices, const bb_pipeline_cfg* cfgs, bb_classify_fn fn,
+                       void* const* users, bb_pool** out);
+void    bb_pool_destroy(bb_pool*);
+/* returns BB_OK when every file succeeded, else the status of a failed file; results[n_files] is always filled */
+int32_t bb_pool_process_wavs(bb_pool*, const char* const* paths, uint32_t n_files, bb_pool_result* results);
+void    bb_pool_free_results(bb_pool_result* results, uint32_t n);
 
 /* ------------------------------------------------------------------------------------------
  * Tiny dense heads on the device: out[B,N] = act(x[B,K] W[K,N] + b[N]), f32.

@@ -49,3 +49,20 @@ def test_product_does_not_import_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "oracle/" in src.replace("NOT the oracle", ""):
                     bad.append(fn)
     assert not bad, bad
+
+
+def test_pool_without_device_fails_loudly():
+    """The multi-GPU file pool refuses to exist without a GPU, like the context it is built on."""
+    import ctypes as C
+
+    import birda_b200 as b
+    from birda_b200 import _lib
+    from birda_b200.api import device_count
+    if device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    cb = _lib.CLASSIFY_FN(lambda *a: 1)
+    cfg = (_lib.PipelineCfg * 1)(_lib.PipelineCfg(48_000, 3.0, 0.0, 8, 0, _lib.PostCfg(1, 0.1, 5, 0.01, 1, 0), None, None))
+    h = C.c_void_p()
+    rc = _lib.lib.bb_pool_create((C.c_int32 * 1)(0), 1, cfg, cb, None, C.byref(h))
+    assert rc == -8 and not h.value
+    assert b"no CPU fallback" in _lib.lib.bb_last_error(None)

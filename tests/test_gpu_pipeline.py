@@ -156,3 +156,36 @@ def test_native_pipeline_mixed_rate_directory_reuses_plans():
         assert r.segments == results[i].segments == 4 and key(r) == key(results[i])
         one.close()
     nat.close(); ctx.close()
+
+
+def test_native_pool_two_workers_match_single_pipeline(tmp_path):
+    """csrc/pool.cpp: two worker threads (two contexts on GPU 0 when the box has one GPU, GPUs 0 and 1 otherwise) share a
+    queue of WAV files, longest first; every file's detections equal those of a single native pipeline."""
+    import torch
+    from birda_b200.api import device_count
+    from birda_b200.pipeline import NativePipeline, NativePool
+    from tests.test_wav_ingest import write_wav
+    C = 265
+    devices = [0, 1] if device_count() > 1 else [0, 0]
+    clfs = []
+    for d in devices:
+        with torch.cuda.device(d):
+            clfs.append(StandInClassifier(144_000, C))
+    cfg = ProcessingConfig(target_rate=48_000, segment_duration=3.0, overlap=1.5, batch_size=4, min_confidence=0.1)
+    paths, pcms = [], []
+    for i, (sr, ch, sec) in enumerate([(44_100, 2, 21.0), (48_000, 1, 7.0), (32_000, 1, 33.0), (44_100, 2, 12.5), (96_000, 2, 9.0), (22_050, 1, 15.0)]):
+        pcm = synth_pcm(300 + i, sec, sr, ch)
+        p = str(tmp_path / f"f{i}.wav"); write_wav(p, pcm, sr, ch)
+        paths.append(p); pcms.append((pcm, ch, sr))
+    pool = NativePool(devices, [cfg] * len(devices), clfs)
+    got = pool.process_wavs(paths)
+    pool.close()
+    ctx = b.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    one = NativePipeline(ctx, cfg, clfs[0])
+    key = lambda r: [(d.segment, d.index, round(d.confidence, 5), d.start_time, d.end_time) for d in r.detections]
+    for p, (pcm, ch, sr), g in zip(paths, pcms, got):
+        r = one.process_pcm(pcm, ch, sr, b.FMT_S16)
+        assert g.segments == r.segments and g.effective_batch_size == r.effective_batch_size
+        assert key(g) == key(r), p
+    assert sum(len(g.detections) for g in got) > 20
+    one.close(); ctx.close()
