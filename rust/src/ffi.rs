@@ -133,3 +133,59 @@ impl GpuFrontEnd {
     }
 }
 impl Drop for GpuFrontEnd { fn drop(&mut self) { unsafe { bb_plan_destroy(self.raw) } } }
+
+// ---- per-file pipeline and multi-GPU file pool (csrc/pipeline.cpp, csrc/pool.cpp) -------------------------------
+#[repr(C)] pub struct bb_pipeline { _p: [u8; 0] }
+#[repr(C)] pub struct bb_pool { _p: [u8; 0] }
+
+/// `BirdClassifier::predict_batch_device` behind a C trampoline: device windows in, device scores out.
+pub type bb_classify_fn = unsafe extern "C" fn(user: *mut c_void, d_segments: *const f32, batch_rows: u32, samples: u32,
+                                               d_scores: *mut *const f32, classes: *mut u32) -> i32;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct bb_pipeline_cfg {
+    pub target_rate: u32,
+    pub segment_duration: f32,
+    pub overlap: f32,
+    pub batch_size: u32,
+    pub bat_mode: i32,
+    pub post: bb_post_cfg,
+    pub d_mask: *const f32,
+    pub d_species_keep: *const u8,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct bb_detection {
+    pub segment: u32,
+    pub index: u32,
+    pub confidence: f32,
+    pub start_time: f32,
+    pub end_time: f32,
+}
+
+#[repr(C)]
+pub struct bb_pool_result {
+    pub status: i32,
+    pub device: i32,
+    pub n_detections: u64,
+    pub n_segments: u64,
+    pub batch_used: u32,
+    pub detections: *mut bb_detection,
+    pub error: [c_char; 200],
+}
+
+extern "C" {
+    pub fn bb_pipeline_create(ctx: *mut bb_ctx, cfg: *const bb_pipeline_cfg, f: bb_classify_fn, user: *mut c_void,
+                              out: *mut *mut bb_pipeline) -> i32;
+    pub fn bb_pipeline_destroy(p: *mut bb_pipeline);
+    pub fn bb_pipeline_last_error(p: *const bb_pipeline) -> *const c_char;
+    pub fn bb_pipeline_process_wav(p: *mut bb_pipeline, path: *const c_char, piece_frames: u64, out: *mut bb_detection,
+                                   capacity: u64, n_detections: *mut u64, n_segments: *mut u64, batch_used: *mut u32) -> i32;
+    pub fn bb_pool_create(devices: *const i32, n_devices: u32, cfgs: *const bb_pipeline_cfg, f: bb_classify_fn,
+                          users: *const *mut c_void, out: *mut *mut bb_pool) -> i32;
+    pub fn bb_pool_destroy(p: *mut bb_pool);
+    pub fn bb_pool_process_wavs(p: *mut bb_pool, paths: *const *const c_char, n_files: u32, results: *mut bb_pool_result) -> i32;
+    pub fn bb_pool_free_results(results: *mut bb_pool_result, n: u32);
+}
