@@ -59,6 +59,8 @@ class PoolResult(C.Structure):
                 ("batch_used", C.c_uint32), ("detections", C.POINTER(DetectionC)), ("error", C.c_char * 200)]
 
 
+WATCHDOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint32)
+BATCH_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64)
 CLASSIFY_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32))
 
 
@@ -77,6 +79,13 @@ SIGNATURES = {
     "bb_rule_date_to_week": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "bb_rule_week_to_start_day": (C.c_uint32, [C.c_uint32]),
     "bb_rule_day_of_year_to_date": (None, [C.c_uint32, u32p, u32p]),
+    "bb_rule_inference_timeout_secs": (C.c_uint64, [C.c_char_p]),
+    "bb_rule_scientific_name_len": (C.c_uint32, [C.c_char_p]),
+    "bb_mask_build": (C.c_int32, [C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_char_p), C.c_uint32,
+                                  C.POINTER(C.c_char_p), f32p, C.c_uint32, f32p, u32p, u32p]),
+    "bb_watchdog_start": (C.c_int32, [C.c_uint64, C.c_uint32, WATCHDOG_FN, vp, C.POINTER(vp)]),
+    "bb_watchdog_cancel": (None, [vp]),
+    "bb_debug_inject_alloc_failure": (None, [C.c_int32]),
     "bb_version": (C.c_uint32, []),
     "bb_device_count": (C.c_int32, [i32p]),
     "bb_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(vp)]),
@@ -103,6 +112,8 @@ SIGNATURES = {
     "bb_pipeline_last_error": (C.c_char_p, [vp]),
     "bb_pipeline_plans_created": (C.c_uint64, [vp]),
     "bb_pipeline_set_sync_before_classify": (None, [vp, C.c_int32]),
+    "bb_pipeline_set_batch_hooks": (None, [vp, BATCH_HOOK, BATCH_HOOK, vp]),
+    "bb_pipeline_set_batch_timeout": (None, [vp, C.c_uint64, WATCHDOG_FN, vp]),
     "bb_pipeline_process_pcm": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(DetectionC),
                                             C.c_uint64, u64p, u64p, u32p]),
     "bb_pipeline_process_wav": (C.c_int32, [vp, C.c_char_p, C.c_uint64, C.POINTER(DetectionC), C.c_uint64, u64p, u64p, u32p]),

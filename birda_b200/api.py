@@ -11,9 +11,9 @@ import numpy as np
 from . import _lib
 from ._lib import BirdaError, MelSpecCfg, PostCfg, check, lib
 
-FMT_S16, FMT_S32, FMT_F32 = 1, 2, 3
+FMT_S16, FMT_S32, FMT_F32, FMT_S24 = 1, 2, 3, 4      # FMT_S24: 3-byte packed little-endian (uint8 arrays)
 ACT_NONE, ACT_SIGMOID, ACT_SOFTMAX = 0, 1, 2
-_NP_FMT = {np.dtype(np.int16): FMT_S16, np.dtype(np.int32): FMT_S32, np.dtype(np.float32): FMT_F32}
+_NP_FMT = {np.dtype(np.int16): FMT_S16, np.dtype(np.int32): FMT_S32, np.dtype(np.float32): FMT_F32, np.dtype(np.uint8): FMT_S24}
 
 
 class rules:
@@ -84,6 +84,17 @@ class rules:
         check(lib.bb_rule_resampled_len(src_len, src_rate, tgt_rate, C.byref(n)))
         return n.value
 
+    @staticmethod
+    def inference_timeout_secs(env_value: Optional[str]) -> int:
+        """BIRDA_INFERENCE_TIMEOUT parsing (src/pipeline/processor.rs:194-211)."""
+        return lib.bb_rule_inference_timeout_secs(None if env_value is None else env_value.encode())
+
+    @staticmethod
+    def scientific_name(label: str) -> str:
+        """src/inference/geomodel.rs:28-33."""
+        raw = label.encode()
+        return raw[: lib.bb_rule_scientific_name_len(raw)].decode()
+
     date_to_week = staticmethod(lambda m, d: lib.bb_rule_date_to_week(m, d))
     week_to_start_day = staticmethod(lambda w: lib.bb_rule_week_to_start_day(w))
 
@@ -94,6 +105,50 @@ class rules:
         return a.value, b.value
 
 
+def mask_build(classifier_labels, geomodel_labels, scores) -> Tuple[np.ndarray, int, int]:
+    """Dense range mask in the classifier's label space (``bb_mask_build``): ``scores`` is a sequence of
+    (geomodel species label, score).  Returns (mask [C] f32 with NaN = no geomodel entry, mapped, unmatched)."""
+    def arr(strings):
+        enc = [s.encode() for s in strings]
+        return (C.c_char_p * max(len(enc), 1))(*enc), enc
+    cl, _k1 = arr(classifier_labels)
+    gl, _k2 = arr(geomodel_labels)
+    sp, _k3 = arr([s for s, _ in scores])
+    sv = np.asarray([v for _, v in scores], dtype=np.float32)
+    mask = np.zeros(max(len(classifier_labels), 1), np.float32)
+    mapped, unmatched = C.c_uint32(), C.c_uint32()
+    check(lib.bb_mask_build(cl, len(classifier_labels), gl, len(geomodel_labels), sp, sv.ctypes.data_as(_lib.f32p), len(sv),
+                            mask.ctypes.data_as(_lib.f32p), C.byref(mapped), C.byref(unmatched)))
+    return mask[: len(classifier_labels)], mapped.value, unmatched.value
+
+
+class Watchdog:
+    """``bb_watchdog``: fires ``on_fire(timeout_secs, batch_size)`` unless cancelled within ``timeout_ms``
+    (src/gpu/watchdog.rs:22-66).  ``on_fire=None`` is the reference's behaviour: message + exit(1)."""
+
+    def __init__(self, timeout_ms: int, batch_size: int, on_fire=None):
+        self._cb = _lib.WATCHDOG_FN(lambda user, secs, batch: on_fire(secs, batch)) if on_fire else C.cast(None, _lib.WATCHDOG_FN)
+        self._h = C.c_void_p()
+        check(lib.bb_watchdog_start(timeout_ms, batch_size, self._cb, None, C.byref(self._h)))
+
+    def cancel(self):
+        if self._h:
+            lib.bb_watchdog_cancel(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.cancel()
+
+    def __del__(self):
+        try:
+            self.cancel()
+        except Exception:
+            pass
+
+
 def wav_probe(path: str) -> _lib.WavInfo:
     """Header of a RIFF/RF64 WAVE file (rate, channels, sample format, frames)."""
     info = _lib.WavInfo()
@@ -102,10 +157,11 @@ def wav_probe(path: str) -> _lib.WavInfo:
 
 
 def wav_read(path: str, info: _lib.WavInfo, first_frame: int = 0, frames: Optional[int] = None) -> np.ndarray:
-    """Interleaved frames [first_frame, first_frame+frames) as int16 / int32 / float32 (no conversion)."""
+    """Interleaved frames [first_frame, first_frame+frames) as int16 / int32 / float32 (no conversion); 24-bit
+    files come back as the packed bytes (uint8, 3 per sample)."""
     n = info.frames - first_frame if frames is None else frames
-    dt = {FMT_S16: np.int16, FMT_S32: np.int32, FMT_F32: np.float32}[info.fmt]
-    out = np.empty(n * info.channels, dtype=dt)
+    dt = {FMT_S16: np.int16, FMT_S32: np.int32, FMT_F32: np.float32, FMT_S24: np.uint8}[info.fmt]
+    out = np.empty(n * info.channels * (3 if info.fmt == FMT_S24 else 1), dtype=dt)
     check(lib.bb_wav_read(path.encode(), C.byref(info), first_frame, n, out.ctypes.data_as(C.c_void_p)))
     return out
 
@@ -252,11 +308,11 @@ class FrontEndPlan:
             pcm = np.ascontiguousarray(pcm)
             keep = pcm
             ptr = pcm.ctypes.data
-            n = pcm.size // self.channels if frames is None else frames
+            n = pcm.size // (self.channels * (3 if self.fmt == FMT_S24 else 1)) if frames is None else frames
             dev = False if is_device is None else is_device
         elif hasattr(pcm, "data_ptr"):
             ptr = pcm.data_ptr()
-            n = pcm.numel() // self.channels if frames is None else frames
+            n = pcm.numel() // (self.channels * (3 if self.fmt == FMT_S24 else 1)) if frames is None else frames
             dev = bool(pcm.is_cuda) if is_device is None else is_device
             keep = pcm
         else:

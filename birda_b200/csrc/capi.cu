@@ -1,13 +1,18 @@
 // extern "C" surface of birda_b200 (see include/birda_b200.h for the contract and the
 // reference file:line each entry point replaces).  No exceptions cross this boundary.
 #include "common.cuh"
+#include "guard.hpp"
 #include <cmath>
 #include <cstring>
 #include <new>
 
 namespace bb {
 static thread_local std::string g_tls_error;
+static thread_local int32_t g_fault_countdown = 0;
 void set_tls_error(const std::string& m) { g_tls_error = m; }
+void fault_point() {
+    if (g_fault_countdown > 0 && --g_fault_countdown == 0) throw std::bad_alloc();
+}
 }  // namespace bb
 
 using namespace bb;
@@ -17,18 +22,23 @@ extern "C" {
 // ------------------------------------------------------------------------------------ rules
 int32_t bb_rule_segment_samples(float segment_duration, float overlap, uint32_t target_rate,
                                 int32_t bat_mode, uint64_t* seg, uint64_t* ovl) {
+    BB_TRY
     if (!seg || !ovl) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
     segment_samples(segment_duration, overlap, target_rate, bat_mode != 0, seg, ovl);
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_rule_source_window(uint64_t seg, uint64_t ovl, uint32_t sr, uint32_t tr, uint64_t* sseg, uint64_t* sovl) {
+    BB_TRY
     if (!sseg || !sovl || sr == 0 || tr == 0) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "bad argument");
     source_window(seg, ovl, sr, tr, sseg, sovl);
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_rule_segment_count(uint64_t total, uint64_t sseg, uint64_t sovl, uint64_t* nseg) {
+    BB_TRY
     if (!nseg) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
     WindowSeq w;
     if (!make_window_seq(total, sseg, sovl, false, &w))
@@ -36,10 +46,12 @@ int32_t bb_rule_segment_count(uint64_t total, uint64_t sseg, uint64_t sovl, uint
                    "overlap_samples (" + std::to_string(sovl) + ") must be less than segment_samples (" + std::to_string(sseg) + ")");
     *nseg = w.nseg;
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_rule_segment_table(uint64_t total, uint64_t sseg, uint64_t sovl, uint64_t first, uint64_t capacity,
                               uint64_t* start_sample, uint64_t* take, uint64_t* written) {
+    BB_TRY
     WindowSeq w;
     if (!make_window_seq(total, sseg, sovl, false, &w))
         BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_OVERLAP_GE_SEGMENT, "overlap_samples must be less than segment_samples");
@@ -51,44 +63,55 @@ int32_t bb_rule_segment_table(uint64_t total, uint64_t sseg, uint64_t sovl, uint
     }
     if (written) *written = n;
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_rule_chunk_times(uint64_t start_sample, uint32_t sr, uint64_t seg, uint32_t tr, float* st, float* et) {
+    BB_TRY
     if (!st || !et || sr == 0 || tr == 0) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "bad argument");
     chunk_times(start_sample, sr, seg, tr, st, et);
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_rule_estimate_segment_count(double duration, int32_t has_duration, float seg_dur, float overlap, int64_t* est) {
+    BB_TRY
     if (!est) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
     *est = estimate_segment_count(duration, has_duration != 0, seg_dur, overlap);
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 uint32_t bb_rule_effective_batch_size(uint32_t batch, int64_t est) { return effective_batch_size(batch, est); }
 
 int32_t bb_rule_resampler_blocks(uint32_t sr, uint32_t tr, uint32_t* n_in, uint32_t* n_out, uint32_t* n_keep, float* cutoff) {
+    BB_TRY
     ResamplerSpec s; std::string err;
     if (!make_resampler_spec(sr, tr, false, &s, &err)) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_UNSUPPORTED_RATE, err);
     if (n_in) *n_in = s.n_in; if (n_out) *n_out = s.n_out; if (n_keep) *n_keep = s.n_keep; if (cutoff) *cutoff = s.cutoff;
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_rule_resampler_taps(uint32_t sr, uint32_t tr, float* taps, uint32_t n) {
+    BB_TRY
     ResamplerSpec s; std::string err;
     if (!make_resampler_spec(sr, tr, false, &s, &err)) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_UNSUPPORTED_RATE, err);
     if (!taps || n != s.n_in) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "taps buffer must hold n_in floats");
     std::memcpy(taps, s.taps.data(), sizeof(float) * n);
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_rule_resampled_len(uint64_t src_len, uint32_t sr, uint32_t tr, uint64_t* out_len) {
+    BB_TRY
     if (!out_len) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
     if (sr == tr) { *out_len = src_len; return BB_OK; }
     ResamplerSpec s; std::string err;
     if (!make_resampler_spec(sr, tr, false, &s, &err)) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_UNSUPPORTED_RATE, err);
     *out_len = resampled_len(src_len, s);
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 uint32_t bb_rule_date_to_week(uint32_t month, uint32_t day) { return date_to_week(month, day); }
@@ -96,18 +119,23 @@ uint32_t bb_rule_week_to_start_day(uint32_t week) { return week_to_start_day(wee
 void     bb_rule_day_of_year_to_date(uint32_t doy, uint32_t* m, uint32_t* d) { uint32_t a, b; day_of_year_to_date(doy, &a, &b); if (m) *m = a; if (d) *d = b; }
 
 // ---------------------------------------------------------------------------------- context
+void bb_debug_inject_alloc_failure(int32_t nth) { bb::g_fault_countdown = nth > 0 ? nth : 0; }
+
 uint32_t bb_version(void) { return (BB_VERSION_MAJOR << 16) | BB_VERSION_MINOR; }
 
 int32_t bb_device_count(int32_t* count) {
+    BB_TRY
     if (!count) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) { *count = 0; cudaGetLastError(); BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
     *count = n;
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 static int32_t ctx_create_impl(int32_t device, void* stream, bool have_stream, bb_ctx** out) {
+    BB_TRY
     if (!out) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
     *out = nullptr;
     int n = 0;
@@ -118,7 +146,7 @@ static int32_t ctx_create_impl(int32_t device, void* stream, bool have_stream, b
                    "no CUDA device: birda_b200 has no CPU fallback (" + std::string(e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") + ")");
     }
     if (device < 0 || device >= n) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "device index out of range");
-    BB_CUDA_OK((bb_ctx*)nullptr, cudaSetDevice(device));
+    BB_DEVICE((bb_ctx*)nullptr, device);
     bb_ctx* c = new (std::nothrow) bb_ctx();
     if (!c) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_OOM, "out of host memory");
     c->device = device;
@@ -132,6 +160,7 @@ static int32_t ctx_create_impl(int32_t device, void* stream, bool have_stream, b
     }
     *out = c;
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_ctx_create(int32_t device, bb_ctx** out) { return ctx_create_impl(device, nullptr, false, out); }
@@ -139,7 +168,7 @@ int32_t bb_ctx_create_on_stream(int32_t device, void* stream, bb_ctx** out) { re
 
 void bb_ctx_destroy(bb_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    bb::DeviceGuard dev_guard(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->d_post_index) cudaFree(c->d_post_index);
     if (c->d_post_conf) cudaFree(c->d_post_conf);
@@ -153,50 +182,61 @@ void* bb_ctx_stream(bb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 uint64_t bb_ctx_kernel_launches(const bb_ctx* c) { return c ? c->launches : 0; }
 
 int32_t bb_sync(bb_ctx* c) {
+    BB_TRY
     if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
     BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
 }
 
 int32_t bb_host_alloc(uint64_t bytes, void** out) {
+    BB_TRY
     if (!out) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null output");
     BB_CUDA_OK((bb_ctx*)nullptr, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 void bb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int32_t bb_dev_alloc(bb_ctx* c, uint64_t bytes, void** out) {
+    BB_TRY
     if (!c || !out) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "bad argument");
-    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    BB_DEVICE(c, c->device);
     BB_CUDA_OK(c, cudaMalloc(out, bytes ? bytes : 1));
     return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
 }
-void bb_dev_free(bb_ctx* c, void* p) { if (c && p) { cudaSetDevice(c->device); cudaFree(p); } }
+void bb_dev_free(bb_ctx* c, void* p) { if (c && p) { bb::DeviceGuard dev_guard(c->device); cudaFree(p); } }
 
 int32_t bb_memcpy_h2d(bb_ctx* c, void* dst, const void* src, uint64_t bytes) {
+    BB_TRY
     if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
     BB_CUDA_OK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
     return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
 }
 int32_t bb_memcpy_d2h(bb_ctx* c, void* dst, const void* src, uint64_t bytes) {
+    BB_TRY
     if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
     BB_CUDA_OK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
 }
 
 // ------------------------------------------------------------------------------------- plan
 int32_t bb_plan_create(bb_ctx* c, uint32_t src_rate, uint32_t channels, bb_sample_fmt fmt, uint32_t tgt_rate,
                        uint64_t seg, uint64_t ovl, bb_plan** out) {
+    BB_TRY
     if (!c || !out) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "bad argument");
     *out = nullptr;
     if (src_rate == 0 || tgt_rate == 0 || channels == 0 || seg == 0)
         BB_SET_ERR(c, BB_ERR_INVALID_ARG, "rates, channels and segment_samples must be > 0");
-    if (fmt != BB_S16 && fmt != BB_S32 && fmt != BB_F32)
-        BB_SET_ERR(c, BB_ERR_UNSUPPORTED_FORMAT, "unsupported sample format (S16, S32, F32 are converted; decode.rs:353-411)");
+    if (fmt != BB_S16 && fmt != BB_S32 && fmt != BB_F32 && fmt != BB_S24)
+        BB_SET_ERR(c, BB_ERR_UNSUPPORTED_FORMAT, "unsupported sample format (S16, S24, S32, F32 are converted; decode.rs:353-411)");
     bb_plan* p = new (std::nothrow) bb_plan();
     if (!p) BB_SET_ERR(c, BB_ERR_OOM, "out of host memory");
     p->ctx = c; p->src_rate = src_rate; p->tgt_rate = tgt_rate; p->channels = channels; p->fmt = fmt;
-    p->bytes_per_sample = fmt == BB_S16 ? 2 : 4;
+    p->bytes_per_sample = sample_bytes(fmt);
     p->seg = seg; p->ovl = ovl;
     source_window(seg, ovl, src_rate, tgt_rate, &p->src_seg, &p->src_ovl);
     if (p->src_ovl >= p->src_seg) {
@@ -209,7 +249,7 @@ int32_t bb_plan_create(bb_ctx* c, uint32_t src_rate, uint32_t channels, bb_sampl
         std::string err;
         if (!make_resampler_spec(src_rate, tgt_rate, true, &p->spec, &err)) { delete p; BB_SET_ERR(c, BB_ERR_UNSUPPORTED_RATE, err); }
         p->resampled_len = resampled_len(p->src_seg, p->spec);
-        cudaSetDevice(c->device);
+        bb::DeviceGuard dev_guard(c->device);
         cudaError_t e = resampler_dev_init(p->spec, &p->rs);
         if (e != cudaSuccess) {
             resampler_dev_free(&p->rs); delete p;
@@ -220,11 +260,12 @@ int32_t bb_plan_create(bb_ctx* c, uint32_t src_rate, uint32_t channels, bb_sampl
     }
     *out = p;
     return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
 }
 
 void bb_plan_destroy(bb_plan* p) {
     if (!p) return;
-    cudaSetDevice(p->ctx->device);
+    bb::DeviceGuard dev_guard(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     if (p->d_pcm) cudaFree(p->d_pcm);
     if (p->d_out) cudaFree(p->d_out);
@@ -239,16 +280,20 @@ void bb_plan_destroy(bb_plan* p) {
 }
 
 int32_t bb_plan_source_window(const bb_plan* p, uint64_t* sseg, uint64_t* sovl) {
+    BB_TRY
     if (!p) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null plan");
     if (sseg) *sseg = p->src_seg; if (sovl) *sovl = p->src_ovl;
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_plan_segment_count(const bb_plan* p, uint64_t total_frames, uint64_t* nseg) {
+    BB_TRY
     if (!p || !nseg) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "bad argument");
     WindowSeq w; make_window_seq(total_frames, p->src_seg, p->src_ovl, false, &w);
     *nseg = w.nseg;
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_frontend_run(bb_plan* p, const void* pcm, uint64_t frames, int32_t pcm_is_device,
@@ -256,6 +301,7 @@ int32_t bb_frontend_run(bb_plan* p, const void* pcm, uint64_t frames, int32_t pc
                         float* d_out_user, uint64_t capacity_rows,
                         float** d_segments, uint64_t* start_sample, float* start_time, float* end_time,
                         uint64_t* nseg_out, uint64_t* nseg_padded, uint64_t* consumed_frames) {
+    BB_TRY
     if (!p) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "null plan");
     bb_ctx* c = p->ctx;
     if (frames > 0 && !pcm) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null pcm");
@@ -281,7 +327,7 @@ int32_t bb_frontend_run(bb_plan* p, const void* pcm, uint64_t frames, int32_t pc
     if (d_segments) *d_segments = nullptr;
     if (rows == 0) return BB_OK;
 
-    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    BB_DEVICE(c, c->device);
     const uint64_t frame_bytes = (uint64_t)p->channels * p->bytes_per_sample;
     const uint64_t pcm_bytes = frames * frame_bytes;
     float* d_out = d_out_user;
@@ -361,6 +407,7 @@ int32_t bb_frontend_run(bb_plan* p, const void* pcm, uint64_t frames, int32_t pc
     }
     if (d_segments) *d_segments = d_out;
     return BB_OK;
+    BB_CATCH((p && p->ctx ? &p->ctx->last_error : nullptr))
 }
 
 // ------------------------------------------------------------------------------------- post
@@ -379,23 +426,26 @@ static int32_t post_check(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t
 int32_t bb_post_run_device(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B,
                            const bb_post_cfg* cfg, const float* d_mask, const uint8_t* d_keep,
                            uint32_t* d_index, float* d_conf, uint32_t* d_count) {
+    BB_TRY
     int32_t rc = post_check(c, d_scores, B, C, valid_B, cfg, d_mask, d_keep);
     if (rc != BB_OK) return rc;
     if (valid_B && (!d_index || !d_conf || !d_count)) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null output");
-    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    BB_DEVICE(c, c->device);
     BB_CUDA_OK(c, launch_post(c->stream, d_scores, B, C, valid_B, *cfg, d_mask, d_keep, d_index, d_conf, d_count));
     if (valid_B) c->launches += 1;
     return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
 }
 
 int32_t bb_post_run(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t C, uint32_t valid_B,
                     const bb_post_cfg* cfg, const float* d_mask, const uint8_t* d_keep,
                     uint32_t* h_index, float* h_conf, uint32_t* h_count) {
+    BB_TRY
     int32_t rc = post_check(c, d_scores, B, C, valid_B, cfg, d_mask, d_keep);
     if (rc != BB_OK) return rc;
     if (valid_B == 0) return BB_OK;
     if (!h_index || !h_conf || !h_count) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null output");
-    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    BB_DEVICE(c, c->device);
     if (c->post_capacity_rows < valid_B || c->post_capacity_k < cfg->top_k) {
         BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
         if (c->d_post_index) cudaFree(c->d_post_index);
@@ -416,20 +466,23 @@ int32_t bb_post_run(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t C, ui
     BB_CUDA_OK(c, cudaMemcpyAsync(h_count, c->d_post_count, (uint64_t)valid_B * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
 }
 
 // ------------------------------------------------------------------------------------ dense heads
 int32_t bb_dense_run(bb_ctx* c, const float* d_x, uint32_t B, uint32_t K, const float* d_W, const float* d_b, uint32_t N,
                      int32_t activation, float* d_out) {
+    BB_TRY
     if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
     if ((uint64_t)B * N == 0) return BB_OK;
     if (!d_x || !d_W || !d_out || K == 0) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null argument");
     if (activation < BB_ACT_NONE || activation > BB_ACT_SOFTMAX) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "unknown activation");
-    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    BB_DEVICE(c, c->device);
     int n = 0;
     BB_CUDA_OK(c, launch_dense(c->stream, d_x, B, K, d_W, d_b, N, activation, d_out, &n));
     c->launches += n;
     return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
 }
 
 }  // extern "C"

@@ -65,6 +65,22 @@ struct bb_plan {
     float* d_out = nullptr; uint64_t d_out_rows = 0;
 };
 
+namespace bb {
+// Makes `device` current for the scope and restores the caller's device on exit: a host that shares its thread
+// with another CUDA user (ONNX Runtime, torch) keeps the device it had.
+struct DeviceGuard {
+    int prev = -1; bool changed = false; cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != device) { err = cudaSetDevice(device); changed = err == cudaSuccess && prev >= 0; }
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+}  // namespace bb
+#define BB_DEVICE(ctx, device) bb::DeviceGuard _bb_dev_guard(device); BB_CUDA_OK(ctx, _bb_dev_guard.err)
+
 #define BB_SET_ERR(ctx, code, msg) do { if (ctx) (ctx)->last_error = (msg); else bb::set_tls_error(msg); return (code); } while (0)
 #define BB_CUDA_OK(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
         std::string _m = std::string(#expr) + ": " + cudaGetErrorString(_e); \

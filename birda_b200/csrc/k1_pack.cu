@@ -185,6 +185,106 @@ pack_kernel(const void* __restrict__ pcm_v, uint32_t channels, uint64_t total_fr
     }
 }
 
+// ---- 24-bit packed PCM (BB_S24).  symphonia's PCM decoder presents a 24-bit sample as S32 `sample << 8`, which
+// append_samples converts through its S32 arm (decode.rs:386-402): value = ((s24 << 8) as f32) / 2^31.
+// Four frames per thread: 12 * CH contiguous bytes, fetched as aligned 32-bit words (one extra word when the group
+// starts mid-word, merged by a funnel shift); the window tail and the last bytes of the buffer go byte by byte.
+__device__ __forceinline__ float conv24(int s_shl8) { return __fmul_rn(__int2float_rn(s_shl8), 1.0f / 2147483648.0f); }
+__device__ __forceinline__ int load24_bytes(const unsigned char* __restrict__ p) {
+    return (int)(((unsigned)__ldg(p) << 8) | ((unsigned)__ldg(p + 1) << 16) | ((unsigned)__ldg(p + 2) << 24));
+}
+__device__ __forceinline__ float downmix24(const unsigned char* __restrict__ p, uint32_t channels, float fch) {
+    if (channels == 1) return conv24(load24_bytes(p));
+    float sum = 0.0f;
+    for (uint32_t c = 0; c < channels; ++c) sum = __fadd_rn(sum, conv24(load24_bytes(p + 3 * c)));
+    return __fdiv_rn(sum, fch);
+}
+// 12 bytes (three little-endian words) -> four samples, each already shifted left by 8
+__device__ __forceinline__ void unpack24x4(unsigned x0, unsigned x1, unsigned x2, int (&s)[4]) {
+    s[0] = (int)(x0 << 8);
+    s[1] = (int)(__funnelshift_r(x0, x1, 24) << 8);
+    s[2] = (int)(__funnelshift_r(x1, x2, 16) << 8);
+    s[3] = (int)(x2 & 0xffffff00u);
+}
+
+template <int CH_T>
+__global__ void __launch_bounds__(kThreads)
+pack24_kernel(const unsigned char* __restrict__ pcm, uint32_t channels, uint64_t total_frames,
+              uint64_t seg, uint64_t hop, uint64_t nseg, uint64_t last_start, uint64_t row_first,
+              float* __restrict__ out, uint32_t tiles_per_row, uint64_t ntiles) {
+    const float fch = (float)channels;
+    const unsigned char* pcm_end = pcm + total_frames * channels * 3;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t lrow = tile / tiles_per_row;
+        const uint64_t row = row_first + lrow;
+        const uint64_t j0 = (tile - lrow * tiles_per_row) * (uint64_t)kTile;
+        uint64_t start = 0, take = 0;
+        if (row < nseg) {
+            start = (row + 1 == nseg) ? last_start : row * hop;
+            take = total_frames - start < seg ? total_frames - start : seg;
+        }
+        float* __restrict__ orow = out + row * seg;
+        const bool vec_store = (seg % 4 == 0) && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0);
+        for (uint64_t j = j0 + (uint64_t)threadIdx.x * 4; j < j0 + kTile && j < seg; j += (uint64_t)kThreads * 4) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            bool done = false;
+            if (CH_T != 0 && j + 4 <= take) {
+                constexpr int ch = CH_T == 0 ? 1 : CH_T;
+                constexpr int NW = 3 * ch;                                     // words of payload
+                const unsigned char* g = pcm + (start + j) * ch * 3;
+                const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+                const unsigned char* ga4 = reinterpret_cast<const unsigned char*>(ga & ~(uintptr_t)3);
+                if (ga4 >= pcm && ga4 + (NW + 1) * 4 <= pcm_end) {
+                    const unsigned sh = (unsigned)(ga & 3) * 8;
+                    unsigned w[NW + 1];
+#pragma unroll
+                    for (int i = 0; i <= NW; ++i) w[i] = __ldg(reinterpret_cast<const unsigned*>(ga4) + i);
+                    unsigned x[NW];
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) x[i] = __funnelshift_r(w[i], w[i + 1], sh);
+                    if (ch == 1) {
+                        int sv[4]; unpack24x4(x[0], x[1], x[2], sv);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = conv24(sv[e]);
+                    } else {
+                        int a[4], b[4];
+                        unpack24x4(x[0], x[1], x[2], a); unpack24x4(x[NW - 3], x[NW - 2], x[NW - 1], b);
+                        // frames (L0 R0) (L1 R1) | (L2 R2) (L3 R3): sum = 0 + l + r ; / 2 in the reference's order
+                        o[0] = __fdiv_rn(__fadd_rn(__fadd_rn(0.0f, conv24(a[0])), conv24(a[1])), 2.0f);
+                        o[1] = __fdiv_rn(__fadd_rn(__fadd_rn(0.0f, conv24(a[2])), conv24(a[3])), 2.0f);
+                        o[2] = __fdiv_rn(__fadd_rn(__fadd_rn(0.0f, conv24(b[0])), conv24(b[1])), 2.0f);
+                        o[3] = __fdiv_rn(__fadd_rn(__fadd_rn(0.0f, conv24(b[2])), conv24(b[3])), 2.0f);
+                    }
+                    done = true;
+                }
+            }
+            if (!done) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (j + e < take) o[e] = downmix24(pcm + (start + j + e) * channels * 3, channels, fch);
+            }
+            if (vec_store && j + 4 <= seg) *reinterpret_cast<float4*>(orow + j) = make_float4(o[0], o[1], o[2], o[3]);
+            else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (j + e < seg) orow[j + e] = o[e];
+            }
+        }
+    }
+}
+
+cudaError_t launch_s24(cudaStream_t st, const void* d_pcm, uint32_t channels, uint64_t total_frames, uint64_t seg,
+                       uint64_t hop, uint64_t nseg, uint64_t last_start, uint64_t row_first, uint64_t rows_total, float* d_out) {
+    const uint32_t tiles_per_row = (uint32_t)((seg + kTile - 1) / kTile);
+    const uint64_t ntiles = rows_total * tiles_per_row;
+    if (ntiles == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)(ntiles > 0x7fffffffull ? 0x7fffffffull : ntiles);
+    const unsigned char* p = static_cast<const unsigned char*>(d_pcm);
+    if (channels == 1) pack24_kernel<1><<<grid, kThreads, 0, st>>>(p, channels, total_frames, seg, hop, nseg, last_start, row_first, d_out, tiles_per_row, ntiles);
+    else if (channels == 2) pack24_kernel<2><<<grid, kThreads, 0, st>>>(p, channels, total_frames, seg, hop, nseg, last_start, row_first, d_out, tiles_per_row, ntiles);
+    else pack24_kernel<0><<<grid, kThreads, 0, st>>>(p, channels, total_frames, seg, hop, nseg, last_start, row_first, d_out, tiles_per_row, ntiles);
+    return cudaGetLastError();
+}
+
 template <int FMT>
 cudaError_t launch_fmt(cudaStream_t st, int sm_count, const void* d_pcm, uint32_t channels,
                        uint64_t total_frames, uint64_t seg, uint64_t hop, uint64_t nseg,
@@ -217,6 +317,7 @@ cudaError_t launch_pack(cudaStream_t st, int sm_count, const void* d_pcm, int fm
         case BB_S16: return launch_fmt<BB_S16>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, row_first, rows_total, d_out);
         case BB_S32: return launch_fmt<BB_S32>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, row_first, rows_total, d_out);
         case BB_F32: return launch_fmt<BB_F32>(st, sm_count, d_pcm, channels, total_frames, seg, hop, nseg, last_start, row_first, rows_total, d_out);
+        case BB_S24: return launch_s24(st, d_pcm, channels, total_frames, seg, hop, nseg, last_start, row_first, rows_total, d_out);
         default: return cudaErrorInvalidValue;
     }
 }

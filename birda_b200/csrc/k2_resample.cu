@@ -116,6 +116,16 @@ __device__ __forceinline__ float mono_at_t(const void* __restrict__ pcm_v, uint6
 __device__ __forceinline__ float mono_at(const void* __restrict__ pcm, int fmt, uint64_t frame, uint32_t channels, float fch) {
     if (fmt == BB_S16) return mono_at_t<int16_t>(pcm, frame, channels, fch);
     if (fmt == BB_S32) return mono_at_t<int32_t>(pcm, frame, channels, fch);
+    if (fmt == BB_S24) {                       // packed 24-bit: (s24 << 8) through the S32 arm (decode.rs:386-402)
+        const unsigned char* p = static_cast<const unsigned char*>(pcm) + frame * channels * 3;
+        auto ld24 = [](const unsigned char* q) {
+            return (int)(((unsigned)__ldg(q) << 8) | ((unsigned)__ldg(q + 1) << 16) | ((unsigned)__ldg(q + 2) << 24));
+        };
+        if (channels == 1) return conv_s(ld24(p));
+        float sum = 0.0f;
+        for (uint32_t c = 0; c < channels; ++c) sum = __fadd_rn(sum, conv_s(ld24(p + 3 * c)));
+        return __fdiv_rn(sum, fch);
+    }
     return mono_at_t<float>(pcm, frame, channels, fch);
 }
 
@@ -357,7 +367,7 @@ cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& r
     if (grid64 > P.nitems) grid64 = P.nitems;
     const unsigned grid = (unsigned)grid64;
     cudaError_t e = cudaSuccess;
-if (fmt != BB_S16 && fmt != BB_S32 && fmt != BB_F32) return cudaErrorInvalidValue;
+    if (fmt != BB_S16 && fmt != BB_S32 && fmt != BB_F32 && fmt != BB_S24) return cudaErrorInvalidValue;
     e = cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     resample_kernel<<<grid, kThreads, smem, st>>>(P);

@@ -80,6 +80,15 @@ struct Source {
             for (uint32_t c = 0; c < ch; ++c) s += (int)__ldg(p + c);
             const float v = __fmul_rn(__int2float_rn(s), 1.0f / 32768.0f);
             return ch == 1 ? v : __fdiv_rn(v, fch);
+        } else if (fmt == BB_S24) {              // packed 24-bit: (s24 << 8) through the S32 arm (decode.rs:386-402)
+            const unsigned char* p = reinterpret_cast<const unsigned char*>(pcm) + f * ch * 3;
+            auto ld24 = [](const unsigned char* q) {
+                return (int)(((unsigned)__ldg(q) << 8) | ((unsigned)__ldg(q + 1) << 16) | ((unsigned)__ldg(q + 2) << 24));
+            };
+            if (ch == 1) return __fmul_rn(__int2float_rn(ld24(p)), 1.0f / 2147483648.0f);
+            float s = 0.0f;
+            for (uint32_t c = 0; c < ch; ++c) s = __fadd_rn(s, __fmul_rn(__int2float_rn(ld24(p + 3 * c)), 1.0f / 2147483648.0f));
+            return __fdiv_rn(s, fch);
         } else if (fmt == BB_S32) {
             const int* p = reinterpret_cast<const int*>(pcm) + f * ch;
             if (ch == 1) return __fmul_rn(__int2float_rn(__ldg(p)), 1.0f / 2147483648.0f);
@@ -222,7 +231,7 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
 
     Source src;
     src.pcm = P.pcm; src.fmt = P.fmt; src.ch = P.channels; src.fch = (float)P.channels;
-    const uint32_t bps = P.fmt == BB_S16 ? 2u : 4u;
+    const uint32_t bps = P.fmt == BB_S16 ? 2u : P.fmt == BB_S24 ? 3u : 4u;
     src.pcm_end = reinterpret_cast<const char*>(P.pcm) + P.total_frames * P.channels * bps;
     src.kind = 2;
     if (P.fmt == BB_S16 && P.channels == 2 && (reinterpret_cast<uintptr_t>(P.pcm) & 3) == 0) src.kind = 0;
@@ -514,7 +523,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
 
     Source src;
     src.pcm = P.pcm; src.fmt = P.fmt; src.ch = P.channels; src.fch = (float)P.channels;
-    const uint32_t bps = P.fmt == BB_S16 ? 2u : 4u;
+    const uint32_t bps = P.fmt == BB_S16 ? 2u : P.fmt == BB_S24 ? 3u : 4u;
     src.pcm_end = reinterpret_cast<const char*>(P.pcm) + P.total_frames * P.channels * bps;
     src.kind = KIND;                                   // chosen by the launcher (source_kind)
     const uint64_t row_end = P.row_first + P.rows_total;

@@ -15,6 +15,7 @@
 // reference pins frame length, hop, mel edges or scaling — SURVEY.md §8f-3), so the layer is a general one: window,
 // mel weights and scaling are inputs; parity is against the float64 statement of the layer kept with the tests.
 #include "common.cuh"
+#include "guard.hpp"
 #include "k2_warp.cuh"
 #include <cstring>
 #include <string>
@@ -358,7 +359,7 @@ extern "C" {
 
 void bb_melspec_destroy(bb_melspec* m) {
     if (!m) return;
-    cudaSetDevice(m->ctx->device);
+    bb::DeviceGuard dev_guard(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     void* ptrs[] = {m->d_twf, m->d_posf, m->d_wk, m->d_window, m->d_w, m->d_P};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -366,6 +367,7 @@ void bb_melspec_destroy(bb_melspec* m) {
 }
 
 int32_t bb_melspec_create(bb_ctx* c, const bb_melspec_cfg* cfg, const float* window, const float* mel_weights, bb_melspec** out) {
+    BB_TRY
     if (!c || !cfg || !window || !mel_weights || !out) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
     const uint32_t nfft = cfg->n_fft;
@@ -376,6 +378,7 @@ int32_t bb_melspec_create(bb_ctx* c, const bb_melspec_cfg* cfg, const float* win
     if (cfg->log_mode < 0 || cfg->log_mode > 2) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "log_mode must be 0, 1 or 2");
     bb_melspec* m = new (std::nothrow) bb_melspec();
     if (!m) BB_SET_ERR(c, BB_ERR_OOM, "out of host memory");
+    struct Owner { bb_melspec* m; ~Owner() { if (m) bb_melspec_destroy(m); } } owner{m};      // released on success
     m->ctx = c; m->cfg = *cfg; m->N = (int)nfft / 2;
     const uint32_t bins = nfft / 2 + 1;
     // support of the mel filters: only those bins are produced and multiplied
@@ -386,10 +389,10 @@ int32_t bb_melspec_create(bb_ctx* c, const bb_melspec_cfg* cfg, const float* win
     if (hi <= lo) { lo = 0; hi = 1; }
     m->bin_lo = lo; m->nb = hi - lo; m->kpad = (m->nb + 31u) & ~31u;
     std::vector<int> fwd, inv;
-    if (!k2w::choose_radices(m->N, false, &fwd)) { delete m; BB_SET_ERR(c, BB_ERR_INTERNAL, "no radix plan"); }
+    if (!k2w::choose_radices(m->N, false, &fwd)) BB_SET_ERR(c, BB_ERR_INTERNAL, "no radix plan");
     // only the forward half of the plan is used; the inverse half is filled in to keep the plan well formed
     if (!k2w::choose_radices(m->N, true, &inv) || !k2w::build_plan_from_radices(m->N, m->N, m->N, &m->plan, &fwd, &inv)) {
-        delete m; BB_SET_ERR(c, BB_ERR_INTERNAL, "no radix plan");
+        BB_SET_ERR(c, BB_ERR_INTERNAL, "no radix plan");
     }
     m->plan.half_in = m->N;                                              // no zero padding: every input slot is live
     std::vector<float2> twf(m->plan.twf_len), twi(m->plan.twi_len), wk(m->N + 1);
@@ -407,7 +410,7 @@ int32_t bb_melspec_create(bb_ctx* c, const bb_melspec_cfg* cfg, const float* win
             float* q = &w2[(size_t)r * m->kpad * 2 + (size_t)(j >> 5) * 64 + (j & 31u)];
             q[0] = h; q[32] = w - h;
         }
-    cudaSetDevice(c->device);
+    bb::DeviceGuard dev_guard(c->device);
     auto up = [&](const void* h, size_t bytes, void** d) -> cudaError_t {
         cudaError_t e = cudaMalloc(d, bytes);
         return e != cudaSuccess ? e : cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
@@ -420,11 +423,12 @@ int32_t bb_melspec_create(bb_ctx* c, const bb_melspec_cfg* cfg, const float* win
     if (e == cudaSuccess) e = up(w2.data(), w2.size() * 4, (void**)&m->d_w);
     if (e != cudaSuccess) {
         std::string msg = std::string("melspec init: ") + cudaGetErrorString(e);
-        bb_melspec_destroy(m);
         BB_SET_ERR(c, e == cudaErrorMemoryAllocation ? BB_ERR_OOM : BB_ERR_CUDA, msg);
     }
+    owner.m = nullptr;
     *out = m;
     return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
 }
 
 int32_t bb_melspec_info(const bb_melspec* m, uint32_t* bin_lo, uint32_t* n_bins, uint32_t* k_padded) {
@@ -436,11 +440,12 @@ int32_t bb_melspec_info(const bb_melspec* m, uint32_t* bin_lo, uint32_t* n_bins,
 }
 
 int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, uint32_t samples, float* d_out) {
+    BB_TRY
     if (!m) return BB_ERR_INVALID_ARG;
     bb_ctx* c = m->ctx;
     if (rows == 0) return BB_OK;
     if (!d_segments || !d_out || samples == 0) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null argument");
-    BB_CUDA_OK(c, cudaSetDevice(c->device));
+    BB_DEVICE(c, c->device);
     const bb_melspec_cfg& cfg = m->cfg;
     // P is produced and consumed in chunks of whole rows: L2-sized (<= 64 MB) when that still fills the GPU
     const uint64_t row_bytes = (uint64_t)cfg.n_frames * m->kpad * 8;       // hi and lo parts
@@ -509,6 +514,7 @@ int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, ui
         c->launches += 2;
     }
     return BB_OK;
+    BB_CATCH((m && m->ctx ? &m->ctx->last_error : nullptr))
 }
 
 }  // extern "C"

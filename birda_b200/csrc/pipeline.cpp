@@ -9,13 +9,15 @@
 //   the valid rows (:317, :363-385) -> detections sorted by (start_time asc, confidence desc) (:178-187).
 #include "../../include/birda_b200.h"
 #include "rules.hpp"
+#include "guard.hpp"
+#include "watchdog.hpp"
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
 
-namespace bb { void set_tls_error(const std::string& m); }
 
 struct bb_pipeline {
     bb_ctx* ctx = nullptr;
@@ -32,6 +34,10 @@ struct bb_pipeline {
     uint64_t use_clock = 0;
     uint64_t plans_created = 0;
     bool sync_before_classify = false;        // bb_pipeline_set_sync_before_classify
+    // per-batch seam (processor.rs:263-277): host hooks and / or a library-kept watchdog
+    bb_batch_hook before_batch = nullptr, after_batch = nullptr; void* hook_user = nullptr;
+    uint64_t batch_timeout_ms = 0; bb_watchdog_fn on_timeout = nullptr; void* timeout_user = nullptr;
+    std::unique_ptr<bb::Watchdog> watchdog;
     void* pinned = nullptr; uint64_t pinned_bytes = 0;
     std::vector<uint32_t> h_index; std::vector<float> h_conf; std::vector<uint32_t> h_count;
     std::vector<float> st, et; std::vector<uint64_t> ss;
@@ -95,11 +101,21 @@ int run_piece(bb_pipeline* p, const void* pcm, uint64_t frames, uint64_t first_s
         const uint32_t valid = (uint32_t)std::min<uint64_t>(B, nseg - first);
         const float* d_scores = nullptr; uint32_t classes = 0;
         if (p->sync_before_classify && bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));
+        // the watchdog brackets the batch exactly as processor.rs:263-277 does: armed before the classifier is called,
+        // dropped once its results are on the host (bb_post_run synchronises the stream)
+        if (p->before_batch) p->before_batch(p->hook_user, B, valid, seg_base + first);
+        if (p->watchdog) p->watchdog->arm(p->batch_timeout_ms, B);
         rc = p->classify(p->user, d_seg + first * seg_samples, B, (uint32_t)seg_samples, &d_scores, &classes);
+        int prc = BB_OK;
+        if (rc == 0 && d_scores && classes)
+            prc = bb_post_run(p->ctx, d_scores, B, classes, valid, &p->cfg.post, p->cfg.d_mask, p->cfg.d_species_keep,
+                              p->h_index.data(), p->h_conf.data(), p->h_count.data());
+        const bool fired = p->watchdog ? p->watchdog->disarm() : false;
+        if (p->after_batch) p->after_batch(p->hook_user, B, valid, seg_base + first);
+        if (fired) return fail(p, BB_ERR_TIMEOUT, "inference batch of " + std::to_string(B) + " outlived the watchdog (" +
+                                                  std::to_string(p->batch_timeout_ms) + " ms)");
         if (rc != 0 || !d_scores || classes == 0) return fail(p, BB_ERR_INTERNAL, "classifier callback failed");   // Error::Inference
-        rc = bb_post_run(p->ctx, d_scores, B, classes, valid, &p->cfg.post, p->cfg.d_mask, p->cfg.d_species_keep,
-                         p->h_index.data(), p->h_conf.data(), p->h_count.data());
-        if (rc != BB_OK) return fail(p, rc, bb_last_error(p->ctx));
+        if (prc != BB_OK) return fail(p, prc, bb_last_error(p->ctx));
         for (uint32_t r = 0; r < valid; ++r)                                       // processor.rs:363-385
             for (uint32_t j = 0; j < p->h_count[r]; ++j) {
                 const float c = p->h_conf[(size_t)r * K + j];
@@ -135,6 +151,7 @@ uint32_t effective_batch(const bb_pipeline* p, uint64_t frames, uint32_t rate) {
 extern "C" {
 
 int32_t bb_pipeline_create(bb_ctx* ctx, const bb_pipeline_cfg* cfg, bb_classify_fn fn, void* user, bb_pipeline** out) {
+    BB_TRY
     if (!ctx || !cfg || !fn || !out) return fail(nullptr, BB_ERR_INVALID_ARG, "null argument");
     if (cfg->batch_size < 1 || cfg->batch_size > 512) return fail(nullptr, BB_ERR_INVALID_ARG, "batch_size must be in [1, 512] (constants.rs:44-55)");
     if (cfg->post.top_k < 1 || cfg->post.top_k > BB_MAX_TOP_K) return fail(nullptr, BB_ERR_INVALID_ARG, "top_k out of range");
@@ -143,6 +160,7 @@ int32_t bb_pipeline_create(bb_ctx* ctx, const bb_pipeline_cfg* cfg, bb_classify_
     p->ctx = ctx; p->cfg = *cfg; p->classify = fn; p->user = user;
     *out = p;
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 void bb_pipeline_destroy(bb_pipeline* p) {
@@ -156,9 +174,24 @@ const char* bb_pipeline_last_error(const bb_pipeline* p) { return p ? p->error.c
 uint64_t bb_pipeline_plans_created(const bb_pipeline* p) { return p ? p->plans_created : 0; }
 void bb_pipeline_set_sync_before_classify(bb_pipeline* p, int32_t on) { if (p) p->sync_before_classify = on != 0; }
 
+void bb_pipeline_set_batch_hooks(bb_pipeline* p, bb_batch_hook before, bb_batch_hook after, void* user) {
+    if (!p) return;
+    p->before_batch = before; p->after_batch = after; p->hook_user = user;
+}
+
+void bb_pipeline_set_batch_timeout(bb_pipeline* p, uint64_t timeout_ms, bb_watchdog_fn on_fire, void* user) {
+    if (!p) return;
+    p->batch_timeout_ms = timeout_ms; p->on_timeout = on_fire; p->timeout_user = user;
+    p->watchdog.reset();
+    if (timeout_ms == 0) return;
+    try { p->watchdog.reset(new bb::Watchdog(on_fire, user)); }
+    catch (...) { p->batch_timeout_ms = 0; fail(p, BB_ERR_INTERNAL, "could not start the watchdog thread"); }
+}
+
 int32_t bb_pipeline_process_pcm(bb_pipeline* p, const void* pcm, uint64_t frames, uint32_t src_rate, uint32_t channels,
                                 int32_t fmt, bb_detection* out, uint64_t capacity, uint64_t* n_detections,
                                 uint64_t* n_segments, uint32_t* batch_used) {
+    BB_TRY
     if (!p || (!pcm && frames) || src_rate == 0) return fail(p, BB_ERR_INVALID_ARG, "bad argument");
     int rc = ensure_plan(p, src_rate, channels, fmt);
     if (rc != BB_OK) return rc;
@@ -173,10 +206,12 @@ int32_t bb_pipeline_process_pcm(bb_pipeline* p, const void* pcm, uint64_t frames
     if (sink.overflow) return fail(p, BB_ERR_CAPACITY, "detection capacity too small (" + std::to_string(sink.n) + " needed)");
     sort_detections(out, sink.n);
     return BB_OK;
+    BB_CATCH((p ? &p->error : nullptr))
 }
 
 int32_t bb_pipeline_process_wav(bb_pipeline* p, const char* path, uint64_t piece_frames, bb_detection* out, uint64_t capacity,
                                 uint64_t* n_detections, uint64_t* n_segments, uint32_t* batch_used) {
+    BB_TRY
     if (!p || !path) return fail(p, BB_ERR_INVALID_ARG, "bad argument");
     bb_wav_info info;
     int rc = bb_wav_probe(path, &info);
@@ -185,7 +220,7 @@ int32_t bb_pipeline_process_wav(bb_pipeline* p, const char* path, uint64_t piece
     if (rc != BB_OK) return rc;
     const uint32_t B = effective_batch(p, info.frames, info.sample_rate);
     if (batch_used) *batch_used = B;
-    const uint64_t fb = (uint64_t)info.channels * (info.fmt == BB_S16 ? 2 : 4);
+    const uint64_t fb = (uint64_t)info.channels * bb::sample_bytes(info.fmt);
     uint64_t src_seg = 0, src_ovl = 0;
     bb_plan_source_window(p->plan, &src_seg, &src_ovl);
     if (piece_frames == 0) piece_frames = (256ull << 20) / fb;                     // ~256 MB of PCM per piece
@@ -200,17 +235,17 @@ int32_t bb_pipeline_process_wav(bb_pipeline* p, const char* path, uint64_t piece
         if (!eof) {                                                                // trim to k*B full windows
             uint64_t nfull = want >= src_seg ? (want - src_seg) / hop + 1 : 0;
             nfull = nfull / B * B;
-            if (nfull == 0) { want = std::min<uint64_t>(info.frames - pos, src_seg + (uint64_t)B * hop); eof = pos + want >= info.frames; }
+            if (nfull == 0) { want = std::min<uint64_t>(info.frames - pos, src_seg + (uint64_t)(B - 1) * hop); eof = pos + want >= info.frames; }
             else want = (nfull - 1) * hop + src_seg;
         }
         if (p->pinned_bytes < want * fb) {
-            bb_sync(p->ctx);
+            if (bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));
             if (p->pinned) bb_host_free(p->pinned);
             p->pinned = nullptr; p->pinned_bytes = 0;
             if (bb_host_alloc(want * fb > 0 ? want * fb : 1, &p->pinned) != BB_OK) return fail(p, BB_ERR_OOM, "pinned staging allocation failed");
             p->pinned_bytes = want * fb;
         }
-        bb_sync(p->ctx);                                                            // previous piece's H2D copies are done
+        if (bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));   // previous piece's H2D copies are done
         rc = bb_wav_read(path, &info, pos, want, p->pinned);
         if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
         uint64_t nseg = 0, consumed = 0;
@@ -226,6 +261,7 @@ int32_t bb_pipeline_process_wav(bb_pipeline* p, const char* path, uint64_t piece
     if (sink.overflow) return fail(p, BB_ERR_CAPACITY, "detection capacity too small (" + std::to_string(sink.n) + " needed)");
     sort_detections(out, sink.n);
     return BB_OK;
+    BB_CATCH((p ? &p->error : nullptr))
 }
 
 }  // extern "C"

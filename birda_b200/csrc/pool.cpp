@@ -11,9 +11,9 @@
 #include <thread>
 #include <vector>
 #include "rules.hpp"
+#include "guard.hpp"
 #include "../../include/birda_b200.h"
 
-namespace bb { void set_tls_error(const std::string& m); }
 
 struct bb_pool {
     struct Worker { int32_t device; bb_ctx* ctx; bb_pipeline* pipe; };
@@ -37,6 +37,7 @@ void bb_pool_destroy(bb_pool* p) {
 
 int32_t bb_pool_create(const int32_t* devices, uint32_t n_devices, const bb_pipeline_cfg* cfgs, bb_classify_fn fn,
                        void* const* users, bb_pool** out) {
+    BB_TRY
     if (!devices || n_devices == 0 || !cfgs || !fn || !out) return pool_fail(BB_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
     bb_pool* p = new (std::nothrow) bb_pool();
@@ -53,6 +54,7 @@ int32_t bb_pool_create(const int32_t* devices, uint32_t n_devices, const bb_pipe
     }
     *out = p;
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 void bb_pool_free_results(bb_pool_result* results, uint32_t n) {
@@ -61,6 +63,7 @@ void bb_pool_free_results(bb_pool_result* results, uint32_t n) {
 }
 
 int32_t bb_pool_process_wavs(bb_pool* p, const char* const* paths, uint32_t n_files, bb_pool_result* results) {
+    BB_TRY
     if (!p || (!paths && n_files) || (!results && n_files)) return pool_fail(BB_ERR_INVALID_ARG, "null argument");
     // longest first (durations from the WAV headers; unreadable files go last and report their error from the worker)
     std::vector<std::pair<double, uint32_t>> order(n_files);
@@ -106,6 +109,7 @@ int32_t bb_pool_process_wavs(bb_pool* p, const char* const* paths, uint32_t n_fi
     int32_t worst = BB_OK;
     for (uint32_t i = 0; i < n_files; ++i) if (results[i].status != BB_OK) worst = results[i].status;
     return worst;
+    BB_CATCH(nullptr)
 }
 
 }  // extern "C"

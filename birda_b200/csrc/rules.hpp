@@ -8,6 +8,9 @@
 
 namespace bb {
 
+// bytes of one sample of a bb_sample_fmt (BB_S16 = 1, BB_S32 = 2, BB_F32 = 3, BB_S24 = 4: 3-byte packed)
+inline uint32_t sample_bytes(int fmt) { return fmt == 1 ? 2u : fmt == 4 ? 3u : 4u; }
+
 struct Window { uint64_t start; uint64_t take; };
 
 // StreamingDecoder::next_segment as a closed form over a fully buffered stream

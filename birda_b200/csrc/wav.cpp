@@ -4,10 +4,14 @@
 // src/pipeline/processor.rs:457, :59; reader src/audio/decode.rs:54-128) become the wall; WAV PCM is
 // already the interleaved layout K1/K2 consume, so the file is read straight into the staging buffer.
 // Sample formats follow what the reference converts (src/audio/decode.rs:353-411): 16-bit PCM -> S16,
-// 32-bit PCM -> S32, 32-bit float -> F32.  8/24-bit PCM and 64-bit float are reported as unsupported
-// (the reference's append_samples drops U8/S24/F64 buffers silently, decode.rs:407-409).
+// 24-bit PCM -> S24 (3-byte packed; symphonia's PCM decoder presents it as S32 `sample << 8`, so it takes the S32
+// arm, decode.rs:386-402), 32-bit PCM -> S32, 32-bit float -> F32.  8-bit PCM and 64-bit float are reported as
+// unsupported (append_samples drops U8 / F64 buffers silently, decode.rs:407-409).  Headers whose block size does
+// not equal channels * bytes per sample (padded containers, EXTENSIBLE with fewer valid bits than container bits)
+// are rejected rather than read at the wrong stride.
 #include "../../include/birda_b200.h"
 #include "rules.hpp"
+#include "guard.hpp"
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -15,7 +19,6 @@
 #include <unistd.h>
 #include <sys/stat.h>
 
-namespace bb { void set_tls_error(const std::string& m); }
 
 namespace {
 uint32_t rd32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -27,11 +30,13 @@ int fail(int code, const std::string& m) { bb::set_tls_error(m); return code; }
 extern "C" {
 
 int32_t bb_wav_probe(const char* path, bb_wav_info* out) {
+    BB_TRY
     if (!path || !out) return fail(BB_ERR_INVALID_ARG, "null argument");
     std::memset(out, 0, sizeof(*out));
     int fd = ::open(path, O_RDONLY);
     if (fd < 0) return fail(BB_ERR_IO, std::string("cannot open ") + path);
-    struct stat st; ::fstat(fd, &st);
+    struct stat st;
+    if (::fstat(fd, &st) != 0) { ::close(fd); return fail(BB_ERR_IO, std::string("cannot stat ") + path); }
     const uint64_t file_size = (uint64_t)st.st_size;
     unsigned char h[12];
     if (::pread(fd, h, 12, 0) != 12 || std::memcmp(h + 8, "WAVE", 4) != 0 ||
@@ -40,7 +45,7 @@ int32_t bb_wav_probe(const char* path, bb_wav_info* out) {
     }
     const bool rf64 = std::memcmp(h, "RF64", 4) == 0;
     uint64_t pos = 12, data_size64 = 0; bool have_ds64 = false, have_fmt = false, have_data = false;
-    uint16_t tag = 0, channels = 0, bits = 0, block_align = 0; uint32_t rate = 0;
+    uint16_t tag = 0, channels = 0, bits = 0, block_align = 0, valid_bits = 0; uint32_t rate = 0;
     uint64_t data_off = 0, data_size = 0;
     while (pos + 8 <= file_size) {
         unsigned char ch[8];
@@ -55,12 +60,16 @@ int32_t bb_wav_probe(const char* path, bb_wav_info* out) {
             const size_t n = sz < 40 ? (size_t)sz : 40;
             if (::pread(fd, f, n, (off_t)body) != (ssize_t)n) break;
             tag = rd16(f); channels = rd16(f + 2); rate = rd32(f + 4); block_align = rd16(f + 12); bits = rd16(f + 14);
-            if (tag == 0xFFFE && sz >= 40) tag = rd16(f + 24);      // WAVE_FORMAT_EXTENSIBLE: sub-format GUID starts with the tag
+            valid_bits = bits;
+            if (tag == 0xFFFE && sz >= 40) { valid_bits = rd16(f + 18); tag = rd16(f + 24); }   // WAVE_FORMAT_EXTENSIBLE: wValidBitsPerSample, then the sub-format GUID (starts with the tag)
             have_fmt = true;
         } else if (std::memcmp(ch, "data", 4) == 0) {
             data_off = body;
             data_size = (sz == 0xFFFFFFFFu && rf64 && have_ds64) ? data_size64 : sz;
-            if (data_off + data_size > file_size) data_size = file_size - data_off;      // truncated file: decode what exists
+            // streamed writers leave 0 (or 0xFFFFFFFF without ds64) in the size field: the data runs to the end of the file
+            if (data_size == 0 || (sz == 0xFFFFFFFFu && !(rf64 && have_ds64))) data_size = file_size > data_off ? file_size - data_off : 0;
+            if (data_off > file_size) data_size = 0;
+            else if (data_size > file_size - data_off) data_size = file_size - data_off;     // truncated file: decode what exists
             have_data = true;
             break;
         }
@@ -74,21 +83,30 @@ int32_t bb_wav_probe(const char* path, bb_wav_info* out) {
     const uint32_t bytes = bits / 8;
     out->fmt = 0;
     if (tag == 1 && bits == 16) out->fmt = BB_S16;
+    else if (tag == 1 && bits == 24) out->fmt = BB_S24;
     else if (tag == 1 && bits == 32) out->fmt = BB_S32;
     else if (tag == 3 && bits == 32) out->fmt = BB_F32;
     const uint32_t frame_bytes = block_align ? block_align : bytes * channels;
     out->frames = frame_bytes ? data_size / frame_bytes : 0;
+    if (out->fmt != 0 && (frame_bytes != bytes * channels || valid_bits != bits)) {
+        out->fmt = 0;
+        return fail(BB_ERR_UNSUPPORTED_FORMAT, std::string(path) + ": block size " + std::to_string(frame_bytes) + " / " +
+                    std::to_string(valid_bits) + " valid bits do not match " + std::to_string(channels) + " channels of " +
+                    std::to_string(bits) + "-bit samples");
+    }
     if (out->fmt == 0)
         return fail(BB_ERR_UNSUPPORTED_FORMAT, std::string(path) + ": sample format tag " + std::to_string(tag) + " / " +
                     std::to_string(bits) + " bits is not converted by the reference (decode.rs:353-411)");
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 int32_t bb_wav_read(const char* path, const bb_wav_info* info, uint64_t first_frame, uint64_t frames, void* dst) {
+    BB_TRY
     if (!path || !info || (!dst && frames)) return fail(BB_ERR_INVALID_ARG, "null argument");
     if (info->fmt == 0) return fail(BB_ERR_UNSUPPORTED_FORMAT, "unsupported sample format");
     if (first_frame > info->frames || frames > info->frames - first_frame) return fail(BB_ERR_INVALID_ARG, "frame range outside the data chunk");
-    const uint64_t fb = (uint64_t)info->channels * (info->fmt == BB_S16 ? 2 : 4);
+    const uint64_t fb = (uint64_t)info->channels * bb::sample_bytes(info->fmt);
     int fd = ::open(path, O_RDONLY);
     if (fd < 0) return fail(BB_ERR_IO, std::string("cannot open ") + path);
     uint64_t off = info->data_offset + first_frame * fb, left = frames * fb;
@@ -100,6 +118,7 @@ int32_t bb_wav_read(const char* path, const bb_wav_info* info, uint64_t first_fr
     }
     ::close(fd);
     return BB_OK;
+    BB_CATCH(nullptr)
 }
 
 }  // extern "C"

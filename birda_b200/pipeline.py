@@ -207,12 +207,30 @@ class NativePipeline:
         res.batches = -(-res.segments // max(res.effective_batch_size, 1))
         return res
 
+    def set_batch_hooks(self, before: Optional[Callable] = None, after: Optional[Callable] = None) -> None:
+        """``before(batch_rows, valid_rows, first_segment)`` / ``after(...)`` around every inference batch — the seam
+        where the reference arms and drops its watchdog (src/pipeline/processor.rs:263-277)."""
+        import ctypes as C
+
+        from . import _lib
+        mk = lambda f: _lib.BATCH_HOOK(lambda user, rows, valid, first: f(int(rows), int(valid), int(first))) if f else C.cast(None, _lib.BATCH_HOOK)
+        self._hooks = (mk(before), mk(after))
+        _lib.lib.bb_pipeline_set_batch_hooks(self._h, self._hooks[0], self._hooks[1], None)
+
+    def set_batch_timeout(self, timeout_ms: int, on_fire: Optional[Callable] = None) -> None:
+        """Library-kept watchdog per batch.  ``on_fire(timeout_secs, batch)``; None = the reference's exit(1)."""
+        import ctypes as C
+
+        from . import _lib
+        self._on_fire = _lib.WATCHDOG_FN(lambda user, secs, batch: on_fire(int(secs), int(batch))) if on_fire else C.cast(None, _lib.WATCHDOG_FN)
+        _lib.lib.bb_pipeline_set_batch_timeout(self._h, timeout_ms, self._on_fire, None)
+
     def process_pcm(self, pcm: np.ndarray, channels: int, source_rate: int, fmt: int) -> ProcessResult:
         import ctypes as C
 
         from . import _lib
         pcm = np.ascontiguousarray(pcm)
-        frames = pcm.size // channels
+        frames = pcm.size // (channels * (3 if fmt == 4 else 1))
         return self._collect(lambda buf, cap, nd, ns, bu: _lib.lib.bb_pipeline_process_pcm(
             self._h, C.c_void_p(pcm.ctypes.data), frames, source_rate, channels, fmt, buf, cap, nd, ns, bu))
 

@@ -41,6 +41,20 @@ def synth_pcm(seed: int, seconds: float, rate: int, channels: int = 1, dtype=np.
     return out.reshape(-1)
 
 
+def pack_s24(samples_i32: np.ndarray) -> np.ndarray:
+    """int32 values in [-2^23, 2^23) -> 3-byte little-endian packed PCM (uint8, 3 per sample) as a 24-bit WAV holds it."""
+    v = np.asarray(samples_i32, dtype=np.int32).astype(np.uint32)
+    out = np.empty((v.size, 3), np.uint8)
+    out[:, 0] = v & 0xFF; out[:, 1] = (v >> 8) & 0xFF; out[:, 2] = (v >> 16) & 0xFF
+    return out.reshape(-1)
+
+
+def synth_pcm24(seed: int, seconds: float, rate: int, channels: int = 1) -> np.ndarray:
+    """The synthetic signal quantised to 24 bits, packed (interleaved, 3 bytes per sample)."""
+    x = synth_pcm(seed, seconds, rate, channels, np.int32)
+    return pack_s24(x >> 8)
+
+
 def synth_logits(seed: int, rows: int, classes: int, adversarial: bool = True) -> np.ndarray:
     """N(-6, 2^2) background with 0-8 planted N(2,1) values per row, plus adversarial rows
     (exact ties, values exactly at logit(0.1), all below threshold, >= 6 above)."""

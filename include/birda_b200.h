@@ -12,6 +12,7 @@
  *     across the boundary (the reference forbids panics: Cargo.toml:85-87);
  *   - `bb_last_error(ctx)` returns a message for the last failure on that context
  *     (ctx == NULL: the calling thread's last context-free failure);
+ *   - entry points leave the calling thread's current CUDA device as they found it;
  *   - a bb_ctx is one GPU + one CUDA stream; it is NOT thread-safe (one owner thread, as
  *     BirdClassifier is only used from the main thread: src/pipeline/processor.rs:659-671).
  *     Several contexts (one per GPU) may run concurrently;
@@ -48,11 +49,16 @@ typedef enum {
     BB_ERR_INTERNAL           = -7,  /* -> Error::Internal { message }                        */
     BB_ERR_NO_DEVICE          = -8,
     BB_ERR_CAPACITY           = -9,  /* caller-provided output array too small                */
-    BB_ERR_IO                 = -10  /* -> Error::AudioOpen / Error::AudioDecode              */
+    BB_ERR_IO                 = -10, /* -> Error::AudioOpen / Error::AudioDecode              */
+    BB_ERR_TIMEOUT            = -11  /* a batch outlived the watchdog (src/gpu/watchdog.rs:22-52) */
 } bb_status;
 
-/* interleaved frames, native endian; the formats src/audio/decode.rs:353-411 converts */
-typedef enum { BB_S16 = 1, BB_S32 = 2, BB_F32 = 3 } bb_sample_fmt;
+/* interleaved frames, little endian; the formats src/audio/decode.rs:353-411 converts.
+ * BB_S24 = 3-byte packed PCM as it sits in a 24-bit WAV file.  symphonia's PCM decoder hands 24-bit PCM to
+ * append_samples as AudioBufferRef::S32 holding `sample << 8` (symphonia-codec-pcm is not vendored under
+ * /root/reference: stated from the crate's published behaviour), so the value converted is
+ * ((s24 << 8) as f32) / 2^31 through the S32 arm, decode.rs:386-402. */
+typedef enum { BB_S16 = 1, BB_S32 = 2, BB_F32 = 3, BB_S24 = 4 } bb_sample_fmt;
 
 /* ------------------------------------------------------------------------------------------
  * Host rules — pure arithmetic, no GPU.  Bit-exact restatements of the reference's integer
@@ -108,6 +114,38 @@ int32_t bb_rule_resampled_len(uint64_t src_len, uint32_t src_rate, uint32_t tgt_
 uint32_t bb_rule_date_to_week(uint32_t month, uint32_t day);
 uint32_t bb_rule_week_to_start_day(uint32_t week);
 void     bb_rule_day_of_year_to_date(uint32_t day_of_year, uint32_t* month, uint32_t* day);
+
+/* BIRDA_INFERENCE_TIMEOUT parsing: seconds in [1, 3600], anything else (NULL, junk, out of range) -> 10.
+ * src/pipeline/processor.rs:194-211 */
+uint64_t bb_rule_inference_timeout_secs(const char* env_value);
+
+/* scientific_name(): bytes of `label` that form the species key before case folding — the part before the first
+ * '_' when that part contains a space, else the whole label.  src/inference/geomodel.rs:28-33 */
+uint32_t bb_rule_scientific_name_len(const char* label);
+
+/* Range-filter precompute, label side (src/inference/geomodel.rs:41-127 SpeciesMapping::build, :129-157
+ * GeomodelScores::project): project geomodel scores into the classifier's label space as the dense vector K3
+ * reads — mask[i] = score_of(classifier_labels[i]), NaN where that is None.  Keys are scientific names, lower-cased
+ * (Unicode simple case folding of the Latin, Greek and Cyrillic blocks; everything else compares as is); the first
+ * classifier label wins a key collision (its later namesakes have no entry unless their label STRING is identical);
+ * mapped species the geomodel did not report read 0.0; later scores overwrite earlier ones.  score_species[j] /
+ * score_values[j] are the LocationScore list of RangeFilter::predict (src/inference/classifier.rs:133-141).
+ * mapped / unmatched: SpeciesMapping::mapped_count / unmatched_count (may be NULL).  Pure host code. */
+int32_t bb_mask_build(const char* const* classifier_labels, uint32_t n_classifier,
+                      const char* const* geomodel_labels, uint32_t n_geomodel,
+                      const char* const* score_species, const float* score_values, uint32_t n_scores,
+                      float* mask, uint32_t* mapped, uint32_t* unmatched);
+
+/* ------------------------------------------------------------------------------------------
+ * Watchdog (src/gpu/watchdog.rs:22-66): a timer armed around one inference batch.  If it is not cancelled
+ * within timeout_ms, on_fire(user, timeout_secs, batch_size) runs on the watchdog's thread; on_fire == NULL is
+ * the reference's behaviour — print its FATAL block to stderr and terminate the process with status 1
+ * (watchdog.rs:31-49).  bb_watchdog_cancel is WatchdogGuard::drop: it disarms the timer and frees it.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bb_watchdog bb_watchdog;
+typedef void (*bb_watchdog_fn)(void* user, uint64_t timeout_secs, uint32_t batch_size);
+int32_t bb_watchdog_start(uint64_t timeout_ms, uint32_t batch_size, bb_watchdog_fn on_fire, void* user, bb_watchdog** out);
+void    bb_watchdog_cancel(bb_watchdog*);
 
 /* ------------------------------------------------------------------------------------------
  * Context
@@ -261,6 +299,16 @@ const char* bb_pipeline_last_error(const bb_pipeline*);
 /* front-end plans are cached per (source rate, channels, format), 8 kinds, least recently used evicted; this counts
  * how many were built so far (a mixed-rate directory builds each kind once) */
 uint64_t    bb_pipeline_plans_created(const bb_pipeline*);
+/* Per-batch seam (src/pipeline/processor.rs:263-277): `before` is called right before the classifier callback of
+ * every batch, `after` once that batch's inference and post step have completed on the device (the pipeline
+ * synchronises the stream per batch while hooks or a timeout are set) — the two places where the reference
+ * creates and drops its WatchdogGuard, so a Rust host arms start_inference_watchdog exactly as today. */
+typedef void (*bb_batch_hook)(void* user, uint32_t batch_rows, uint32_t valid_rows, uint64_t first_segment);
+void        bb_pipeline_set_batch_hooks(bb_pipeline*, bb_batch_hook before, bb_batch_hook after, void* user);
+/* Or let the library keep the watchdog: every batch is bracketed by a timer of timeout_ms (0 = off).  With
+ * on_fire == NULL a batch that outlives it ends the process like the reference; with a callback, on_fire runs and
+ * the file fails with BB_ERR_TIMEOUT as soon as the batch returns. */
+void        bb_pipeline_set_batch_timeout(bb_pipeline*, uint64_t timeout_ms, bb_watchdog_fn on_fire, void* user);
 /* for classifiers that do not run on the ctx stream: synchronise it before every callback (the callback then has to
  * finish its own work before it returns).  Off by default; bb_pool turns it on. */
 void        bb_pipeline_set_sync_before_classify(bb_pipeline*, int32_t on);
@@ -334,6 +382,10 @@ int32_t bb_melspec_info(const bb_melspec*, uint32_t* bin_lo, uint32_t* n_bins, u
 /* d_segments: device [rows, samples] f32 (the packed tensor of bb_frontend_run); d_out: device [rows, n_mels, n_frames].
  * Asynchronous on the ctx stream. */
 int32_t bb_melspec_run(bb_melspec*, const float* d_segments, uint32_t rows, uint32_t samples, float* d_out);
+
+/* Debug hook (tests): the n-th guarded entry point called on this thread from now on fails as if a host
+ * allocation had thrown (n = 1: the next one; 0 disarms).  Proves that exceptions stop at the boundary. */
+void bb_debug_inject_alloc_failure(int32_t nth);
 
 /* Device memory helpers for hosts without a CUDA binding of their own (tests, Rust shim) */
 int32_t bb_dev_alloc(bb_ctx*, uint64_t bytes, void** out);

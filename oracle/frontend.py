@@ -22,7 +22,15 @@ from . import rules
 
 f32 = np.float32
 
-FMT_S16, FMT_S32, FMT_F32 = 1, 2, 3   # mirrors bb_sample_fmt in include/birda_b200.h
+FMT_S16, FMT_S32, FMT_F32, FMT_S24 = 1, 2, 3, 4   # mirrors bb_sample_fmt in include/birda_b200.h
+
+
+def s24_to_s32(packed: np.ndarray) -> np.ndarray:
+    """3-byte little-endian PCM -> the S32 buffer symphonia's PCM decoder hands to append_samples for a 24-bit
+    stream: ``sample << 8`` (symphonia-codec-pcm, not vendored under /root/reference: stated from the crate's
+    published behaviour; the reference then takes the S32 arm, src/audio/decode.rs:386-402)."""
+    b = np.asarray(packed, dtype=np.uint8).reshape(-1, 3).astype(np.uint32)
+    return ((b[:, 0] << np.uint32(8)) | (b[:, 1] << np.uint32(16)) | (b[:, 2] << np.uint32(24))).astype(np.uint32).view(np.int32)
 
 
 # --------------------------------------------------------------------------- A1
@@ -33,6 +41,8 @@ def to_mono_f32(pcm: np.ndarray, channels: int) -> np.ndarray:
     int16 / int32 / float32.  Mono: straight convert.  Multi-channel: ``sum = 0f32``,
     left-to-right f32 adds of the converted samples, one f32 divide by ``channels``."""
     a = np.asarray(pcm)
+    if a.dtype == np.uint8:                                           # packed 24-bit PCM (FMT_S24)
+        a = s24_to_s32(a)
     if a.dtype == np.int16:
         conv = lambda x: x.astype(np.float32) / f32(32768.0)          # f32::from(s) / 32768.0
     elif a.dtype == np.int32:
