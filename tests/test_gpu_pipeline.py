@@ -189,3 +189,58 @@ def test_native_pool_two_workers_match_single_pipeline(tmp_path):
         assert key(g) == key(r), p
     assert sum(len(g.detections) for g in got) > 20
     one.close(); ctx.close()
+
+
+def test_native_pipeline_batch_hooks_bracket_every_batch():
+    """The watchdog seam (src/pipeline/processor.rs:263-277): before/after fire once per batch, in order, with the
+    padded batch size, the valid rows and the batch's first segment."""
+    import torch
+    from birda_b200.pipeline import NativePipeline
+    ctx = b.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    clf = StandInClassifier(144_000, 265)
+    cfg = ProcessingConfig(target_rate=48_000, segment_duration=3.0, overlap=0.0, batch_size=4, min_confidence=0.1)
+    nat = NativePipeline(ctx, cfg, clf)
+    events = []
+    nat.set_batch_hooks(lambda rows, valid, first: events.append(("before", rows, valid, first)),
+                        lambda rows, valid, first: events.append(("after", rows, valid, first)))
+    res = nat.process_pcm(synth_pcm(40, 31.0, 48_000, 1), 1, 48_000, b.FMT_S16)        # 11 windows: 4 + 4 + 3 (padded)
+    assert res.segments == 11
+    want = []
+    for first, valid in ((0, 4), (4, 4), (8, 3)):
+        want += [("before", 4, valid, first), ("after", 4, valid, first)]
+    assert events == want
+    nat.close(); ctx.close()
+
+
+def test_native_pipeline_batch_timeout_fails_the_file():
+    """A classifier that outlives the library-kept watchdog: on_fire runs on the watchdog thread with the reference's
+    arguments (whole seconds, batch size) and the file fails with BB_ERR_TIMEOUT; with a generous timeout the same
+    pipeline then completes."""
+    import time
+
+    import torch
+    from birda_b200.pipeline import NativePipeline
+    ctx = b.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    inner = StandInClassifier(144_000, 265)
+    slow = {"sleep": 0.6}
+
+    def clf(x):
+        time.sleep(slow["sleep"])
+        return inner(x)
+
+    cfg = ProcessingConfig(target_rate=48_000, segment_duration=3.0, overlap=0.0, batch_size=4, min_confidence=0.1)
+    nat = NativePipeline(ctx, cfg, clf)
+    fired = []
+    nat.set_batch_timeout(150, lambda secs, batch: fired.append((secs, batch)))
+    pcm = synth_pcm(41, 13.0, 48_000, 1)
+    with pytest.raises(b.BirdaError) as e:
+        nat.process_pcm(pcm, 1, 48_000, b.FMT_S16)
+    assert e.value.code == -11 and "watchdog" in e.value.message
+    assert fired == [(0, 4)]
+    slow["sleep"] = 0.0
+    nat.set_batch_timeout(60_000, lambda secs, batch: fired.append((secs, batch)))
+    res = nat.process_pcm(pcm, 1, 48_000, b.FMT_S16)
+    assert res.segments == 5 and len(fired) == 1
+    nat.set_batch_timeout(0)
+    assert nat.process_pcm(pcm, 1, 48_000, b.FMT_S16).segments == 5
+    nat.close(); ctx.close()
