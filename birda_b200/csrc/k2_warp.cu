@@ -6,8 +6,10 @@
 // resample_plan_kernel (compile-time plan, one window) and resample_warp_kernel (runtime plan, any supported rate pair).
 #include "common.cuh"
 #include "k2_warp.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <numeric>
 #include <vector>
 
 namespace bb {
@@ -174,8 +176,12 @@ template <class AM> struct RtView {
     static __device__ __forceinline__ int n(const RtPlan& p) { return p.N; }
     static __device__ __forceinline__ int m(const RtPlan& p) { return p.M; }
     static __device__ __forceinline__ int half_in(const RtPlan& p) { return p.half_in; }
-    template <class C, class Exec, class Loader, class Sink, class After>
-    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const Tables<C>& T, typename Mem<C>::T* A,
+    static __device__ __forceinline__ int adv_in(const RtPlan& p) { return p.adv_in; }
+    static __device__ __forceinline__ int adv_out(const RtPlan& p) { return p.adv_out; }
+    static __device__ __forceinline__ int carry_slots(const RtPlan& p) { return p.carry_slots; }
+    static constexpr bool kCompactTw = false;
+    template <class C, class Exec, class Loader, class Sink, class After, class TB>
+    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const TB& T, typename Mem<C>::T* A,
                                                  typename Mem<C>::T* B, typename Mem<C>::T* carry, const Loader& ld,
                                                  const Sink& sink, After&& after) {
         process_block<C, AM>(ex, p, T, A, B, carry, ld, sink, after);
@@ -186,8 +192,12 @@ template <class PL> struct CtView {
     static __device__ __forceinline__ constexpr int n(const RtPlan&) { return PL::N; }
     static __device__ __forceinline__ constexpr int m(const RtPlan&) { return PL::M; }
     static __device__ __forceinline__ constexpr int half_in(const RtPlan&) { return PL::HALF_IN; }
-    template <class C, class Exec, class Loader, class Sink, class After>
-    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const Tables<C>& T, typename Mem<C>::T* A,
+    static __device__ __forceinline__ constexpr int adv_in(const RtPlan&) { return PL::ADV_IN; }
+    static __device__ __forceinline__ constexpr int adv_out(const RtPlan&) { return PL::ADV_OUT; }
+    static __device__ __forceinline__ constexpr int carry_slots(const RtPlan&) { return PL::CARRY; }
+    static constexpr bool kCompactTw = PL::COMPACT_TW;      // two-stream kernel only
+    template <class C, class Exec, class Loader, class Sink, class After, class TB>
+    static __device__ __forceinline__ void block(const Exec& ex, const RtPlan& p, const TB& T, typename Mem<C>::T* A,
                                                  typename Mem<C>::T* B, typename Mem<C>::T* carry, const Loader& ld,
                                                  const Sink& sink, After&& after) {
         process_block_ct<PL, C>(ex, T, A, B, carry, ld, sink, after);
@@ -226,8 +236,9 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
     float2* A = reinterpret_cast<float2*>(gbase);
     float2* B = reinterpret_cast<float2*>(gbase + P.off_B);
     float2* carry = reinterpret_cast<float2*>(gbase + P.off_carry);
-    const Tables<float2> T{s_twf, s_twi, s_sidx, s_pq1, s_pq2, s_WI, P.ordf_len ? s_ordf : nullptr, P.ordi_len ? s_ordi : nullptr};
-    const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
+    const Tables<float2> T{{s_twf}, {s_twi}, s_sidx, s_pq1, s_pq2, s_WI, P.ordf_len ? s_ordf : nullptr, P.ordi_len ? s_ordi : nullptr};
+    // N / M: input samples consumed / output samples emitted per block (the blocking; rubato's: the transform lengths)
+    const int N = PV::adv_in(PL), M = PV::adv_out(PL), HALF_IN = PV::half_in(PL), CARRY = PV::carry_slots(PL);
 
     Source src;
     src.pcm = P.pcm; src.fmt = P.fmt; src.ch = P.channels; src.fch = (float)P.channels;
@@ -263,7 +274,7 @@ __device__ __forceinline__ void resample_body(const WarpParams& P) {
             return q0 < take ? (int)(take - q0 < (uint64_t)N ? take - q0 : (uint64_t)N) : 0;
         };
 
-        for (int j = lane; j < M / 2; j += nl) carry[j] = make_float2(0.f, 0.f);
+        for (int j = lane; j < CARRY; j += nl) carry[j] = make_float2(0.f, 0.f);
         const bool vec = ((reinterpret_cast<uintptr_t>(orow) & 7) == 0);      // M is even: b*M keeps 8-byte alignment
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
         int shift = prefetch_block<typename PV::MapA>(src, A, start + (uint64_t)bfirst * N, valid_of(bfirst), HALF_IN, lane, nl);
@@ -489,14 +500,16 @@ template <class PV, int KIND, int NLH>
 __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     extern __shared__ __align__(16) unsigned char smem[];
     const RtPlan& PL = P.plan;
-    float4* s_twf = reinterpret_cast<float4*>(smem);
-    float4* s_twi = reinterpret_cast<float4*>(smem + P.off_twi);
+    constexpr bool CTW = PV::kCompactTw;
+    using TwE = typename Tw<cx2, CTW>::E;                 // float4 (x, x, y, y), or float2 when the plan keeps its twiddles compact
+    TwE* s_twf = reinterpret_cast<TwE*>(smem);
+    TwE* s_twi = reinterpret_cast<TwE*>(smem + P.off_twi);
     uint4* s_sidx = reinterpret_cast<uint4*>(smem + P.off_sidx);
     float4* s_pq1 = reinterpret_cast<float4*>(smem + P.off_pq1);
     float4* s_pq2 = reinterpret_cast<float4*>(smem + P.off_pq2);
     float2* s_WI = reinterpret_cast<float2*>(smem + P.off_WI);
     const int NT = blockDim.x;
-    auto bc = [](float2 w) { return make_float4(w.x, w.x, w.y, w.y); };
+    auto bc = [](float2 w) { if constexpr (CTW) return w; else return make_float4(w.x, w.x, w.y, w.y); };
     for (int i = threadIdx.x; i < PL.twf_len; i += NT) s_twf[i] = bc(P.twf[i]);
     for (int i = threadIdx.x; i < PL.twi_len; i += NT) s_twi[i] = bc(P.twi[i]);
     for (int i = threadIdx.x; i < PL.split_len; i += NT) { s_sidx[i] = P.sidx[i]; s_pq1[i] = P.pq1[i]; s_pq2[i] = P.pq2[i]; s_WI[i] = P.WI[i]; }
@@ -518,8 +531,9 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
     float4* A = reinterpret_cast<float4*>(gbase);
     float4* B = reinterpret_cast<float4*>(gbase + P.off_B);
     float4* carry = reinterpret_cast<float4*>(gbase + P.off_carry);
-    const Tables<cx2> T{s_twf, s_twi, s_sidx, s_pq1, s_pq2, s_WI, P.ordf_len ? s_ordf : nullptr, P.ordi_len ? s_ordi : nullptr};
-    const int N = PV::n(PL), M = PV::m(PL), HALF_IN = PV::half_in(PL);
+    const Tables<cx2, CTW> T{{s_twf}, {s_twi}, s_sidx, s_pq1, s_pq2, s_WI, P.ordf_len ? s_ordf : nullptr, P.ordi_len ? s_ordi : nullptr};
+    // N / M: input samples consumed / output samples emitted per block (the blocking; rubato's: the transform lengths)
+    const int N = PV::adv_in(PL), M = PV::adv_out(PL), HALF_IN = PV::half_in(PL), CARRY = PV::carry_slots(PL);
 
     Source src;
     src.pcm = P.pcm; src.fmt = P.fmt; src.ch = P.channels; src.fch = (float)P.channels;
@@ -563,7 +577,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
             d.base = start[s] + q0;
             return d;
         };
-        for (int j = lane; j < M / 2; j += nl) carry[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = lane; j < CARRY; j += nl) carry[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t bfirst = b0 > 0 ? b0 - 1 : 0;       // recompute the block before the run for its carry
         DualStream c0 = stream_of(0, bfirst), c1 = stream_of(1, bfirst);
         prefetch_pair<KIND, typename PV::MapA, NLH, PV::half_in(RtPlan{})>(src, A, c0, c1, HALF_IN, N, lane, nl);
@@ -602,7 +616,7 @@ template <class PL, int THREADS, int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
 resample_plan2_kernel(const __grid_constant__ WarpParams P) {
     // expected thread-group size (the staging loops unroll for it; any other size takes their generic form)
-    resample_body_dual<CtView<PL>, KIND, THREADS == 640 ? 160 : 64>(P);
+    resample_body_dual<CtView<PL>, KIND, PL::dual_group_lanes(THREADS, (int)kSmemMax, kMaxGroups)>(P);
 }
 
 // how the kernels read the PCM: 0 = S16 stereo staged with cp.async, 1 = S16 mono staged, 2 = direct loads
@@ -632,20 +646,57 @@ int ct_plan_dual_threads(int ct_index) {
     return 384;
 }
 
+bool ct_plan_compact_tw(int ct_index) {
+    int i = 0;
+#define BB_CT(NAME, NI, NO, TH, ...) if (i == ct_index) return __VA_ARGS__::COMPACT_TW; ++i;
+    BB_K2_CT_PLANS(BB_CT)
+#undef BB_CT
+    return false;
+}
+
 // index of the compile-time plan for (n_in, n_out), -1 when only the runtime plan applies
+// BIRDA_K2_BLOCKING=rubato skips the plans that use their own blocking (A/B runs, tests)
 int ct_plan_index(uint32_t n_in, uint32_t n_out) {
     if (const char* g = std::getenv("BIRDA_K2_RUNTIME_PLAN")) if (g[0] == '1') return -1;
+    bool own_blocking = true;
+    if (const char* g = std::getenv("BIRDA_K2_BLOCKING")) if (g[0] == 'r') own_blocking = false;
     int i = 0;
-#define BB_CT(NAME, NI, NO, TH, ...) if (n_in == NI && n_out == NO) return i; ++i;
+#define BB_CT(NAME, NI, NO, TH, ...) if (n_in == NI && n_out == NO && (own_blocking || __VA_ARGS__::ADV_IN == NI)) return i; ++i;
     BB_K2_CT_PLANS(BB_CT)
 #undef BB_CT
     return -1;
 }
 
-template <class PL> void ct_radices(std::vector<int>* f, std::vector<int>* v) {
+template <class PL> void ct_radices(std::vector<int>* f, std::vector<int>* v, int* adv_in, int* adv_out) {
     f->clear(); v->clear();
     for (int i = 0; i < PL::Fwd::count; ++i) f->push_back(PL::Fwd::at(i));
     for (int i = 0; i < PL::Inv::count; ++i) v->push_back(PL::Inv::at(i));
+    *adv_in = PL::ADV_IN; *adv_out = PL::ADV_OUT;
+}
+
+// Spectrum of the reference's taps for a transform of 2N real points (N != n_in: a plan with its own blocking):
+// bins [0, nkeep) of the taps zero-padded to 2N, with the forward transform's normalisation 1 / (2N) in place of
+// the reference's 1 / (2 n_in) (rules.cpp: make_resampler_spec applies the latter to spec.taps).  f64, exact index
+// reduction, rounded once.
+void blocked_filter_spectrum(const ResamplerSpec& spec, int N, int nkeep, std::vector<float>* re, std::vector<float>* im) {
+    const uint32_t L = 2u * (uint32_t)N, n = spec.n_in;
+    const double scale = (double)(2u * n) / (double)L;
+    std::vector<double> cs(L), sn(L);
+    for (uint32_t j = 0; j < L; ++j) {
+        const double a = -2.0 * 3.14159265358979323846 * (double)j / (double)L;
+        cs[j] = std::cos(a); sn[j] = std::sin(a);
+    }
+    re->assign(nkeep, 0.f); im->assign(nkeep, 0.f);
+    for (int k = 0; k < nkeep; ++k) {
+        double r = 0, i = 0;
+        uint32_t idx = 0;
+        for (uint32_t x = 0; x < n; ++x) {
+            r += (double)spec.taps[x] * cs[idx];
+            i += (double)spec.taps[x] * sn[idx];
+            idx += (uint32_t)k; if (idx >= L) idx -= L;
+        }
+        (*re)[k] = (float)(r * scale); (*im)[k] = (float)(i * scale);
+    }
 }
 
 }  // namespace
@@ -663,12 +714,29 @@ bool warp_plan_available(const ResamplerSpec& spec) {
 cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     RtPlan P; std::vector<int> fwd, inv;
     rs->ct_index = ct_plan_index(spec.n_in, spec.n_out);
+    std::vector<float> own_re, own_im;
+    const float* filt_re = spec.filt_re.data(); const float* filt_im = spec.filt_im.data();
     if (rs->ct_index >= 0) {
-        int i = 0;
-#define BB_CT(NAME, NI, NO, TH, ...) if (i == rs->ct_index) ct_radices<__VA_ARGS__>(&fwd, &inv); ++i;
+        int i = 0, adv_in = 0, adv_out = 0;
+#define BB_CT(NAME, NI, NO, TH, ...) if (i == rs->ct_index) ct_radices<__VA_ARGS__>(&fwd, &inv, &adv_in, &adv_out); ++i;
         BB_K2_CT_PLANS(BB_CT)
 #undef BB_CT
-        if (!build_plan_from_radices((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
+        int N = 1, M = 1;
+        for (int r : fwd) N *= r;
+        for (int r : inv) M *= r;
+        if (N == (int)spec.n_in && M == (int)spec.n_out) {
+            if (!build_plan_from_radices(N, M, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
+        } else {
+            // a plan with its own blocking: longer transforms over the same taps.  Only where the spectrum is extended
+            // (up-sampling): truncating it ties the result to rubato's block length.
+            const uint64_t g = std::gcd((uint64_t)spec.n_in, (uint64_t)spec.n_out);
+            const uint64_t a = spec.n_in / g, b = spec.n_out / g;
+            if (spec.n_in >= spec.n_out || (uint64_t)N * b != (uint64_t)M * a || (uint64_t)adv_in * b != (uint64_t)adv_out * a ||
+                (uint64_t)adv_in + spec.n_in - 1 > 2ull * N) return cudaErrorInvalidConfiguration;
+            if (!build_plan_from_radices(N, M, N + 1, &P, &fwd, &inv, adv_in, adv_out)) return cudaErrorInvalidConfiguration;
+            blocked_filter_spectrum(spec, N, P.nkeep, &own_re, &own_im);
+            filt_re = own_re.data(); filt_im = own_im.data();
+        }
     } else if (!build_plan((int)spec.n_in, (int)spec.n_out, (int)spec.n_keep, &P, &fwd, &inv)) return cudaErrorInvalidConfiguration;
     if (rs->ct_index >= 0) ct_plan_pads(&P); else rt_plan_pads(&P);
     // order tables: groups of 8 lanes for the two-stream kernels of compile-time plans (their offsets are compile-time,
@@ -678,7 +746,7 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     std::vector<uint16_t> pf(P.N), pi_(P.M);
     build_pos_tables(fwd, inv, P.N, P.M, pf.data(), pi_.data());
     std::vector<float2> Pt(P.nkeep), Qt(P.nkeep), WI(P.M / 2 + 1), twf(P.twf_len), twi(P.twi_len);
-    build_split_tables(P.N, P.M, P.nkeep, spec.filt_re.data(), spec.filt_im.data(), Pt.data(), Qt.data(), WI.data());
+    build_split_tables(P.N, P.M, P.nkeep, filt_re, filt_im, Pt.data(), Qt.data(), WI.data());
     build_twiddles(P, twf.data(), twi.data());
     // bank groups: 8 lanes of 16-byte elements in two-stream mode (compile-time plans), 16 lanes of 8-byte ones otherwise
     SplitLayout SL;
@@ -742,7 +810,7 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     P.twf = rs.f_twf; P.twi = rs.f_twi; P.WI = rs.f_WI; P.sidx = rs.f_sidx; P.pq1 = rs.f_pq1; P.pq2 = rs.f_pq2;
     P.ordf = rs.f_ordf; P.ordi = rs.f_ordi; P.ordf_len = rs.ordf_len; P.ordi_len = rs.ordi_len;
     P.counter = rs.f_counter;
-    P.nblk = (P.out_len + rs.n_out - 1) / rs.n_out;
+    P.nblk = (P.out_len + (uint32_t)PL.adv_out - 1) / (uint32_t)PL.adv_out;
     if (P.nblk == 0) P.nblk = 1;
     auto a16 = [](size_t x) { return (uint32_t)((x + 15) & ~(size_t)15); };
     // two-stream mode: compile-time plans only, at least two rows
@@ -751,8 +819,9 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     const size_t esz = dual ? 16 : 8;                   // bytes per complex element in shared memory
     const int max_threads = dual ? ct_plan_dual_threads(rs.ct_index) : kMaxThreads;
     P.dual = dual ? 1 : 0;
-    P.off_twi = a16((size_t)PL.twf_len * esz);
-    P.off_sidx = P.off_twi + a16((size_t)PL.twi_len * esz);
+    const size_t tw_esz = (dual && ct_plan_compact_tw(rs.ct_index)) ? 8 : esz;
+    P.off_twi = a16((size_t)PL.twf_len * tw_esz);
+    P.off_sidx = P.off_twi + a16((size_t)PL.twi_len * tw_esz);
     P.off_pq1 = P.off_sidx + a16((size_t)PL.split_len * 16);       // split tables have the same layout in both modes
     P.off_pq2 = P.off_pq1 + a16((size_t)PL.split_len * 16);
     P.off_WI = P.off_pq2 + a16((size_t)PL.split_len * 16);
@@ -762,7 +831,7 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     P.tables = P.off_items + a16((size_t)kMaxGroups * 8);
     P.off_B = a16((size_t)phys_len(PL.N, PL.pad_a) * esz);
     P.off_carry = P.off_B + a16((size_t)phys_len(PL.M, PL.pad_b) * esz);
-    P.per_group = P.off_carry + a16((size_t)(PL.M / 2) * esz);
+    P.per_group = P.off_carry + a16((size_t)PL.carry_slots * esz);
     if (P.tables + P.per_group > kSmemMax) {
         if (!dual) return cudaErrorInvalidConfiguration;
         // does not fit with two streams: one stream per group
@@ -774,8 +843,11 @@ static cudaError_t launch_warp_impl(cudaStream_t st, int sm_count, const Resampl
     if (groups > max_threads / 32) groups = max_threads / 32;
     int gw = (max_threads / 32) / groups;               // warps cooperating on one block (pair)
     if (gw < 1) gw = 1;
-    if (gw > 6) gw = 6;
-    if (const char* g = std::getenv("BIRDA_K2_GROUP_WARPS")) { int v = atoi(g); if (v >= 1 && v <= 6 && v * groups * 32 <= max_threads) gw = v; }
+    if (gw > 16) gw = 16;
+    if (const char* g = std::getenv("BIRDA_K2_GROUP_WARPS")) { int v = atoi(g); if (v >= 1 && v <= 16 && v * groups * 32 <= max_threads) gw = v; }
+    if (const char* g = std::getenv("BIRDA_K2_DEBUG")) if (g[0] == '1')
+        fprintf(stderr, "[k2] plan N=%d M=%d adv %d/%d dual=%d tables=%u per_group=%u groups=%d gw=%d smem=%zu nblk=%u\n", PL.N, PL.M, PL.adv_in, PL.adv_out,
+                (int)dual, P.tables, P.per_group, groups, gw, (size_t)P.tables + (size_t)groups * P.per_group, P.nblk);
     P.groups = groups; P.gw = gw;
     const size_t smem = P.tables + (size_t)groups * P.per_group;
     const uint64_t units = dual ? (rows_total + 1) / 2 : rows_total;      // rows or row pairs

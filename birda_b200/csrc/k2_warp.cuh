@@ -136,6 +136,13 @@ struct RtPlan {
     int twf_len, twi_len;        // compact twiddle table sizes (float2 entries)
     int pad_a, pad_b;            // 1: the forward (A) / inverse (B) buffer uses MapPad8 (one slot of padding after every eight)
     int split_len;               // pairs (k, M-k) the split pass visits = M/2 + 1 (order and addresses come from a host-built table)
+    // Blocking (overlap-add geometry).  The transforms are 2N real points in, 2M real points out; a block consumes
+    // adv_in input samples and emits adv_out output samples.  rubato's own blocking is adv_in = N, adv_out = M (the
+    // filter is N taps long); up-sampling plans may use LONGER transforms over the same taps (adv_in + taps - 1 <= 2N):
+    // the result is the same linear map of the window with less transform work per sample.
+    int adv_in, adv_out;
+    int carry_slots;             // complex slots of overlap-add carry = M - adv_out/2  (<= adv_out/2)
+    int emit_k;                  // of the last inverse stage's R outputs per butterfly, the first emit_k are emitted
 };
 
 // shared-memory storage of one element: float2 for a single stream, float4 (re0, re1, im0, im1) for two
@@ -153,6 +160,19 @@ template <> struct Mem<cx2> {
     static BB_HD cx2 bcast(float2 w) { cx2 c; c.re = make_float2(w.x, w.x); c.im = make_float2(w.y, w.y); return c; }
 };
 
+// Twiddle table pointer.  Full form: entries in the element's own storage layout (two streams: float4 (x, x, y, y), one
+// LDS.128 and no moves).  Compact form: float2 entries broadcast to the stream(s) at load time — half the shared memory,
+// for plans whose buffers leave no room (CtPlan::COMPACT_TW).
+template <class C, bool COMPACT> struct Tw {
+    using E = typename std::conditional<COMPACT, float2, typename Mem<C>::T>::type;
+    const E* p;
+    BB_HD C operator[](int i) const {
+        if constexpr (COMPACT) return Mem<C>::bcast(p[i]);
+        else return Mem<C>::ld(p + i);
+    }
+    BB_HD Tw operator+(int o) const { return Tw{p + o}; }
+};
+
 // Address map of a transform buffer: logical slot -> physical slot.  MapPad8 leaves one slot of padding after every
 // eight: a power-of-two plan's stride-8 stage (span 8, m = 1: lanes 8 slots = 128 bytes apart, an 8-way bank conflict
 // with 16-byte elements) becomes a stride-9 walk, and the runs of 8 consecutive slots the other stages touch stay
@@ -161,13 +181,13 @@ struct MapId  { static BB_HD constexpr int at(int i) { return i; } };
 struct MapPad8 { static BB_HD constexpr int at(int i) { return i + (i >> 3); } };
 
 // a[k] *= w_span^(p k), k = 1..R-1.  Table layout: chain mode [p] holds w^p; table mode [(k-1)*m + p]
-template <int R, class C> BB_HD void apply_twiddles(C (&a)[R], const typename Mem<C>::T* __restrict__ tw, int m, int p) {
+template <int R, class C, class TW> BB_HD void apply_twiddles(C (&a)[R], const TW tw, int m, int p) {
     if constexpr (tw_table_mode(R)) {
 #pragma unroll
-        for (int k = 1; k < R; ++k) a[k] = cmul(a[k], Mem<C>::ld(tw + (k - 1) * m + p));
+        for (int k = 1; k < R; ++k) a[k] = cmul(a[k], tw[(k - 1) * m + p]);
     } else {
         C pw[R];
-        pw[1] = Mem<C>::ld(tw + p);
+        pw[1] = tw[p];
 #pragma unroll
         for (int k = 2; k < R; ++k) pw[k] = cmul(pw[k / 2], pw[k - k / 2]);
 #pragma unroll
@@ -176,8 +196,8 @@ template <int R, class C> BB_HD void apply_twiddles(C (&a)[R], const typename Me
 }
 
 // ---- forward DIF stage, in place
-template <int R, class C, class AM = MapId, class S>
-BB_HD void dif_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl,
+template <int R, class C, class AM = MapId, class S, class TW>
+BB_HD void dif_stage(typename Mem<C>::T* __restrict__ buf, const TW tw, const S& s, int lane, int nl,
                      const uint32_t* __restrict__ order = nullptr) {
     const int m = s.M_();
     const int ooff = order != nullptr ? s.template ordoff<C>() : -1;
@@ -197,8 +217,8 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 }
 
 // first forward stage: input z[n] comes from `ld(n)` for n < half_in, zero above
-template <int R, class C, class AM = MapId, class S, class Loader>
-BB_HD void dif_first(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int half_in,
+template <int R, class C, class AM = MapId, class S, class Loader, class TW>
+BB_HD void dif_first(typename Mem<C>::T* __restrict__ buf, const TW tw, const S& s, int half_in,
                      const Loader& ld, int lane, int nl) {
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
@@ -217,8 +237,8 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 }
 
 // ---- inverse DIT stage, in place
-template <int R, class C, class AM = MapId, class S>
-BB_HD void dit_stage(typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s, int lane, int nl,
+template <int R, class C, class AM = MapId, class S, class TW>
+BB_HD void dit_stage(typename Mem<C>::T* __restrict__ buf, const TW tw, const S& s, int lane, int nl,
                      const uint32_t* __restrict__ order = nullptr) {
     const int m = s.M_();
     const int ooff = order != nullptr ? s.template ordoff<C>() : -1;
@@ -237,12 +257,13 @@ BB_UNROLL_N(BB_K2W_UNROLL)
     }
 }
 
-// last inverse stage (span == M): output z'[n] = (y[2n], y[2n+1]).  n < M/2: add the carry and emit;
-// n >= M/2: becomes the carry of the next block.  R even, so both halves of one carry slot belong
-// to the same butterfly (no cross-lane hazard).
-template <int R, class C, class AM = MapId, class S, class Sink>
-BB_HD void dit_last(const typename Mem<C>::T* __restrict__ buf, const typename Mem<C>::T* __restrict__ tw, const S& s,
-                    typename Mem<C>::T* __restrict__ carry, const Sink& sink, int lane, int nl) {
+// last inverse stage (span == M): output z'[n] = (y[2n], y[2n+1]), n = p + k*m.  The first `ke` values of k are this
+// block's output samples (n < adv_out/2), the rest the overlap-add carry of the next block; the old carry covers the
+// first R - ke values.  adv_out/2 is a multiple of m, so a carry slot is read (k = j) and rewritten (k = j + ke) by
+// the same lane: all reads first, then the writes (no cross-lane hazard).  rubato's blocking: ke = R/2.
+template <int R, class C, class AM = MapId, class S, class Sink, class TW>
+BB_HD void dit_last(const typename Mem<C>::T* __restrict__ buf, const TW tw, const S& s,
+                    typename Mem<C>::T* __restrict__ carry, const Sink& sink, int lane, int nl, const int ke) {
     const int m = s.M_();
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int p = lane; p < m; p += nl) {
@@ -252,10 +273,11 @@ BB_UNROLL_N(BB_K2W_UNROLL)
         if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, p);
         Dft<R, true>::run(a);
 #pragma unroll
-        for (int k = 0; k < R / 2; ++k) {
-            const int n = p + k * m;
-            sink(n, cadd(a[k], Mem<C>::ld(carry + n)));
-            Mem<C>::st(carry + n, a[k + R / 2]);
+        for (int k = 0; k < R; ++k) if (k < R - ke) a[k] = cadd(a[k], Mem<C>::ld(carry + p + k * m));
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            if (k < ke) sink(p + k * m, a[k]);
+            else Mem<C>::st(carry + p + (k - ke) * m, a[k]);
         }
     }
 }
@@ -266,9 +288,9 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 //   w = flags: 1 = Y(k) present (k < nkeep), 2 = Y(k2) present, 4 = k == 0 (DC / Nyquist are real), 8 = write Z'(k2)
 constexpr unsigned kSplitHasK = 1u, kSplitHasK2 = 2u, kSplitDc = 4u, kSplitStore2 = 8u;
 
-template <class C> struct Tables {
+template <class C, bool COMPACT_TW = false> struct Tables {
     using T = typename Mem<C>::T;
-    const T* twf; const T* twi;
+    Tw<C, COMPACT_TW> twf, twi;
     const uint4* sidx;                       // [split_len]
     const float4* pq1; const float4* pq2;    // [split_len] (P[k], Q[k]) and (P[k2], Q[k2]); broadcast to the stream(s) at load time
     const float2* WI;                        // [split_len] exp(+i pi k / M)
@@ -278,12 +300,24 @@ template <class C> struct Tables {
 // ---- fused split / filter / re-bin / inverse pack:  A (digit-reversed forward result) -> B
 //   Y(k)  = P[k] Z[k] + Q[k] conj(Z[N-k])                       (k < nkeep, else 0)
 //   Z'(k) = Y(k) + conj(Y(M-k)) + i wi[k] (Y(k) - conj(Y(M-k)))
-template <class C>
-BB_HD void split_pass(const typename Mem<C>::T* __restrict__ A, typename Mem<C>::T* __restrict__ B, const Tables<C>& T,
+// one 128-bit shared-memory load of a split-table entry (left to itself the compiler splits it into two 64-bit loads
+// because the halves are consumed at different times: twice the wavefronts at a 16-byte lane stride)
+BB_HD uint4 ld_entry128(const uint4* p) {
+#ifdef __CUDA_ARCH__
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+#else
+    return *p;
+#endif
+}
+
+template <class C, class TB>
+BB_HD void split_pass(const typename Mem<C>::T* __restrict__ A, typename Mem<C>::T* __restrict__ B, const TB& T,
                       int L, int lane, int nl) {
 BB_UNROLL_N(BB_K2W_UNROLL)
     for (int idx = lane; idx < L; idx += nl) {
-        const uint4 e = T.sidx[idx];
+        const uint4 e = ld_entry128(T.sidx + idx);      // the tables live in shared memory in every kernel that runs this pass
         const unsigned fl = e.w;
         C yk = czero<C>(), yk2 = czero<C>();
         if (fl & kSplitHasK) {
@@ -335,8 +369,8 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 // One block, in two halves.  ex.each(f) runs f(lane, nlanes) for every lane of the thread group that owns
 // the block and orders memory between calls (device: __syncwarp or a named barrier; host harness: a loop).
 // forward half: loader -> in-place DIF in A -> (before_split) -> split / filter / re-bin into B
-template <class C, class AM = MapId, class Exec, class Loader, class BeforeSplit>
-BB_HD void forward_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
+template <class C, class AM = MapId, class Exec, class Loader, class BeforeSplit, class TB>
+BB_HD void forward_half(const Exec& ex, const RtPlan& P, const TB& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
                         const Loader& ld, BeforeSplit&& before_split) {
     ex.each([&](int lane, int nl) {
         BB_K2W_RADIX_SWITCH(P.f[0].radix, (dif_first<R, C, AM>(A, T.twf, P.f[0], P.half_in, ld, lane, nl)))
@@ -347,18 +381,18 @@ BB_HD void forward_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typ
     ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.split_len, lane, nl); });
 }
 // inverse half: in-place DIT in B -> overlap-add with the carry -> sink
-template <class C, class AM = MapId, class Exec, class Sink>
-BB_HD void inverse_half(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry,
+template <class C, class AM = MapId, class Exec, class Sink, class TB>
+BB_HD void inverse_half(const Exec& ex, const RtPlan& P, const TB& T, typename Mem<C>::T* B, typename Mem<C>::T* carry,
                         const Sink& sink) {
     for (int t = 0; t + 1 < P.ni; ++t)
         ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.i[t].radix, (dit_stage<R, C, AM>(B, T.twi, P.i[t], lane, nl, T.order_i))) });
     ex.each([&](int lane, int nl) {
-        BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R, C, AM>(B, T.twi, P.i[P.ni - 1], carry, sink, lane, nl)))
+        BB_K2W_EVEN_RADIX_SWITCH(P.i[P.ni - 1].radix, (dit_last<R, C, AM>(B, T.twi, P.i[P.ni - 1], carry, sink, lane, nl, P.emit_k)))
     });
 }
 // runtime plans pad both buffers or neither (AM); the plan's pad_a / pad_b say which (rt_plan_pads)
-template <class C, class AM = MapId, class Exec, class Loader, class Sink, class AfterSplit>
-BB_HD void process_block(const Exec& ex, const RtPlan& P, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
+template <class C, class AM = MapId, class Exec, class Loader, class Sink, class AfterSplit, class TB>
+BB_HD void process_block(const Exec& ex, const RtPlan& P, const TB& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
                          typename Mem<C>::T* carry, const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
     forward_half<C, AM>(ex, P, T, A, B, ld, [] {});
     after_split();
@@ -389,7 +423,7 @@ inline WorkItems plan_work_items(uint64_t units, uint64_t groups, uint32_t nblk,
         uint64_t best = ~0ull;
         for (uint32_t pieces = 1; pieces <= nblk; ++pieces) {
             const uint32_t r = (nblk + pieces - 1) / pieces;
-            if (pieces > 1 && r < 8) break;
+            if (pieces > 1 && r < 4) break;
             const uint32_t ip = (nblk + r - 1) / r;
             const uint64_t rounds = (rem * ip + groups - 1) / groups;
             const uint64_t t = rounds * (r + (ip > 1 ? 1u : 0u));
@@ -428,13 +462,22 @@ template <int... Rs> struct RSeq {
 
 // FWD: DIF radices in application order (product N).  INV: DIT radices in application order (product M,
 // last one even).  Offsets follow build_plan_from_radices exactly (checked on the host at init).
-template <class FWD, class INV_>
+// ADV_IN_T / ADV_OUT_T: the blocking (RtPlan::adv_in / adv_out); 0 = rubato's own (N, M).
+// COMPACT_TW_T: the two-stream kernel keeps its twiddles as float2 (Tw<C, true>).
+template <class FWD, class INV_, int ADV_IN_T = 0, int ADV_OUT_T = 0, bool COMPACT_TW_T = false>
 struct CtPlan {
+    static constexpr bool COMPACT_TW = COMPACT_TW_T;
     using Fwd = FWD; using Inv = INV_;
     static constexpr int N = FWD::total();
     static constexpr int M = INV_::total();
     static constexpr int NKEEP = N < M ? N + 1 : M;
-    static constexpr int HALF_IN = (N + 1) / 2;
+    static constexpr int ADV_IN = ADV_IN_T ? ADV_IN_T : N;
+    static constexpr int ADV_OUT = ADV_OUT_T ? ADV_OUT_T : M;
+    static constexpr int HALF_IN = (ADV_IN + 1) / 2;
+    static constexpr int CARRY = M - ADV_OUT / 2;
+    static constexpr int EMIT_K = INV_::at(INV_::count - 1) * (ADV_OUT / 2) / M;
+    static_assert(ADV_OUT % 2 == 0 && (ADV_OUT / 2) % (M / INV_::at(INV_::count - 1)) == 0, "adv_out/2 must be a multiple of the last inverse stage's m");
+    static_assert(CARRY <= ADV_OUT / 2 && ADV_IN <= 2 * N, "the carry may only reach the next block");
     // buffers whose length is a multiple of 64 have stride-8 stages: pad them (MapPad8) — unless the transform has
     // two or more odd radices: their odd-stride walks are conflict-free only in the unpadded layout (measured:
     // padding the 2240-point buffer of 1029/2240 = 7 5 8 8 costs 37 %, padding 1536 = 3 8 8 8 gains 25 %)
@@ -477,6 +520,26 @@ struct CtPlan {
         for (int u = 0; u < t; ++u) if (inv_wants(u)) off += M / INV_::at(u);
         return off;
     }
+    // shared-memory footprint of the two-stream kernel (16-byte elements), the launcher's formula at compile time:
+    // the kernel needs the lanes-per-group it will be launched with to unroll its staging loops
+    static constexpr int a16(int x) { return (x + 15) & ~15; }
+    static constexpr int twf_len() { int off = 0; for (int t = 0; t + 1 < FWD::count; ++t) off += tw_entries(FWD::at(t), fwd_span(t) / FWD::at(t)); return off > 0 ? off : 1; }
+    static constexpr int twi_len() { int off = 0; for (int t = 1; t < INV_::count; ++t) off += tw_entries(INV_::at(t), INV_::prod_upto(t)); return off > 0 ? off : 1; }
+    static constexpr int ordf_len() { int n = 0; for (int t = 1; t < FWD::count; ++t) if (fwd_wants(t)) n += N / FWD::at(t); return n; }
+    static constexpr int ordi_len() { int n = 0; for (int t = 0; t + 1 < INV_::count; ++t) if (inv_wants(t)) n += M / INV_::at(t); return n; }
+    static constexpr int dual_tables_bytes(int max_groups) {
+        return a16(twf_len() * (COMPACT_TW ? 8 : 16)) + a16(twi_len() * (COMPACT_TW ? 8 : 16)) + 3 * a16((M / 2 + 1) * 16) + a16((M / 2 + 1) * 8) + a16(ordf_len() * 4) + a16(ordi_len() * 4) + a16(max_groups * 8);
+    }
+    static constexpr int dual_group_bytes() {
+        return a16((PAD_A ? N + (N + 7) / 8 : N) * 16) + a16((PAD_B ? M + (M + 7) / 8 : M) * 16) + a16(CARRY * 16);
+    }
+    static constexpr int dual_group_lanes(int threads, int smem_max, int max_groups) {
+        int groups = (smem_max - dual_tables_bytes(max_groups)) / dual_group_bytes();
+        if (groups > max_groups) groups = max_groups;
+        if (groups > threads / 32) groups = threads / 32;
+        if (groups < 1) return 0;
+        return (threads / 32) / groups * 32;
+    }
     template <int T> using FwdStage = CtStage<FWD::at(T), fwd_span(T), N, fwd_twoff(T), fwd_ordoff(T)>;
     template <int T> using InvStage = CtStage<INV_::at(T), inv_span(T), M, inv_twoff(T), inv_ordoff(T)>;
     static_assert(INV_::at(INV_::count - 1) % 2 == 0, "last inverse radix must be even");
@@ -488,7 +551,7 @@ template <class L, class F> BB_HD auto loader_pick(const L& l, F&& f, int) -> de
 template <class L, class F> BB_HD void loader_pick(const L& l, F&& f, long) { f(l); }
 
 template <class PL, class C, class Exec, int T> struct CtFwdRest {
-    static BB_HD void run(const Exec& ex, typename Mem<C>::T* A, const typename Mem<C>::T* twf, const uint32_t* order) {
+    template <class TW> static BB_HD void run(const Exec& ex, typename Mem<C>::T* A, const TW twf, const uint32_t* order) {
         if constexpr (T < PL::Fwd::count) {
             using S = typename PL::template FwdStage<T>;
             ex.each([&](int lane, int nl) { dif_stage<S::radix, C, typename PL::MapA>(A, twf, S{}, lane, nl, order); });
@@ -497,7 +560,7 @@ template <class PL, class C, class Exec, int T> struct CtFwdRest {
     }
 };
 template <class PL, class C, class Exec, int T> struct CtInvMid {
-    static BB_HD void run(const Exec& ex, typename Mem<C>::T* B, const typename Mem<C>::T* twi, const uint32_t* order) {
+    template <class TW> static BB_HD void run(const Exec& ex, typename Mem<C>::T* B, const TW twi, const uint32_t* order) {
         if constexpr (T + 1 < PL::Inv::count) {
             using S = typename PL::template InvStage<T>;
             ex.each([&](int lane, int nl) { dit_stage<S::radix, C, typename PL::MapB>(B, twi, S{}, lane, nl, order); });
@@ -506,8 +569,8 @@ template <class PL, class C, class Exec, int T> struct CtInvMid {
     }
 };
 
-template <class PL, class C, class Exec, class Loader, class BeforeSplit>
-BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B, const Loader& ld,
+template <class PL, class C, class Exec, class Loader, class BeforeSplit, class TB>
+BB_HD void forward_half_ct(const Exec& ex, const TB& T, typename Mem<C>::T* A, typename Mem<C>::T* B, const Loader& ld,
                            BeforeSplit&& before_split) {
     using S0 = typename PL::template FwdStage<0>;
     loader_pick(ld, [&](const auto& l) {
@@ -517,14 +580,14 @@ BB_HD void forward_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::
     before_split();
     ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::M / 2 + 1, lane, nl); });
 }
-template <class PL, class C, class Exec, class Sink>
-BB_HD void inverse_half_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* B, typename Mem<C>::T* carry, const Sink& sink) {
+template <class PL, class C, class Exec, class Sink, class TB>
+BB_HD void inverse_half_ct(const Exec& ex, const TB& T, typename Mem<C>::T* B, typename Mem<C>::T* carry, const Sink& sink) {
     CtInvMid<PL, C, Exec, 0>::run(ex, B, T.twi, T.order_i);
     using SL = typename PL::template InvStage<PL::Inv::count - 1>;
-    ex.each([&](int lane, int nl) { dit_last<SL::radix, C, typename PL::MapB>(B, T.twi, SL{}, carry, sink, lane, nl); });
+    ex.each([&](int lane, int nl) { dit_last<SL::radix, C, typename PL::MapB>(B, T.twi, SL{}, carry, sink, lane, nl, PL::EMIT_K); });
 }
-template <class PL, class C, class Exec, class Loader, class Sink, class AfterSplit>
-BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
+template <class PL, class C, class Exec, class Loader, class Sink, class AfterSplit, class TB>
+BB_HD void process_block_ct(const Exec& ex, const TB& T, typename Mem<C>::T* A, typename Mem<C>::T* B,
                             typename Mem<C>::T* carry, const Loader& ld, const Sink& sink, AfterSplit&& after_split) {
     forward_half_ct<PL, C>(ex, T, A, B, ld, [] {});
     after_split();
@@ -545,7 +608,15 @@ BB_HD void process_block_ct(const Exec& ex, const Tables<C>& T, typename Mem<C>:
 #define BB_P1026_684_F 6, 19, 9
 #define BB_P1026_684_I 19, 9, 4
 #endif
+// 44.1k -> 48k with its own blocking: transforms of 4116 -> 4480 real points over rubato's 1029 taps, 3087 samples in /
+// 3360 out per block (3/4 of the transform is payload instead of 1/2)
+#ifndef BB_P2058_2240_TH
+#define BB_P2058_2240_TH 640
+#define BB_P2058_2240_F 7, 6, 7, 7
+#define BB_P2058_2240_I 5, 7, 8, 8
+#endif
 #define BB_K2_CT_PLANS(X)                                                                                        \
+    X(p2058_2240, 1029, 1120, BB_P2058_2240_TH, bb::k2w::CtPlan<bb::k2w::RSeq<BB_P2058_2240_F>, bb::k2w::RSeq<BB_P2058_2240_I>, 3087, 3360, true>)  /* 44.1k -> 48k, own blocking */ \
     X(p1029_1120, 1029, 1120, BB_P1029_1120_TH, bb::k2w::CtPlan<bb::k2w::RSeq<BB_P1029_1120_F>, bb::k2w::RSeq<BB_P1029_1120_I>>)  /* 44.1k -> 48k */ \
     X(p1026_684, 1026, 684, BB_P1026_684_TH, bb::k2w::CtPlan<bb::k2w::RSeq<BB_P1026_684_F>, bb::k2w::RSeq<BB_P1026_684_I>>)        /* 48k -> 32k */   \
     X(p1029_2240, 1029, 2240, 384, bb::k2w::CtPlan<bb::k2w::RSeq<7, 7, 7, 3>, bb::k2w::RSeq<7, 5, 8, 8>>)  /* 22.05k -> 48k */ \
@@ -597,7 +668,8 @@ inline bool choose_radices(int n, bool inverse, std::vector<int>* out) {
     return true;
 }
 
-inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const std::vector<int>* fwd, const std::vector<int>* inv);
+inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const std::vector<int>* fwd, const std::vector<int>* inv,
+                                    int adv_in = 0, int adv_out = 0);
 
 inline bool build_plan(int N, int M, int nkeep, RtPlan* P, std::vector<int>* fwd, std::vector<int>* inv) {
     if (M % 2 != 0 || N >= 65536 || M >= 65536) return false;
@@ -605,10 +677,16 @@ inline bool build_plan(int N, int M, int nkeep, RtPlan* P, std::vector<int>* fwd
     return build_plan_from_radices(N, M, nkeep, P, fwd, inv);
 }
 
-inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const std::vector<int>* fwd, const std::vector<int>* inv) {
+inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const std::vector<int>* fwd, const std::vector<int>* inv,
+                                    int adv_in, int adv_out) {
     if (M % 2 != 0 || N >= 65536 || M >= 65536) return false;
     if ((int)fwd->size() > kMaxStages || (int)inv->size() > kMaxStages || inv->empty() || inv->back() % 2) return false;
-    P->N = N; P->M = M; P->nkeep = nkeep; P->half_in = (N + 1) / 2; P->split_len = M / 2 + 1;
+    if (adv_in <= 0) adv_in = N;
+    if (adv_out <= 0) adv_out = M;
+    const int m_last = M / inv->back();
+    if (adv_out % 2 != 0 || (adv_out / 2) % m_last != 0 || adv_in > 2 * N || M - adv_out / 2 > adv_out / 2 || adv_out / 2 > M) return false;
+    P->adv_in = adv_in; P->adv_out = adv_out; P->carry_slots = M - adv_out / 2; P->emit_k = (adv_out / 2) / m_last;
+    P->N = N; P->M = M; P->nkeep = nkeep; P->half_in = (adv_in + 1) / 2; P->split_len = M / 2 + 1;
     P->pad_a = 0; P->pad_b = 0;            // set by the caller: ct_plan_pads / rt_plan_pads
     P->nf = (int)fwd->size(); P->ni = (int)inv->size();
     int span = N, off = 0;
@@ -743,6 +821,9 @@ inline void build_stage_orders(RtPlan* P, int group, bool set_offsets, std::vect
 // 8-byte ones); a group is conflict-free when, for each of the six, its lanes hit distinct residues mod `group`.
 // The order is built greedily group by group and polished by pair swaps (deterministic); a plain stride walk left
 // ~40 % extra wavefronts on 1029/1120, this leaves ~14 %.
+#ifndef BB_SPLIT_POLISH_ITERS_PER_PAIR
+#define BB_SPLIT_POLISH_ITERS_PER_PAIR 100
+#endif
 struct SplitLayout {
     std::vector<uint4> sidx; std::vector<float4> pq1, pq2; std::vector<float2> wi;
     int extra_wavefronts = 0;      // residual conflicts of the chosen order (diagnostic)
@@ -771,11 +852,15 @@ inline void build_split_layout(int N, int M, int nkeep, const uint16_t* pos_f_lo
         if (k != 0 && k2 != k) { e.v[5] = pos_i[k2]; e.flags |= kSplitStore2; }
     }
     const int G = group;
+    // residues of the six positions of every pair (255 = the pair does not make that access)
+    std::vector<unsigned char> res((size_t)L * 6);
+    for (int k = 0; k < L; ++k) for (int a = 0; a < 6; ++a) res[(size_t)k * 6 + a] = it[k].v[a] >= 0 ? (unsigned char)(it[k].v[a] % G) : 255;
     auto group_cost = [&](const int* g, int n) {
         int c = 0;
         for (int a = 0; a < 6; ++a) {
-            int cnt[16] = {0}, mx = 0;
-            for (int i = 0; i < n; ++i) { const int p = it[g[i]].v[a]; if (p >= 0) { const int r = ++cnt[p % G]; mx = r > mx ? r : mx; } }
+            unsigned char cnt[16] = {0};
+            int mx = 0;
+            for (int i = 0; i < n; ++i) { const unsigned r = res[(size_t)g[i] * 6 + a]; if (r != 255) { const int v = ++cnt[r]; mx = v > mx ? v : mx; } }
             if (mx > 1) c += mx - 1;
         }
         return c;
@@ -806,17 +891,36 @@ inline void build_split_layout(int N, int M, int nkeep, const uint16_t* pos_f_lo
     for (int g = 0; g < ng; ++g) { cost[g] = group_cost(&order[(size_t)g * G], gsize(g)); total += cost[g]; }
     uint64_t rng = 0x9E3779B97F4A7C15ull;
     auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); };
-    for (int iter = 0; iter < 150000 && total > 0; ++iter) {
+    // a colliding pair of a conflicting group is offered to every seat of a random other group; the best exchange is
+    // taken when it does not raise the cost (ties keep the walk moving)
+    const int polish_iters = BB_SPLIT_POLISH_ITERS_PER_PAIR * L;
+    for (int iter = 0; iter < polish_iters && total > 0; ++iter) {
         int g1 = (int)(next() % ng);
-        for (int tries = 0; tries < 8 && cost[g1] == 0; ++tries) g1 = (int)(next() % ng);
+        for (int tries = 0; tries < 16 && cost[g1] == 0; ++tries) g1 = (int)(next() % ng);
         if (cost[g1] == 0) continue;
+        const int n1 = gsize(g1);
+        int cand[16], nc = 0;
+        for (int a = 0; a < 6; ++a) {
+            int cnt[16] = {0};
+            for (int i = 0; i < n1; ++i) { const unsigned r = res[(size_t)order[(size_t)g1 * G + i] * 6 + a]; if (r != 255) ++cnt[r]; }
+            for (int i = 0; i < n1 && nc < 16; ++i) { const unsigned r = res[(size_t)order[(size_t)g1 * G + i] * 6 + a]; if (r != 255 && cnt[r] > 1) cand[nc++] = i; }
+        }
+        if (nc == 0) continue;
+        const int i1 = g1 * G + cand[next() % nc];
         const int g2 = (int)(next() % ng);
         if (g1 == g2) continue;
-        const int i1 = g1 * G + (int)(next() % gsize(g1)), i2 = g2 * G + (int)(next() % gsize(g2));
-        std::swap(order[i1], order[i2]);
-        const int c1 = group_cost(&order[(size_t)g1 * G], gsize(g1)), c2 = group_cost(&order[(size_t)g2 * G], gsize(g2));
-        if (c1 + c2 <= cost[g1] + cost[g2]) { total += c1 + c2 - cost[g1] - cost[g2]; cost[g1] = c1; cost[g2] = c2; }
-        else std::swap(order[i1], order[i2]);
+        int best_j = -1, best_c = cost[g1] + cost[g2] + 1, best_c1 = 0, best_c2 = 0;
+        for (int j = 0; j < gsize(g2); ++j) {
+            const int i2 = g2 * G + j;
+            std::swap(order[i1], order[i2]);
+            const int c1 = group_cost(&order[(size_t)g1 * G], n1), c2 = group_cost(&order[(size_t)g2 * G], gsize(g2));
+            std::swap(order[i1], order[i2]);
+            if (c1 + c2 < best_c) { best_c = c1 + c2; best_j = j; best_c1 = c1; best_c2 = c2; }
+        }
+        if (best_j >= 0 && best_c <= cost[g1] + cost[g2]) {
+            std::swap(order[i1], order[g2 * G + best_j]);
+            total += best_c - cost[g1] - cost[g2]; cost[g1] = best_c1; cost[g2] = best_c2;
+        }
     }
     out->extra_wavefronts = total;
     out->sidx.resize(L); out->pq1.resize(L); out->pq2.resize(L); out->wi.resize(L);

@@ -83,7 +83,7 @@ template <class PL, int T> struct Fft2Rest {
     template <class Ex> static __device__ __forceinline__ void run(const Ex& ex, float4* A, const float4* twf) {
         if constexpr (T < PL::Fwd::count) {
             using S = typename PL::template FwdStage<T>;
-            ex.each([&](int l, int n_l) { dif_stage<S::radix, cx2, MapPad8>(A, twf, S{}, l, n_l); });
+            ex.each([&](int l, int n_l) { dif_stage<S::radix, cx2, MapPad8>(A, Tw<cx2, false>{twf}, S{}, l, n_l); });
             Fft2Rest<PL, T + 1>::run(ex, A, twf);
         }
     }
@@ -139,7 +139,7 @@ stft_power2_kernel(const __grid_constant__ StftParams p) {
                 return c;
             };
             using S0 = typename PL::template FwdStage<0>;
-            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2, MapPad8>(A, s_twf, S0{}, N, ld, l, n_l); });
+            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2, MapPad8>(A, Tw<cx2, false>{s_twf}, S0{}, N, ld, l, n_l); });
         } else {
             auto ld = [&](int n) -> cx2 {
                 float v[2][2];
@@ -154,7 +154,7 @@ stft_power2_kernel(const __grid_constant__ StftParams p) {
                 return c;
             };
             using S0 = typename PL::template FwdStage<0>;
-            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2, MapPad8>(A, s_twf, S0{}, N, ld, l, n_l); });
+            ex.each([&](int l, int n_l) { dif_first<S0::radix, cx2, MapPad8>(A, Tw<cx2, false>{s_twf}, S0{}, N, ld, l, n_l); });
         }
         Fft2Rest<PL, 1>::run(ex, A, s_twf);
         float* __restrict__ P0 = p.P + (2 * pi) * (2ull * p.kpad);

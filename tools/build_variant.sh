@@ -16,8 +16,10 @@ for f in capi k1_pack k2_resample k2_warp k3_post k4_dense k5_melspec; do
 done
 g++ -O2 -std=c++17 -fPIC -fno-fast-math -ffp-contract=off -c rules.cpp -o $D/rules.o
 g++ -O2 -std=c++17 -fPIC -c wav.cpp -o $D/wav.o
-g++ -O2 -std=c++17 -fPIC -fno-fast-math -c pipeline.cpp -o $D/pipeline.o
+g++ -O2 -std=c++17 -fPIC -fno-fast-math -pthread -c pipeline.cpp -o $D/pipeline.o
 g++ -O2 -std=c++17 -fPIC -pthread -c pool.cpp -o $D/pool.o
+g++ -O2 -std=c++17 -fPIC -pthread -c watchdog.cpp -o $D/watchdog.o
+g++ -O2 -std=c++17 -fPIC -c mask.cpp -o $D/mask.o
 wait
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $ROOT/birda_b200/variants/libbirda_b200_$1.so $D/*.o -cudart static
 grep "Used" $D/k2_warp.log | tail -1
