@@ -485,12 +485,18 @@ __device__ __forceinline__ void prefetch_pair(const Source& s, float4* A, DualSt
 
 struct DualSink {
     float* p0; float* p1; int lim0, lim1; bool vec0, vec1;
+    bool full;          // both streams take every sample of the block and both rows are 8-byte aligned: plain vector stores
     __device__ __forceinline__ void put(float* p, int lim, bool vec, int o, float a, float b) const {
         if (vec && o + 1 < lim) *reinterpret_cast<float2*>(p + o) = make_float2(a, b);
         else { if (o < lim) p[o] = a; if (o + 1 < lim) p[o + 1] = b; }
     }
     __device__ __forceinline__ void operator()(int n, const cx2& y) const {
         const int o = 2 * n;
+        if (full) {
+            *reinterpret_cast<float2*>(p0 + o) = make_float2(y.re.x, y.im.x);
+            *reinterpret_cast<float2*>(p1 + o) = make_float2(y.re.y, y.im.y);
+            return;
+        }
         put(p0, lim0, vec0, o, y.re.x, y.im.x);
         put(p1, lim1, vec1, o, y.re.y, y.im.y);
     }
@@ -591,6 +597,7 @@ __device__ __forceinline__ void resample_body_dual(const WarpParams& P) {
             sink.p0 = orow[0] + (size_t)b * M; sink.p1 = orow[1] + (size_t)b * M;
             sink.lim0 = active[0] ? l : 0; sink.lim1 = active[1] ? l : 0;
             sink.vec0 = (reinterpret_cast<uintptr_t>(orow[0]) & 7) == 0; sink.vec1 = (reinterpret_cast<uintptr_t>(orow[1]) & 7) == 0;
+            sink.full = sink.vec0 && sink.vec1 && sink.lim0 == M && sink.lim1 == M;
             DualStream n0 = c0, n1 = c1;
             PV::template block<cx2>(ex, PL, T, A, B, carry, ld, sink, [&] {
                 if (b + 1 < b1) {

@@ -77,7 +77,11 @@ def test_c2_full_hour_all_rows_and_tables(ctx):
     assert worst <= 1e-5, (worst, row)
     del cseg
     tail = out[2399].cpu().numpy()
-    assert not tail[72_000 + 2_000:].any() and tail[:70_000].any()   # half-filled last window, zero padded
+    # half-filled last window, zero padded: silence after the filter's tail.  The reference's transforms of all-zero
+    # blocks give exact zeros from 72 000 + 2 240 on; K2's own blocking (4 480-sample transforms) leaves rounding noise
+    # (~1e-9, inside the 1e-5 gate checked above) up to the end of the block that holds the last input sample
+    assert tail[:70_000].any() and not tail[72_000 + 4_480 + 1_120:].any()
+    assert float(np.abs(tail[72_000 + 2_240:]).max()) < 1e-7
     plan.close()
 
 
