@@ -126,6 +126,12 @@ SIGNATURES = {
     "bb_melspec_destroy": (None, [vp]),
     "bb_melspec_info": (C.c_int32, [vp, u32p, u32p, u32p]),
     "bb_melspec_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp]),
+    "bb_standin_create": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(vp)]),
+    "bb_standin_destroy": (None, [vp]),
+    "bb_standin_use_stream": (None, [vp, vp, C.c_int32]),
+    "bb_standin_weights": (C.c_int32, [vp, f32p, f32p]),
+    "bb_standin_launches": (C.c_uint64, [vp]),
+    "bb_standin_classify": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32)]),
     "bb_dev_alloc": (C.c_int32, [vp, C.c_uint64, C.POINTER(vp)]),
     "bb_dev_free": (None, [vp, vp]),
     "bb_memcpy_h2d": (C.c_int32, [vp, vp, vp, C.c_uint64]),

@@ -122,6 +122,54 @@ def mask_build(classifier_labels, geomodel_labels, scores) -> Tuple[np.ndarray, 
     return mask[: len(classifier_labels)], mapped.value, unmatched.value
 
 
+class StandIn:
+    """``bb_standin``: the library's stand-in classifier (NOT a model) — [B, samples] windows -> [B, classes] logits on
+    the device, as a native ``bb_classify_fn`` for NativePipeline / NativePool and the benches.  ``stream``: queue on
+    that CUDA stream asynchronously (a pipeline on its own context); default: own stream, finished on return."""
+
+    def __init__(self, device: int, samples: int, classes: int, max_batch: int, seed: int = 0, stream=None):
+        self.device, self.samples, self.classes, self.max_batch = device, samples, classes, max_batch
+        self.handle = C.c_void_p()
+        check(lib.bb_standin_create(device, samples, classes, max_batch, seed, C.byref(self.handle)))
+        if stream is not None:
+            lib.bb_standin_use_stream(self.handle, C.c_void_p(stream), 1)
+        self.fn = C.cast(lib.bb_standin_classify, _lib.CLASSIFY_FN)
+
+    def weights(self) -> Tuple[np.ndarray, np.ndarray]:
+        W = np.zeros((48, self.classes), np.float32); b = np.zeros(self.classes, np.float32)
+        check(lib.bb_standin_weights(self.handle, W.ctypes.data_as(_lib.f32p), b.ctypes.data_as(_lib.f32p)))
+        return W, b
+
+    @property
+    def launches(self) -> int:
+        return int(lib.bb_standin_launches(self.handle))
+
+    def __call__(self, x):
+        """torch tensor [B, samples] on the device -> torch tensor [B, classes] (a copy; tests)."""
+        import torch
+
+        from .pipeline import _DevView
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.samples
+        torch.cuda.current_stream(x.device).synchronize()
+        ds, nc = C.c_void_p(), C.c_uint32()
+        rc = lib.bb_standin_classify(self.handle, C.c_void_p(x.data_ptr()), x.shape[0], x.shape[1], C.byref(ds), C.byref(nc))
+        if rc != 0:
+            raise BirdaError(-7, f"stand-in classifier failed ({rc})")
+        torch.cuda.synchronize(x.device)
+        return torch.as_tensor(_DevView(ds.value, (x.shape[0], nc.value)), device=x.device).clone()
+
+    def close(self):
+        if self.handle:
+            lib.bb_standin_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Watchdog:
     """``bb_watchdog``: fires ``on_fire(timeout_secs, batch_size)`` unless cancelled within ``timeout_ms``
     (src/gpu/watchdog.rs:22-66).  ``on_fire=None`` is the reference's behaviour: message + exit(1)."""
@@ -188,6 +236,11 @@ class Context:
     @property
     def handle(self):
         return self._h
+
+    @property
+    def stream(self) -> int:
+        """The context's cudaStream_t as an integer (``bb_ctx_stream``)."""
+        return int(lib.bb_ctx_stream(self._h) or 0)
 
     def sync(self):
         check(lib.bb_sync(self._h), self._h)

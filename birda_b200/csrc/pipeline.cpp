@@ -11,11 +11,15 @@
 #include "rules.hpp"
 #include "guard.hpp"
 #include "watchdog.hpp"
+#include "pipeline_internal.hpp"
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 
@@ -38,7 +42,11 @@ struct bb_pipeline {
     bb_batch_hook before_batch = nullptr, after_batch = nullptr; void* hook_user = nullptr;
     uint64_t batch_timeout_ms = 0; bb_watchdog_fn on_timeout = nullptr; void* timeout_user = nullptr;
     std::unique_ptr<bb::Watchdog> watchdog;
-    void* pinned = nullptr; uint64_t pinned_bytes = 0;
+    // two pinned staging buffers: a reader thread fills one with piece k+1 while the GPU works on piece k
+    void* pinned[2] = {nullptr, nullptr}; uint64_t pinned_bytes[2] = {0, 0};
+    // post-step results of one piece stay on the device and come back in ONE copy per piece (bb_post_run_device per
+    // batch); with batch hooks or a watchdog set every batch is synchronous instead, as in the reference
+    uint32_t* d_index = nullptr; float* d_conf = nullptr; uint32_t* d_count = nullptr; uint64_t d_res_rows = 0; uint32_t d_res_k = 0;
     std::vector<uint32_t> h_index; std::vector<float> h_conf; std::vector<uint32_t> h_count;
     std::vector<float> st, et; std::vector<uint64_t> ss;
     std::string error;
@@ -77,7 +85,38 @@ int ensure_plan(bb_pipeline* p, uint32_t rate, uint32_t channels, int fmt) {
     return BB_OK;
 }
 
-struct Sink { bb_detection* out; uint64_t cap; uint64_t n; bool overflow; };
+// detections go to the caller's array (count beyond its capacity: BB_ERR_CAPACITY) or to a growing vector (bb_pool)
+struct Sink {
+    bb_detection* out; uint64_t cap; uint64_t n; bool overflow; std::vector<bb_detection>* grow;
+    void push(uint32_t segment, uint32_t index, float conf, float st, float et) {
+        bb_detection d{}; d.segment = segment; d.index = index; d.confidence = conf; d.start_time = st; d.end_time = et;
+        if (grow) grow->push_back(d);
+        else if (n < cap) out[n] = d;
+        else overflow = true;
+        ++n;
+    }
+};
+
+void free_results(bb_pipeline* p) {
+    if (p->d_index) bb_dev_free(p->ctx, p->d_index);
+    if (p->d_conf) bb_dev_free(p->ctx, p->d_conf);
+    if (p->d_count) bb_dev_free(p->ctx, p->d_count);
+    p->d_index = nullptr; p->d_conf = nullptr; p->d_count = nullptr; p->d_res_rows = 0; p->d_res_k = 0;
+}
+int ensure_results(bb_pipeline* p, uint64_t rows, uint32_t K) {
+    if (p->d_res_rows >= rows && p->d_res_k == K) return BB_OK;
+    if (bb_sync(p->ctx) != BB_OK) return BB_ERR_CUDA;
+    free_results(p);
+    void* a = nullptr; void* b = nullptr; void* c = nullptr;
+    if (bb_dev_alloc(p->ctx, rows * K * 4, &a) != BB_OK || bb_dev_alloc(p->ctx, rows * K * 4, &b) != BB_OK ||
+        bb_dev_alloc(p->ctx, rows * 4, &c) != BB_OK) {
+        for (void* q : {a, b, c}) if (q) bb_dev_free(p->ctx, q);
+        return BB_ERR_OOM;
+    }
+    p->d_index = static_cast<uint32_t*>(a); p->d_conf = static_cast<float*>(b); p->d_count = static_cast<uint32_t*>(c);
+    p->d_res_rows = rows; p->d_res_k = K;
+    return BB_OK;
+}
 
 // one piece of PCM already in host memory -> detections appended to the sink
 int run_piece(bb_pipeline* p, const void* pcm, uint64_t frames, uint64_t first_start, bool eof, uint32_t B,
@@ -96,38 +135,61 @@ int run_piece(bb_pipeline* p, const void* pcm, uint64_t frames, uint64_t first_s
     bb_rule_segment_samples(p->cfg.segment_duration, p->cfg.overlap, p->cfg.bat_mode ? p->plan_rate : p->cfg.target_rate,
                             p->cfg.bat_mode, &seg_samples, &dummy);
     const uint32_t K = p->cfg.post.top_k;
-    p->h_index.resize((size_t)B * K); p->h_conf.resize((size_t)B * K); p->h_count.resize(B);
+    // processor.rs:363-385: second threshold test (matters after rerank), one Detection per surviving prediction
+    auto extract = [&](uint64_t first, uint32_t valid, const uint32_t* idx, const float* conf, const uint32_t* cnt) {
+        for (uint32_t r = 0; r < valid; ++r)
+            for (uint32_t j = 0; j < cnt[r] && j < K; ++j) {
+                const float c = conf[(size_t)r * K + j];
+                if (!(c >= p->cfg.post.min_confidence)) continue;
+                sink->push((uint32_t)(seg_base + first + r), idx[(size_t)r * K + j], c, p->st[first + r], p->et[first + r]);
+            }
+    };
+    const bool per_batch_sync = p->before_batch || p->after_batch || p->watchdog;
+    if (per_batch_sync) {
+        p->h_index.resize((size_t)B * K); p->h_conf.resize((size_t)B * K); p->h_count.resize(B);
+        for (uint64_t first = 0; first < nseg; first += B) {
+            const uint32_t valid = (uint32_t)std::min<uint64_t>(B, nseg - first);
+            const float* d_scores = nullptr; uint32_t classes = 0;
+            if (p->sync_before_classify && bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));
+            // the watchdog brackets the batch exactly as processor.rs:263-277 does: armed before the classifier is called,
+            // dropped once its results are on the host (bb_post_run synchronises the stream)
+            if (p->before_batch) p->before_batch(p->hook_user, B, valid, seg_base + first);
+            if (p->watchdog) p->watchdog->arm(p->batch_timeout_ms, B);
+            rc = p->classify(p->user, d_seg + first * seg_samples, B, (uint32_t)seg_samples, &d_scores, &classes);
+            int prc = BB_OK;
+            if (rc == 0 && d_scores && classes)
+                prc = bb_post_run(p->ctx, d_scores, B, classes, valid, &p->cfg.post, p->cfg.d_mask, p->cfg.d_species_keep,
+                                  p->h_index.data(), p->h_conf.data(), p->h_count.data());
+            const bool fired = p->watchdog ? p->watchdog->disarm() : false;
+            if (p->after_batch) p->after_batch(p->hook_user, B, valid, seg_base + first);
+            if (fired) return fail(p, BB_ERR_TIMEOUT, "inference batch of " + std::to_string(B) + " outlived the watchdog (" +
+                                                      std::to_string(p->batch_timeout_ms) + " ms)");
+            if (rc != 0 || !d_scores || classes == 0) return fail(p, BB_ERR_INTERNAL, "classifier callback failed");   // Error::Inference
+            if (prc != BB_OK) return fail(p, prc, bb_last_error(p->ctx));
+            extract(first, valid, p->h_index.data(), p->h_conf.data(), p->h_count.data());
+        }
+        return BB_OK;
+    }
+    // no per-batch seam in use: every batch's classifier call and post kernel are queued back to back, the piece's
+    // results come back in one copy and one synchronisation
+    if (nseg == 0) return BB_OK;
+    if (ensure_results(p, cap, K) != BB_OK) return fail(p, BB_ERR_OOM, "device allocation for the post-step results failed");
     for (uint64_t first = 0; first < nseg; first += B) {
         const uint32_t valid = (uint32_t)std::min<uint64_t>(B, nseg - first);
         const float* d_scores = nullptr; uint32_t classes = 0;
         if (p->sync_before_classify && bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));
-        // the watchdog brackets the batch exactly as processor.rs:263-277 does: armed before the classifier is called,
-        // dropped once its results are on the host (bb_post_run synchronises the stream)
-        if (p->before_batch) p->before_batch(p->hook_user, B, valid, seg_base + first);
-        if (p->watchdog) p->watchdog->arm(p->batch_timeout_ms, B);
         rc = p->classify(p->user, d_seg + first * seg_samples, B, (uint32_t)seg_samples, &d_scores, &classes);
-        int prc = BB_OK;
-        if (rc == 0 && d_scores && classes)
-            prc = bb_post_run(p->ctx, d_scores, B, classes, valid, &p->cfg.post, p->cfg.d_mask, p->cfg.d_species_keep,
-                              p->h_index.data(), p->h_conf.data(), p->h_count.data());
-        const bool fired = p->watchdog ? p->watchdog->disarm() : false;
-        if (p->after_batch) p->after_batch(p->hook_user, B, valid, seg_base + first);
-        if (fired) return fail(p, BB_ERR_TIMEOUT, "inference batch of " + std::to_string(B) + " outlived the watchdog (" +
-                                                  std::to_string(p->batch_timeout_ms) + " ms)");
-        if (rc != 0 || !d_scores || classes == 0) return fail(p, BB_ERR_INTERNAL, "classifier callback failed");   // Error::Inference
-        if (prc != BB_OK) return fail(p, prc, bb_last_error(p->ctx));
-        for (uint32_t r = 0; r < valid; ++r)                                       // processor.rs:363-385
-            for (uint32_t j = 0; j < p->h_count[r]; ++j) {
-                const float c = p->h_conf[(size_t)r * K + j];
-                if (!(c >= p->cfg.post.min_confidence)) continue;
-                if (sink->n < sink->cap) {
-                    bb_detection& d = sink->out[sink->n];
-                    d.segment = (uint32_t)(seg_base + first + r); d.index = p->h_index[(size_t)r * K + j]; d.confidence = c;
-                    d.start_time = p->st[first + r]; d.end_time = p->et[first + r];
-                } else sink->overflow = true;
-                ++sink->n;
-            }
+        if (rc != 0 || !d_scores || classes == 0) return fail(p, BB_ERR_INTERNAL, "classifier callback failed");       // Error::Inference
+        rc = bb_post_run_device(p->ctx, d_scores, B, classes, valid, &p->cfg.post, p->cfg.d_mask, p->cfg.d_species_keep,
+                                p->d_index + first * K, p->d_conf + first * K, p->d_count + first);
+        if (rc != BB_OK) return fail(p, rc, bb_last_error(p->ctx));
     }
+    p->h_index.resize((size_t)nseg * K); p->h_conf.resize((size_t)nseg * K); p->h_count.resize(nseg);
+    if (bb_memcpy_d2h(p->ctx, p->h_index.data(), p->d_index, nseg * K * 4) != BB_OK ||
+        bb_memcpy_d2h(p->ctx, p->h_conf.data(), p->d_conf, nseg * K * 4) != BB_OK ||
+        bb_memcpy_d2h(p->ctx, p->h_count.data(), p->d_count, nseg * 4) != BB_OK || bb_sync(p->ctx) != BB_OK)
+        return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));
+    extract(0, (uint32_t)nseg, p->h_index.data(), p->h_conf.data(), p->h_count.data());
     return BB_OK;
 }
 
@@ -146,7 +208,109 @@ uint32_t effective_batch(const bb_pipeline* p, uint64_t frames, uint32_t rate) {
     return B ? B : 1;
 }
 
+int ensure_pinned(bb_pipeline* p, int slot, uint64_t bytes) {
+    if (p->pinned_bytes[slot] >= bytes) return BB_OK;
+    if (p->pinned[slot]) bb_host_free(p->pinned[slot]);
+    p->pinned[slot] = nullptr; p->pinned_bytes[slot] = 0;
+    if (bb_host_alloc(bytes > 0 ? bytes : 1, &p->pinned[slot]) != BB_OK) return BB_ERR_OOM;
+    p->pinned_bytes[slot] = bytes;
+    return BB_OK;
+}
+
+// A WAV file through the pipeline in pieces of ~256 MB of PCM.  Pieces are cut so that every piece but the last holds a
+// whole number of batches (only the file's LAST batch is padded, processor.rs:132-170).  A file of several pieces is
+// read by a second thread into the other pinned buffer while the GPU works on the current piece (the reference's decode
+// thread, processor.rs:20-47).  run_piece ends with the stream synchronised, so a buffer is free again two pieces later.
+int process_wav(bb_pipeline* p, const char* path, uint64_t piece_frames, Sink* sink, uint64_t* n_segments, uint32_t* batch_used) {
+    bb_wav_info info;
+    int rc = bb_wav_probe(path, &info);
+    if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
+    rc = ensure_plan(p, info.sample_rate, info.channels, info.fmt);
+    if (rc != BB_OK) return rc;
+    const uint32_t B = effective_batch(p, info.frames, info.sample_rate);
+    if (batch_used) *batch_used = B;
+    const uint64_t fb = (uint64_t)info.channels * bb::sample_bytes(info.fmt);
+    uint64_t src_seg = 0, src_ovl = 0;
+    bb_plan_source_window(p->plan, &src_seg, &src_ovl);
+    if (piece_frames == 0) piece_frames = (256ull << 20) / fb;
+    if (piece_frames < 2 * src_seg) piece_frames = 2 * src_seg;
+    const uint64_t hop = src_seg - src_ovl;
+    // the piece table is a pure function of the header: (first frame, frames, last piece)
+    struct Piece { uint64_t pos, frames; bool eof; };
+    std::vector<Piece> pieces;
+    for (uint64_t pos = 0;;) {
+        uint64_t want = std::min<uint64_t>(piece_frames, info.frames - pos);
+        bool eof = pos + want >= info.frames;
+        if (!eof) {                                                                // trim to k*B full windows
+            uint64_t nfull = want >= src_seg ? (want - src_seg) / hop + 1 : 0;
+            nfull = nfull / B * B;
+            if (nfull == 0) { want = std::min<uint64_t>(info.frames - pos, src_seg + (uint64_t)(B - 1) * hop); eof = pos + want >= info.frames; }
+            else want = (nfull - 1) * hop + src_seg;
+        }
+        pieces.push_back({pos, want, eof});
+        if (eof) break;
+        const uint64_t nwin = (want - src_seg) / hop + 1;                         // windows of a non-final piece: all full
+        pos += nwin * hop;
+    }
+    uint64_t max_bytes = 0;
+    for (const Piece& pc : pieces) max_bytes = std::max(max_bytes, pc.frames * fb);
+    const int nbuf = pieces.size() > 1 ? 2 : 1;
+    if (bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));   // earlier H2D copies out of the staging buffers are done
+    for (int b = 0; b < nbuf; ++b) if (ensure_pinned(p, b, max_bytes) != BB_OK) return fail(p, BB_ERR_OOM, "pinned staging allocation failed");
+
+    // reader: piece k goes to buffer k % nbuf once piece k - nbuf has been consumed
+    std::mutex mu; std::condition_variable cv;
+    size_t read_done = 0, consumed_n = 0, fail_at = ~(size_t)0; int read_rc = BB_OK; bool stop = false; std::string read_err;
+    auto read_piece = [&](size_t k) { return bb_wav_read(path, &info, pieces[k].pos, pieces[k].frames, p->pinned[k % nbuf]); };
+    std::thread reader;
+    if (nbuf == 2)
+        reader = std::thread([&] {
+            for (size_t k = 0; k < pieces.size(); ++k) {
+                { std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return stop || k < consumed_n + 2; }); if (stop) return; }
+                const int r = read_piece(k);
+                { std::lock_guard<std::mutex> l(mu); if (r != BB_OK) { read_rc = r; fail_at = k; read_err = bb_last_error(nullptr); } read_done = k + 1; }
+                cv.notify_all();
+                if (r != BB_OK) return;
+            }
+        });
+    struct Joiner { std::thread& t; std::mutex& mu; std::condition_variable& cv; bool& stop;
+                    ~Joiner() { if (t.joinable()) { { std::lock_guard<std::mutex> l(mu); stop = true; } cv.notify_all(); t.join(); } } } joiner{reader, mu, cv, stop};
+
+    uint64_t seg_base = 0;
+    for (size_t k = 0; k < pieces.size(); ++k) {
+        if (nbuf == 2) {
+            std::unique_lock<std::mutex> l(mu);
+            cv.wait(l, [&] { return read_done > k; });
+            if (fail_at == k) return fail(p, read_rc, read_err);
+        } else {
+            rc = read_piece(k);
+            if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
+        }
+        uint64_t nseg = 0, consumed = 0;
+        rc = run_piece(p, p->pinned[k % nbuf], pieces[k].frames, pieces[k].pos, pieces[k].eof, B, seg_base, sink, &nseg, &consumed);
+        if (rc != BB_OK) return rc;
+        seg_base += nseg;
+        if (!pieces[k].eof && pieces[k].pos + consumed != pieces[k + 1].pos) return fail(p, BB_ERR_INTERNAL, "piece table and front end disagree");
+        if (nbuf == 2) { { std::lock_guard<std::mutex> l(mu); consumed_n = k + 1; } cv.notify_all(); }
+    }
+    if (n_segments) *n_segments = seg_base;
+    return BB_OK;
+}
+
 }  // namespace
+
+namespace bb {
+int32_t pipeline_process_wav_into(bb_pipeline* p, const char* path, uint64_t piece_frames, std::vector<bb_detection>* out,
+                                  uint64_t* n_segments, uint32_t* batch_used) {
+    if (!p || !path || !out) return fail(p, BB_ERR_INVALID_ARG, "bad argument");
+    out->clear();
+    Sink sink{nullptr, 0, 0, false, out};
+    const int rc = process_wav(p, path, piece_frames, &sink, n_segments, batch_used);
+    if (rc != BB_OK) return rc;
+    sort_detections(out->data(), out->size());
+    return BB_OK;
+}
+}  // namespace bb
 
 extern "C" {
 
@@ -166,7 +330,8 @@ int32_t bb_pipeline_create(bb_ctx* ctx, const bb_pipeline_cfg* cfg, bb_classify_
 void bb_pipeline_destroy(bb_pipeline* p) {
     if (!p) return;
     for (auto& c : p->cache) bb_plan_destroy(c.plan);
-    if (p->pinned) bb_host_free(p->pinned);
+    for (void* b : p->pinned) if (b) bb_host_free(b);
+    free_results(p);
     delete p;
 }
 
@@ -197,7 +362,7 @@ int32_t bb_pipeline_process_pcm(bb_pipeline* p, const void* pcm, uint64_t frames
     if (rc != BB_OK) return rc;
     const uint32_t B = effective_batch(p, frames, src_rate);
     if (batch_used) *batch_used = B;
-    Sink sink{out, out ? capacity : 0, 0, false};
+    Sink sink{out, out ? capacity : 0, 0, false, nullptr};
     uint64_t nseg = 0, consumed = 0;
     rc = run_piece(p, pcm, frames, 0, true, B, 0, &sink, &nseg, &consumed);
     if (rc != BB_OK) return rc;
@@ -213,50 +378,9 @@ int32_t bb_pipeline_process_wav(bb_pipeline* p, const char* path, uint64_t piece
                                 uint64_t* n_detections, uint64_t* n_segments, uint32_t* batch_used) {
     BB_TRY
     if (!p || !path) return fail(p, BB_ERR_INVALID_ARG, "bad argument");
-    bb_wav_info info;
-    int rc = bb_wav_probe(path, &info);
-    if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
-    rc = ensure_plan(p, info.sample_rate, info.channels, info.fmt);
+    Sink sink{out, out ? capacity : 0, 0, false, nullptr};
+    int rc = process_wav(p, path, piece_frames, &sink, n_segments, batch_used);
     if (rc != BB_OK) return rc;
-    const uint32_t B = effective_batch(p, info.frames, info.sample_rate);
-    if (batch_used) *batch_used = B;
-    const uint64_t fb = (uint64_t)info.channels * bb::sample_bytes(info.fmt);
-    uint64_t src_seg = 0, src_ovl = 0;
-    bb_plan_source_window(p->plan, &src_seg, &src_ovl);
-    if (piece_frames == 0) piece_frames = (256ull << 20) / fb;                     // ~256 MB of PCM per piece
-    if (piece_frames < 2 * src_seg) piece_frames = 2 * src_seg;
-    // keep the number of windows per non-final piece a multiple of the batch so only the file's LAST batch is padded
-    const uint64_t hop = src_seg - src_ovl;
-    Sink sink{out, out ? capacity : 0, 0, false};
-    uint64_t pos = 0, seg_base = 0;
-    while (true) {
-        uint64_t want = std::min<uint64_t>(piece_frames, info.frames - pos);
-        bool eof = pos + want >= info.frames;
-        if (!eof) {                                                                // trim to k*B full windows
-            uint64_t nfull = want >= src_seg ? (want - src_seg) / hop + 1 : 0;
-            nfull = nfull / B * B;
-            if (nfull == 0) { want = std::min<uint64_t>(info.frames - pos, src_seg + (uint64_t)(B - 1) * hop); eof = pos + want >= info.frames; }
-            else want = (nfull - 1) * hop + src_seg;
-        }
-        if (p->pinned_bytes < want * fb) {
-            if (bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));
-            if (p->pinned) bb_host_free(p->pinned);
-            p->pinned = nullptr; p->pinned_bytes = 0;
-            if (bb_host_alloc(want * fb > 0 ? want * fb : 1, &p->pinned) != BB_OK) return fail(p, BB_ERR_OOM, "pinned staging allocation failed");
-            p->pinned_bytes = want * fb;
-        }
-        if (bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));   // previous piece's H2D copies are done
-        rc = bb_wav_read(path, &info, pos, want, p->pinned);
-        if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
-        uint64_t nseg = 0, consumed = 0;
-        rc = run_piece(p, p->pinned, want, pos, eof, B, seg_base, &sink, &nseg, &consumed);
-        if (rc != BB_OK) return rc;
-        seg_base += nseg;
-        if (eof) break;
-        if (consumed == 0) return fail(p, BB_ERR_INTERNAL, "streaming made no progress");
-        pos += consumed;
-    }
-    if (n_segments) *n_segments = seg_base;
     if (n_detections) *n_detections = sink.n;
     if (sink.overflow) return fail(p, BB_ERR_CAPACITY, "detection capacity too small (" + std::to_string(sink.n) + " needed)");
     sort_detections(out, sink.n);

@@ -12,6 +12,7 @@
 #include <vector>
 #include "rules.hpp"
 #include "guard.hpp"
+#include "pipeline_internal.hpp"
 #include "../../include/birda_b200.h"
 
 
@@ -77,25 +78,24 @@ int32_t bb_pool_process_wavs(bb_pool* p, const char* const* paths, uint32_t n_fi
     std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
     std::atomic<uint32_t> next{0};
     auto work = [&](bb_pool::Worker& w) {
-        std::vector<bb_detection> buf(4096);
+        std::vector<bb_detection> buf;
         for (;;) {
             const uint32_t k = next.fetch_add(1);
             if (k >= n_files) break;
             const uint32_t f = order[k].second;
             bb_pool_result& r = results[f];
             r.device = w.device;
-            uint64_t nd = 0, ns = 0; uint32_t bu = 0;
-            int rc = bb_pipeline_process_wav(w.pipe, paths[f], 0, buf.data(), buf.size(), &nd, &ns, &bu);
-            if (rc == BB_ERR_CAPACITY) {                              // needed count reported: retry once with room
-                buf.resize(nd);
-                rc = bb_pipeline_process_wav(w.pipe, paths[f], 0, buf.data(), buf.size(), &nd, &ns, &bu);
-            }
+            uint64_t ns = 0; uint32_t bu = 0;
+            int rc;
+            try { rc = bb::pipeline_process_wav_into(w.pipe, paths[f], 0, &buf, &ns, &bu); }      // the list grows as needed: one pass per file
+            catch (...) { rc = bb::translate_exception("bb_pool worker", nullptr); }
             r.status = rc; r.n_segments = ns; r.batch_used = bu;
             if (rc != BB_OK) {
-                const char* m = bb_pipeline_last_error(w.pipe);
+                const char* m = rc == BB_ERR_OOM || !*bb_pipeline_last_error(w.pipe) ? bb_last_error(nullptr) : bb_pipeline_last_error(w.pipe);
                 std::strncpy(r.error, m ? m : "", sizeof(r.error) - 1);
                 continue;
             }
+            const uint64_t nd = buf.size();
             r.detections = new (std::nothrow) bb_detection[nd ? nd : 1];
             if (!r.detections) { r.status = BB_ERR_OOM; continue; }
             std::memcpy(r.detections, buf.data(), nd * sizeof(bb_detection));

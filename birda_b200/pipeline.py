@@ -173,12 +173,15 @@ class NativePipeline:
                 self._error = e
                 return 1
 
-        self._cb = _lib.CLASSIFY_FN(_cb)
+        from .api import StandIn
+        native = isinstance(classifier, StandIn)           # a bb_classify_fn of the library: no Python in the loop
+        self._cb = classifier.fn if native else _lib.CLASSIFY_FN(_cb)
         c = _lib.PipelineCfg(cfg.target_rate, cfg.segment_duration, cfg.overlap, cfg.batch_size, int(cfg.bat_mode),
                              PostConfig(cfg.activation, cfg.min_confidence, cfg.top_k, cfg.range_threshold,
                                         cfg.keep_unmatched, cfg.rerank).to_c(), cfg.d_mask, cfg.d_species_keep)
         self._h = C.c_void_p()
-        _lib.check(_lib.lib.bb_pipeline_create(ctx.handle, C.byref(c), self._cb, None, C.byref(self._h)), ctx.handle)
+        _lib.check(_lib.lib.bb_pipeline_create(ctx.handle, C.byref(c), self._cb, classifier.handle if native else None,
+                                               C.byref(self._h)), ctx.handle)
 
     def _collect(self, call) -> ProcessResult:
         import ctypes as C
@@ -283,13 +286,15 @@ class NativePool:
                 self._errors.append(e)
                 return 1
 
-        self._cb = _lib.CLASSIFY_FN(_cb)
+        from .api import StandIn
+        native = all(isinstance(c, StandIn) for c in classifiers)      # bb_classify_fn of the library: no Python in the loop
+        self._cb = classifiers[0].fn if native else _lib.CLASSIFY_FN(_cb)
         n = len(devices)
         c_cfgs = (_lib.PipelineCfg * n)(*[
             _lib.PipelineCfg(c.target_rate, c.segment_duration, c.overlap, c.batch_size, int(c.bat_mode),
                              PostConfig(c.activation, c.min_confidence, c.top_k, c.range_threshold, c.keep_unmatched, c.rerank).to_c(),
                              c.d_mask, c.d_species_keep) for c in cfgs])
-        users = (C.c_void_p * n)(*[C.c_void_p(i + 1) for i in range(n)])
+        users = (C.c_void_p * n)(*[(classifiers[i].handle if native else C.c_void_p(i + 1)) for i in range(n)])
         devs = (C.c_int32 * n)(*devices)
         self._h = C.c_void_p()
         _lib.check(_lib.lib.bb_pool_create(devs, n, c_cfgs, self._cb, users, C.byref(self._h)))

@@ -383,6 +383,23 @@ int32_t bb_melspec_info(const bb_melspec*, uint32_t* bin_lo, uint32_t* n_bins, u
  * Asynchronous on the ctx stream. */
 int32_t bb_melspec_run(bb_melspec*, const float* d_segments, uint32_t rows, uint32_t samples, float* d_out);
 
+/* ------------------------------------------------------------------------------------------
+ * Stand-in classifier (benches and tests; NOT a model, nothing of the reference's is replaced by it): the I/O contract
+ * of BirdClassifier::predict_batch (src/inference/classifier.rs:469-582) — [batch, samples] f32 windows on the device
+ * in, [batch, classes] f32 logits on the device out — with trivial arithmetic (48 band energies times a fixed
+ * pseudo-random matrix).  bb_standin_classify is a bb_classify_fn whose `user` is the bb_standin*.  By default it runs
+ * on a stream of its own and finishes before it returns (what bb_pool requires); after bb_standin_use_stream(s, stream,
+ * 1) it queues its two kernels on that stream and returns at once (a pipeline on its own context: bb_ctx_stream).
+ * The logits stay valid until the next call.  bb_standin_weights copies out W [48, classes] and bias [classes].
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bb_standin bb_standin;
+int32_t  bb_standin_create(int32_t device, uint32_t samples, uint32_t classes, uint32_t max_batch, uint64_t seed, bb_standin** out);
+void     bb_standin_destroy(bb_standin*);
+void     bb_standin_use_stream(bb_standin*, void* cuda_stream, int32_t on);
+int32_t  bb_standin_weights(const bb_standin*, float* W, float* bias);
+uint64_t bb_standin_launches(const bb_standin*);
+int32_t  bb_standin_classify(void* user, const float* d_segments, uint32_t batch, uint32_t samples, const float** d_scores, uint32_t* classes);
+
 /* Debug hook (tests): the n-th guarded entry point called on this thread from now on fails as if a host
  * allocation had thrown (n = 1: the next one; 0 disarms).  Proves that exceptions stop at the boundary. */
 void bb_debug_inject_alloc_failure(int32_t nth);

@@ -244,3 +244,64 @@ def test_native_pipeline_batch_timeout_fails_the_file():
     nat.set_batch_timeout(0)
     assert nat.process_pcm(pcm, 1, 48_000, b.FMT_S16).segments == 5
     nat.close(); ctx.close()
+
+
+def test_standin_classifier_matches_its_formula():
+    """bb_standin (the library's stand-in classifier, NOT a model): logits = log10(mean square of 48 frames + 1e-6) @ W + b."""
+    import torch
+    st = b.StandIn(0, 144_000, 6522, 16, seed=5)
+    W, bias = st.weights()
+    x = torch.from_numpy(synth_pcm(50, 3.0 * 7, 48_000, 1).astype(np.float32).reshape(7, 144_000) / 32768.0).cuda().contiguous()
+    got = st(x).cpu().numpy()
+    xs = x.cpu().numpy().astype(np.float64).reshape(7, 48, 3000)
+    feat = np.log10((xs ** 2).mean(axis=2) + 1e-6)
+    want = feat @ W.astype(np.float64) + bias
+    assert got.shape == (7, 6522) and np.abs(got - want).max() < 2e-4
+    assert st.launches == 2
+    frac = float((1 / (1 + np.exp(-want)) >= 0.1).mean())
+    assert 1e-4 < frac < 0.05                                   # a few classes per window clear the usual threshold
+    st.close()
+
+
+def test_native_callback_multi_piece_file_and_pool(tmp_path):
+    """The library's own bb_classify_fn (no Python in the loop): a WAV streamed in several pieces (reader thread + two
+    pinned buffers, one result copy per piece) gives the same detections as the whole file in one piece and as the
+    Python-callback pipeline; two pool workers on the same files agree too."""
+    import torch
+    from birda_b200.pipeline import NativePipeline, NativePool
+    from tests.test_wav_ingest import write_wav
+    C = 6522
+    cfg = ProcessingConfig(target_rate=48_000, segment_duration=3.0, overlap=1.5, batch_size=8, min_confidence=0.1)
+    pcm = synth_pcm(51, 95.0, 44_100, 2)
+    p = str(tmp_path / "long.wav"); write_wav(p, pcm, 44_100, 2)
+    ctx = b.Context(0)
+    st = b.StandIn(0, 144_000, C, 8, seed=9, stream=ctx.stream)
+    nat = NativePipeline(ctx, cfg, st)
+    key = lambda r: [(d.segment, d.index, round(d.confidence, 6), d.start_time, d.end_time) for d in r.detections]
+    whole = nat.process_wav(p)
+    pieces = nat.process_wav(p, piece_frames=44_100 * 11)        # 9 pieces
+    assert whole.segments == pieces.segments == 64 and key(whole) == key(pieces) and len(whole.detections) > 20
+    frompcm = nat.process_pcm(pcm, 2, 44_100, b.FMT_S16)
+    assert key(frompcm) == key(whole)
+    # the same classifier behind the Python trampoline
+    st2 = b.StandIn(0, 144_000, C, 8, seed=9)
+    py = NativePipeline(ctx, cfg, lambda x: st2(x))
+    assert key(py.process_wav(p, piece_frames=44_100 * 17)) == key(whole)
+    # hooks force the per-batch synchronous path: same detections
+    nat.set_batch_hooks(lambda *a: None, lambda *a: None)
+    assert key(nat.process_wav(p, piece_frames=44_100 * 11)) == key(whole)
+    nat.close(); py.close(); ctx.close()
+    # pool: two workers, native callbacks
+    paths = [p]
+    for i, (sr, ch, sec) in enumerate([(48_000, 1, 20.0), (22_050, 1, 41.0), (32_000, 2, 15.0)]):
+        q = str(tmp_path / f"g{i}.wav"); write_wav(q, synth_pcm(60 + i, sec, sr, ch), sr, ch); paths.append(q)
+    sts = [b.StandIn(0, 144_000, C, 8, seed=9) for _ in range(2)]
+    pool = NativePool([0, 0], [cfg, cfg], sts)
+    got = pool.process_wavs(paths)
+    pool.close()
+    assert key(got[0]) == key(whole) and all(g.segments > 0 for g in got)
+    ctx = b.Context(0)
+    one = NativePipeline(ctx, cfg, b.StandIn(0, 144_000, C, 8, seed=9, stream=ctx.stream))
+    for q, g in zip(paths[1:], got[1:]):
+        assert key(one.process_wav(q)) == key(g), q
+    one.close(); ctx.close()
