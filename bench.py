@@ -38,25 +38,18 @@ ALGO_BYTES_FRONT = SECONDS * SRC_RATE * CHANNELS * 2 + 2400 * SEG * 4          #
 ALGO_FLOPS_FRONT = 118_955 * 129 * 2400                                      # 36.8 GFLOP
 
 
-def k2_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch over the bench workload, from the committed
-    ncu --set full capture (profiles/k2_traffic.json); None when no capture exists."""
+def k2_profile(kernel: str):
+    """Numbers that only a profiler can give (DRAM bytes per launch, shared-memory pipe share) for the dominant kernel,
+    from the committed ncu --set full capture (profiles/k2_traffic.json, written by tools/collect_profiles.py).  They are
+    quoted only when that capture names the kernel this run launched (bb_plan_describe); otherwise None + the reason."""
     p = os.path.join(ROOT, "profiles", "k2_traffic.json")
     try:
-        return int(json.load(open(p))["dram_bytes_per_launch"])
+        j = json.load(open(p))
     except Exception:
-        return None
-
-
-def k2_smem_pipe_pct():
-    """Shared-memory pipe utilisation of the dominant kernel from the committed ncu summary (what actually binds K2)."""
-    import re
-    try:
-        txt = open(os.path.join(ROOT, "profiles", "r01_final_k2_c2_1h.txt")).read()
-        m = re.search(r"l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum\.pct_of_peak_sustained_elapsed\s+([0-9.]+)", txt)
-        return float(m.group(1)) if m else None
-    except Exception:
-        return None
+        return None, None, "no committed capture"
+    if j.get("kernel") != kernel:
+        return None, None, f"committed capture is of another kernel ({j.get('kernel')})"
+    return int(j["dram_bytes_per_launch"]), j.get("smem_pipe_pct"), j.get("source")
 
 
 def measured_peaks():
@@ -158,7 +151,7 @@ def _cpu_worker(args):
     mask = (rng.random(CLASSES) ** 2).astype(np.float32)
     mask[rng.choice(CLASSES, 305, replace=False)] = np.nan
     t0 = time.perf_counter()
-    r = ofe.decode_and_stream(pcm, CHANNELS, SRC_RATE, TGT_RATE, SEG, OVL)
+    r = ofe.decode_and_stream(pcm, CHANNELS, SRC_RATE, TGT_RATE, SEG, OVL, batched=True)   # all blocks of a window in one pocketfft call
     n = r.segments.shape[0]
     cport.post(x[:n], min(n, nseg), 1, 0.1, 5, mask, None, 0.01, True, False, threads=1)
     dt = time.perf_counter() - t0
@@ -179,12 +172,16 @@ def cpu_arm(cores: int, nseg_per_worker: int, seed: int = 100):
     return audio_s / 3600.0 / wall, wall, time.perf_counter() - t0
 
 
+CPU_SAMPLE_NOTE = ("oracle restatement of the reference's CPU path: pocketfft (SIMD) f32 block transforms, all blocks of a "
+                   "window per call, + C post step")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0)) or 1        # the threads this process may actually use
-    nseg = 200                                   # 5 min of audio per worker per step
+    nseg = 400                                   # 10 min of audio per worker per step
     vals = []
     for i in range(args.warmup + args.steps):
         v, wall, _ = cpu_arm(cores, nseg, seed=100 + 1000 * i)
@@ -192,13 +189,15 @@ def run_reference(args):
             vals.append((v, wall))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([w for _, w in vals]) * 1e3)
-    sample = (f"{cores} worker processes x {nseg} windows (5 min of C2 audio each) per step; oracle restatement: "
-              "numpy/pocketfft f32 front end + C post step")
+    one, _, _ = cpu_arm(1, nseg, seed=99)        # the faithful figure: one decode thread per file, files sequential (processor.rs:31, lib.rs:694)
+    sample = (f"{cores} worker processes x {nseg} windows (10 min of C2 audio each) per step; {CPU_SAMPLE_NOTE}; "
+              "value = all cores (N cooperating birda processes), single_thread_value = one process")
     line = {"impl": "reference", "metric": "audio-hours/sec", "value": value, "unit": "audio-h/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "reference CPU algorithm restated (oracle); the Rust binary cannot be built here"},
-            "cpu_baseline": {"value": value, "unit": "audio-h/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "audio-h/s", "cores": cores, "kind": "port", "sample": sample,
+                             "single_thread_value": one},
             "e2e": {"value": value, "unit": "audio-h/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -315,6 +314,26 @@ def run_gpu(args):
         h_idx.copy_(d_idx, non_blocking=True); h_conf.copy_(d_conf, non_blocking=True); h_cnt.copy_(d_cnt, non_blocking=True)
         return r
 
+    # front end + (stand-in) inference + post: the library's stand-in classifier (NOT BirdNET: 48 band energies times a
+    # fixed matrix, the real [B, 144000] -> [B, 6522] contract) over the 38 batches the front end packed, its logits
+    # through the post step batch by batch — the per-file loop of the product (csrc/pipeline.cpp) on resident PCM
+    standin = b.StandIn(local, SEG, CLASSES, BATCH, seed=11, stream=stream.cuda_stream)
+    import ctypes as C
+
+    from birda_b200 import _lib
+
+    def step_with_standin():
+        r = plan.run(pcm, pad_to_batch=BATCH, want_tables=False)
+        base = r.device_ptr
+        ds, nc = C.c_void_p(), C.c_uint32()
+        for first in range(0, r.rows, BATCH):
+            rc = _lib.lib.bb_standin_classify(standin.handle, C.c_void_p(base + first * SEG * 4), BATCH, SEG, C.byref(ds), C.byref(nc))
+            assert rc == 0
+            valid = min(BATCH, r.nseg - first)
+            ctx.post_run_device(ds.value, BATCH, CLASSES, valid, cfg, mask.data_ptr(), None,
+                                d_idx.data_ptr() + first * 20, d_conf.data_ptr() + first * 20, d_cnt.data_ptr() + first * 4)
+        return r
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -350,6 +369,10 @@ def run_gpu(args):
     ms_front = timed(lambda: plan.run(pcm, pad_to_batch=BATCH, want_tables=False), args.steps) / args.steps
     ms_post = timed(lambda: ctx.post_run_device(scores.data_ptr(), rows, CLASSES, 2400, cfg, mask.data_ptr(), None,
                                                 d_idx.data_ptr(), d_conf.data_ptr(), d_cnt.data_ptr()), args.steps) / args.steps
+    step_with_standin()
+    sl0, cl0 = standin.launches, ctx.kernel_launches
+    ms_standin = timed(step_with_standin, args.steps)
+    launches_standin = (standin.launches - sl0) + (ctx.kernel_launches - cl0)
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -375,8 +398,12 @@ def run_gpu(args):
         e2e = args.steps * hours * world / (ms_e2e / 1e3)
         peak, peak_src = measured_peaks()
         ach = ALGO_BYTES_FRONT / (ms_front / 1e3) / 1e9
+        kernel = plan.describe()
+        traffic, smem_pct, prof_src = k2_profile(kernel)
+        h2d_bytes = int(h_pcm.numel() * 2)
         cores = len(os.sched_getaffinity(0)) or 1        # the threads this process may actually use
-        cpu_v, cpu_wall, _ = cpu_arm(cores, 200, seed=7)      # 5 min of audio per core, a few seconds
+        cpu_v, cpu_wall, _ = cpu_arm(cores, 400, seed=7)      # 10 min of audio per core, a few seconds
+        cpu_one, _, _ = cpu_arm(1, 400, seed=8)
         line = {
             "metric": "audio-hours/sec", "value": value, "unit": "audio-h/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -385,25 +412,153 @@ def run_gpu(args):
                        "l2": "inputs (635 MB PCM) and outputs (1.4 GB) per step exceed the 126 MB L2",
                        "model_forward": "not executed (not on the path; ONNX Runtime absent) - scores synthetic, resident",
                        "ms_front_end": ms_front, "ms_post": ms_post, "host": numa_note,
+                       "front_end_plus_standin_inference": {
+                           "value": args.steps * hours * world / (ms_standin / 1e3), "unit": "audio-h/s", "ms_per_step": ms_standin / args.steps,
+                           "gpu_launches": int(launches_standin),
+                           "note": "front end + the library's STAND-IN classifier (not BirdNET; same [64,144000]->[64,6522] contract, "
+                                   "38 batches) + post step per batch, inputs resident"},
                        "other_kernels": extras},
             "e2e": {"value": e2e, "unit": "audio-h/s", "h2d_bytes_per_step": int(h_pcm.numel() * 2),
                     "d2h_bytes_per_step": int(rows * 5 * 8 + rows * 4), "ms_per_step": ms_e2e / args.steps,
-                    "h2d_copy_alone_ms": ms_h2d_only, "frac_of_pcie_floor": ms_h2d_only / (ms_e2e / args.steps)},
+                    "h2d_copy_alone_ms": ms_h2d_only, "frac_of_pcie_floor": ms_h2d_only / (ms_e2e / args.steps),
+                    # the same bytes as ONE plain pinned->device copy per rank, all ranks at once (max over ranks): what the
+                    # host's DMA path gives this box at this N; e2e cannot beat it
+                    "host_dma_floor": {"gbs_per_gpu": h2d_bytes / ms_h2d_only / 1e6, "aggregate_gbs": world * h2d_bytes / ms_h2d_only / 1e6,
+                                       "audio_h_per_s": hours * world / (ms_h2d_only / 1e3)}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "resample_plan2_kernel (K2, two-stream compile-time plan 1029/1120, 640 threads)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": k2_traffic_bytes(), "algorithmic_bytes": ALGO_BYTES_FRONT,
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": traffic, "algorithmic_bytes": ALGO_BYTES_FRONT,
                          "peak_source": peak_src,
-                         "note": "K2 is FP32/shared-memory bound, not HBM bound (SURVEY 7.3 item 2)",
-                         "shared_memory_pipe_pct_ncu": k2_smem_pipe_pct(),
+                         "note": "K2 is FP32/shared-memory bound, not HBM bound (SURVEY 7.3 item 2); algorithmic flops are the reference "
+                                 "blocking's (SURVEY 8d): the kernel's own blocking does about a third less transform work",
+                         "shared_memory_pipe_pct_ncu": smem_pct, "profile_source": prof_src,
                          "fp32": {"achieved_tflops": ALGO_FLOPS_FRONT / (ms_front / 1e3) / 1e12, "peak_tflops": 74.5,
                                   "frac": ALGO_FLOPS_FRONT / (ms_front / 1e3) / 1e12 / 74.5}},
-            "cpu_baseline": {"value": cpu_v, "unit": "audio-h/s", "cores": cores, "kind": "port",
-                             "sample": f"{cores} worker processes x 200 windows (5 min of C2 audio each): numpy/pocketfft f32 "
-                                       "front end + C post step (oracle restatement of the reference's CPU path)"},
+            "cpu_baseline": {"value": cpu_v, "unit": "audio-h/s", "cores": cores, "kind": "port", "single_thread_value": cpu_one,
+                             "sample": f"{cores} worker processes x 400 windows (10 min of C2 audio each); {CPU_SAMPLE_NOTE}; "
+                                       "single_thread_value = one process (the reference decodes on one thread per file)"},
             "clocks": clocks,
         }
         print(json.dumps(line))
-    plan.close(); ctx.close()
+    standin.close(); plan.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ C5: directory batch
+C5_KINDS = [(16_000, 1), (22_050, 2), (32_000, 1), (44_100, 2), (48_000, 1), (96_000, 2)]     # rates and channel counts cycling
+C5_WORKLOAD = ("C5: directory of {n} synthetic 10-min s16 WAV files at mixed rates (16/22.05/32/44.1/48/96 kHz, mono/stereo) in "
+               "/dev/shm, BirdNET v2.4 windows (3 s, overlap 0, batch 64), stand-in classifier, range mask, through bb_pool_process_wavs")
+
+
+def c5_make_files(n_files: int, seconds: float, directory: str):
+    """12 distinct files (6 kinds x 2 seeds: one synthetic minute tiled, perturbed) hard-linked to n_files names."""
+    from birda_b200.synth import synth_pcm, write_wav
+    os.makedirs(directory, exist_ok=True)
+    masters = {}
+    for k, (sr, ch) in enumerate(C5_KINDS):
+        for v in range(2):
+            path = os.path.join(directory, f"master_{k}_{v}.wav")
+            if not os.path.exists(path):
+                base = synth_pcm(1000 + 2 * k + v, 60.0, sr, ch).reshape(-1, ch)
+                reps = int(np.ceil(seconds / 60.0))
+                pcm = np.tile(base, (reps, 1))[: int(seconds * sr)].copy()
+                pcm[:: 9973, 0] += 17
+                write_wav(path + ".tmp", pcm.reshape(-1), sr, ch)
+                os.replace(path + ".tmp", path)
+            masters[(k, v)] = path
+    paths = []
+    for i in range(n_files):
+        p = os.path.join(directory, f"file_{i:04d}.wav")
+        if not os.path.exists(p):
+            os.link(masters[(i % 6, (i // 6) % 2)], p)
+        paths.append(p)
+    return paths
+
+
+def run_c5(args):
+    """BASELINE config 5 through the product's multi-GPU path: files sharded over the ranks (longest first), each rank
+    runs the library's file pool (csrc/pool.cpp) with `--workers` contexts on its GPU and the library's stand-in
+    classifier as a native callback (no Python in the loop).  Strong scaling: the directory is fixed, ranks share it.
+    Timed with the host clock between barriers (max over ranks): the path is host-driven — file reads, worker threads,
+    H2D copies — and no device event sees all of it."""
+    import torch
+    import torch.distributed as dist
+
+    import birda_b200 as b
+    from birda_b200.pipeline import NativePool, ProcessingConfig
+    from birda_b200.shard import shard_files
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    numa_note = bind_to_gpu_numa_node(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    seconds, directory = 600.0, "/dev/shm/birda_b200_c5"
+    if rank == 0:
+        paths = c5_make_files(args.files, seconds, directory)
+    if world > 1:
+        dist.barrier()
+    paths = [os.path.join(directory, f"file_{i:04d}.wav") for i in range(args.files)]
+    mine = shard_files([seconds] * args.files, world)[rank]
+    my_paths = [paths[i] for i in mine]
+    my_bytes = sum(os.path.getsize(p) for p in my_paths)
+    g = torch.Generator(device=device); g.manual_seed(5)
+    mask = torch.rand(CLASSES, generator=g, device=device) ** 2
+    mask[torch.randperm(CLASSES, generator=g, device=device)[:305]] = float("nan")
+    cfg = ProcessingConfig(target_rate=TGT_RATE, segment_duration=3.0, overlap=0.0, batch_size=BATCH, min_confidence=0.1,
+                           d_mask=mask.data_ptr(), range_threshold=0.01, keep_unmatched=True, rerank=False)
+    W = max(1, args.workers)
+    standins = [b.StandIn(local, SEG, CLASSES, BATCH, seed=11) for _ in range(W)]
+    pool = NativePool([local] * W, [cfg] * W, standins)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    res = None
+    for _ in range(max(args.warmup, 1)):
+        res = pool.process_wavs(my_paths)
+    if rank == 0:
+        sampler.start()
+    l0 = pool.kernel_launches + sum(s.launches for s in standins)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = pool.process_wavs(my_paths)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    dt = float(t.item())
+    launches = pool.kernel_launches + sum(s.launches for s in standins) - l0
+    clocks = sampler.stop() if rank == 0 else None
+    nseg = sum(r.segments for r in res); ndet = sum(len(r.detections) for r in res)
+    assert all(r.segments == 200 for r in res), "every 10-min file is 200 windows at overlap 0"
+    if rank == 0:
+        hours = args.files * seconds / 3600.0
+        value = args.steps * hours / dt
+        cores = len(os.sched_getaffinity(0)) or 1
+        line = {"metric": "audio-hours/sec", "value": value, "unit": "audio-h/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": C5_WORKLOAD.format(n=args.files), "files": args.files, "workers_per_gpu": W,
+                           "sharding": f"files sharded longest-first over {world} rank(s), no collective", "host": numa_note,
+                           "timer": "host wall clock between barriers, max over ranks (host-driven path: file reads + worker threads + copies)",
+                           "l2": "every file's PCM (19-230 MB) is read from page cache, copied H2D and packed to 115 MB of windows: > L2 per file",
+                           "rank0_segments": nseg, "rank0_detections": ndet, "host_cores": cores},
+                "e2e": {"value": value, "unit": "audio-h/s", "h2d_bytes_per_step": int(my_bytes), "d2h_bytes_per_step": int(nseg * 44),
+                        "note": "this workload IS end to end: WAV files in page cache -> detections on the host"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+    pool.close()
+    for s_ in standins:
+        s_.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -414,9 +569,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: the headline step (default); c5: directory batch through the file pool")
+    ap.add_argument("--files", type=int, default=1000, help="c5: files in the directory")
+    ap.add_argument("--workers", type=int, default=3, help="c5: pool workers (contexts) per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        if args.steps == 20:
+            args.steps = 2
+        run_c5(args)
     else:
         run_gpu(args)
 

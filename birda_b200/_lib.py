@@ -101,6 +101,7 @@ SIGNATURES = {
     "bb_plan_destroy": (None, [vp]),
     "bb_plan_source_window": (C.c_int32, [vp, u64p, u64p]),
     "bb_plan_segment_count": (C.c_int32, [vp, C.c_uint64, u64p]),
+    "bb_plan_describe": (C.c_int32, [vp, C.c_char_p, C.c_uint32]),
     "bb_frontend_run": (C.c_int32, [vp, vp, C.c_uint64, C.c_int32, C.c_uint64, C.c_int32, C.c_uint32, vp, C.c_uint64,
                                     C.POINTER(vp), u64p, f32p, f32p, u64p, u64p, u64p]),
     "bb_post_run_device": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostCfg), vp, vp, vp, vp, vp]),
@@ -121,6 +122,7 @@ SIGNATURES = {
     "bb_pool_destroy": (None, [vp]),
     "bb_pool_process_wavs": (C.c_int32, [vp, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(PoolResult)]),
     "bb_pool_free_results": (None, [C.POINTER(PoolResult), C.c_uint32]),
+    "bb_pool_kernel_launches": (C.c_uint64, [vp]),
     "bb_dense_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_int32, vp]),
     "bb_melspec_create": (C.c_int32, [vp, C.POINTER(MelSpecCfg), f32p, f32p, C.POINTER(vp)]),
     "bb_melspec_destroy": (None, [vp]),

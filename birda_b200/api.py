@@ -349,6 +349,12 @@ class FrontEndPlan:
         check(lib.bb_plan_segment_count(self._h, total_frames, C.byref(n)))
         return n.value
 
+    def describe(self) -> str:
+        """Which kernel, transform sizes and blocking this plan launches (``bb_plan_describe``)."""
+        buf = C.create_string_buffer(320)
+        check(lib.bb_plan_describe(self._h, buf, 320))
+        return buf.value.decode()
+
     def run(self, pcm, frames: Optional[int] = None, *, is_device: Optional[bool] = None, first_start_sample: int = 0,
             is_eof: bool = True, pad_to_batch: int = 0, out_ptr: Optional[int] = None,
             out_capacity_rows: int = 0, want_tables: bool = True) -> Segments:

@@ -296,6 +296,16 @@ int32_t bb_plan_segment_count(const bb_plan* p, uint64_t total_frames, uint64_t*
     BB_CATCH(nullptr)
 }
 
+int32_t bb_plan_describe(const bb_plan* p, char* buf, uint32_t buf_len) {
+    BB_TRY
+    if (!p || !buf || buf_len == 0) BB_SET_ERR((bb_ctx*)nullptr, BB_ERR_INVALID_ARG, "bad argument");
+    const std::string s = p->resample ? "K2 " + warp_plan_describe(p->rs) : std::string("K1 pack_kernel (no resampling)");
+    std::strncpy(buf, s.c_str(), buf_len - 1);
+    buf[buf_len - 1] = 0;
+    return BB_OK;
+    BB_CATCH(nullptr)
+}
+
 int32_t bb_frontend_run(bb_plan* p, const void* pcm, uint64_t frames, int32_t pcm_is_device,
                         uint64_t first_start_sample, int32_t is_eof, uint32_t pad_to_batch,
                         float* d_out_user, uint64_t capacity_rows,

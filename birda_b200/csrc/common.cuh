@@ -103,6 +103,7 @@ cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& r
 cudaError_t resampler_dev_init(const ResamplerSpec& spec, ResamplerDev* rs);
 // K2 warp-per-block kernel (runtime plans; even N_out with supported radices).  k2_warp.cu
 bool        warp_plan_available(const ResamplerSpec& spec);
+std::string warp_plan_describe(const ResamplerDev& rs);     // which kernel / plan / blocking a launch will use
 cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs);
 void        warp_tables_free(ResamplerDev* rs);
 cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerDev& rs, const void* d_pcm, int fmt,

@@ -781,6 +781,17 @@ cudaError_t warp_tables_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     return cudaSuccess;
 }
 
+std::string warp_plan_describe(const ResamplerDev& rs) {
+    if (!rs.fast) return "resample_kernel (CTA-cooperative fallback) blocks " + std::to_string(rs.n_in) + "/" + std::to_string(rs.n_out);
+    RtPlan P; memcpy(&P, rs.plan_blob, sizeof(P));
+    std::string s = rs.ct_index >= 0 ? "resample_plan2_kernel (two-stream compile-time plan" : "resample_warp_kernel (runtime plan";
+    s += ", transforms " + std::to_string(2 * P.N) + " -> " + std::to_string(2 * P.M) + " real points, " + std::to_string(P.adv_in) + " in / " +
+         std::to_string(P.adv_out) + " out per block";
+    s += (P.adv_in == (int)rs.n_in) ? ", the reference's blocking" : ", own blocking over the reference's " + std::to_string(rs.n_in) + " taps";
+    if (rs.ct_index >= 0) s += ", " + std::to_string(ct_plan_dual_threads(rs.ct_index)) + " threads";
+    return s + ")";
+}
+
 void warp_tables_free(ResamplerDev* rs) {
     void* ptrs[] = {rs->f_twf, rs->f_twi, rs->f_sidx, rs->f_pq1, rs->f_pq2, rs->f_WI, rs->f_counter, rs->f_ordf, rs->f_ordi};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -58,6 +58,12 @@ int32_t bb_pool_create(const int32_t* devices, uint32_t n_devices, const bb_pipe
     BB_CATCH(nullptr)
 }
 
+uint64_t bb_pool_kernel_launches(const bb_pool* p) {
+    uint64_t n = 0;
+    if (p) for (const auto& w : p->workers) n += bb_ctx_kernel_launches(w.ctx);
+    return n;
+}
+
 void bb_pool_free_results(bb_pool_result* results, uint32_t n) {
     if (!results) return;
     for (uint32_t i = 0; i < n; ++i) { delete[] results[i].detections; results[i].detections = nullptr; results[i].n_detections = 0; }

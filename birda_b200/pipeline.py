@@ -299,6 +299,11 @@ class NativePool:
         self._h = C.c_void_p()
         _lib.check(_lib.lib.bb_pool_create(devs, n, c_cfgs, self._cb, users, C.byref(self._h)))
 
+    @property
+    def kernel_launches(self) -> int:
+        from . import _lib
+        return int(_lib.lib.bb_pool_kernel_launches(self._h))
+
     def process_wavs(self, paths: List[str]) -> List[ProcessResult]:
         import ctypes as C
 

@@ -72,3 +72,17 @@ def synth_logits(seed: int, rows: int, classes: int, adversarial: bool = True) -
         x[4, :] = 30.0                                    # everything saturates to 1.0: lowest indices win
         x[5, :] = -20.0; x[5, classes - 3:] = 5.0         # ties at the end of the row
     return x
+
+
+def write_wav(path: str, pcm: np.ndarray, rate: int, channels: int) -> None:
+    """Plain RIFF/WAVE file of interleaved int16 / int32 / float32 samples (benches and tools)."""
+    import struct
+    pcm = np.ascontiguousarray(pcm)
+    tag, bits = {np.dtype(np.int16): (1, 16), np.dtype(np.int32): (1, 32), np.dtype(np.float32): (3, 32)}[pcm.dtype]
+    raw = pcm.tobytes()
+    fmt = struct.pack("<HHIIHH", tag, channels, rate, rate * channels * bits // 8, channels * bits // 8, bits)
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 4 + 8 + len(fmt) + 8 + len(raw)) + b"WAVE")
+        f.write(b"fmt " + struct.pack("<I", len(fmt)) + fmt)
+        f.write(b"data" + struct.pack("<I", len(raw)))
+        f.write(raw)

@@ -183,6 +183,9 @@ int32_t bb_plan_create(bb_ctx*, uint32_t src_rate, uint32_t channels, bb_sample_
 void    bb_plan_destroy(bb_plan*);
 int32_t bb_plan_source_window(const bb_plan*, uint64_t* src_segment, uint64_t* src_overlap);
 int32_t bb_plan_segment_count(const bb_plan*, uint64_t total_frames, uint64_t* nseg);
+/* which kernel, transform sizes and blocking bb_frontend_run will launch for this plan (benches record it next to
+ * their timings; a committed profile is only quoted when it names the same kernel) */
+int32_t bb_plan_describe(const bb_plan*, char* buf, uint32_t buf_len);
 
 /* One piece of a file in, packed segments out.
  *
@@ -344,6 +347,7 @@ void    bb_pool_destroy(bb_pool*);
 /* returns BB_OK when every file succeeded, else the status of a failed file; results[n_files] is always filled */
 int32_t bb_pool_process_wavs(bb_pool*, const char* const* paths, uint32_t n_files, bb_pool_result* results);
 void    bb_pool_free_results(bb_pool_result* results, uint32_t n);
+uint64_t bb_pool_kernel_launches(const bb_pool*);      /* kernels the workers' contexts launched so far (classifier's not included) */
 
 /* ------------------------------------------------------------------------------------------
  * Tiny dense heads on the device: out[B,N] = act(x[B,K] W[K,N] + b[N]), f32.

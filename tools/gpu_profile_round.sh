@@ -3,6 +3,7 @@
 # usage: tools/gpu_profile_round.sh TAG
 TAG=${1:-r01}
 mkdir -p gpurun_out
+python -c "import birda_b200 as b; c=b.Context(0); print(b.FrontEndPlan(c,44100,2,b.FMT_S16,48000,144000,72000).describe())" > gpurun_out/${TAG}_k2_describe.txt
 ncu --set full --clock-control none --import-source on -k regex:resample_ -s 2 -c 1 -f -o gpurun_out/${TAG}_k2_c2_1h python tools/prof_run.py 60 2 c2 > gpurun_out/${TAG}_ncu_k2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:resample_ -s 2 -c 1 -f -o gpurun_out/${TAG}_k2_c3_1h python tools/prof_run.py 60 2 c3 > gpurun_out/${TAG}_ncu_k2c3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pack_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_k1_c4 python tools/prof_run.py 20 2 c4 > gpurun_out/${TAG}_ncu_k1.log 2>&1
