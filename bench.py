@@ -451,8 +451,11 @@ C5_WORKLOAD = ("C5: directory of {n} synthetic 10-min s16 WAV files at mixed rat
                "/dev/shm, BirdNET v2.4 windows (3 s, overlap 0, batch 64), stand-in classifier, range mask, through bb_pool_process_wavs")
 
 
-def c5_make_files(n_files: int, seconds: float, directory: str):
-    """12 distinct files (6 kinds x 2 seeds: one synthetic minute tiled, perturbed) hard-linked to n_files names."""
+def c5_make_files(n_files: int, seconds: float, directory: str, copies: bool = True):
+    """12 master files (6 kinds x 2 seeds: one synthetic minute tiled, perturbed) copied to n_files files (own pages in
+    the page cache each, as a real directory has; `copies=False` hard-links them instead: less RAM, but readers of the
+    same inode then contend for its pages)."""
+    import shutil
     from birda_b200.synth import synth_pcm, write_wav
     os.makedirs(directory, exist_ok=True)
     masters = {}
@@ -471,7 +474,10 @@ def c5_make_files(n_files: int, seconds: float, directory: str):
     for i in range(n_files):
         p = os.path.join(directory, f"file_{i:04d}.wav")
         if not os.path.exists(p):
-            os.link(masters[(i % 6, (i // 6) % 2)], p)
+            if copies:
+                shutil.copyfile(masters[(i % 6, (i // 6) % 2)], p + ".tmp"); os.replace(p + ".tmp", p)
+            else:
+                os.link(masters[(i % 6, (i // 6) % 2)], p)
         paths.append(p)
     return paths
 
@@ -497,7 +503,7 @@ def run_c5(args):
         dist.init_process_group("nccl", device_id=device)
     seconds, directory = 600.0, "/dev/shm/birda_b200_c5"
     if rank == 0:
-        paths = c5_make_files(args.files, seconds, directory)
+        paths = c5_make_files(args.files, seconds, directory, copies=not args.hardlinks)
     if world > 1:
         dist.barrier()
     paths = [os.path.join(directory, f"file_{i:04d}.wav") for i in range(args.files)]
@@ -512,6 +518,8 @@ def run_c5(args):
     W = max(1, args.workers)
     standins = [b.StandIn(local, SEG, CLASSES, BATCH, seed=11) for _ in range(W)]
     pool = NativePool([local] * W, [cfg] * W, standins)
+    if not args.pool_sync:
+        pool.bind_standins_to_worker_streams()      # the classifier queues on its worker's stream: one wait per file
 
     def barrier():
         if world > 1:
@@ -521,14 +529,14 @@ def run_c5(args):
     sampler = ClockSampler(local)
     res = None
     for _ in range(max(args.warmup, 1)):
-        res = pool.process_wavs(my_paths)
+        res = pool.process_wavs_counts(my_paths)
     if rank == 0:
         sampler.start()
     l0 = pool.kernel_launches + sum(s.launches for s in standins)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = pool.process_wavs(my_paths)
+        res = pool.process_wavs_counts(my_paths)       # detections stay C arrays: the library is timed, not a Python conversion
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device=device, dtype=torch.float64)
@@ -538,8 +546,8 @@ def run_c5(args):
     dt = float(t.item())
     launches = pool.kernel_launches + sum(s.launches for s in standins) - l0
     clocks = sampler.stop() if rank == 0 else None
-    nseg = sum(r.segments for r in res); ndet = sum(len(r.detections) for r in res)
-    assert all(r.segments == 200 for r in res), "every 10-min file is 200 windows at overlap 0"
+    nseg = sum(r[0] for r in res); ndet = sum(r[1] for r in res)
+    assert all(r[0] == 200 for r in res), "every 10-min file is 200 windows at overlap 0"
     if rank == 0:
         hours = args.files * seconds / 3600.0
         value = args.steps * hours / dt
@@ -547,7 +555,7 @@ def run_c5(args):
         line = {"metric": "audio-hours/sec", "value": value, "unit": "audio-h/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": C5_WORKLOAD.format(n=args.files), "files": args.files, "workers_per_gpu": W,
+                "config": {"workload": C5_WORKLOAD.format(n=args.files), "files": args.files, "workers_per_gpu": W, "classifier_stream": "own, waits per batch" if args.pool_sync else "worker's stream, one wait per file",
                            "sharding": f"files sharded longest-first over {world} rank(s), no collective", "host": numa_note,
                            "timer": "host wall clock between barriers, max over ranks (host-driven path: file reads + worker threads + copies)",
                            "l2": "every file's PCM (19-230 MB) is read from page cache, copied H2D and packed to 115 MB of windows: > L2 per file",
@@ -571,7 +579,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2: the headline step (default); c5: directory batch through the file pool")
     ap.add_argument("--files", type=int, default=1000, help="c5: files in the directory")
-    ap.add_argument("--workers", type=int, default=3, help="c5: pool workers (contexts) per GPU")
+    ap.add_argument("--workers", type=int, default=6, help="c5: pool workers (contexts) per GPU")
+    ap.add_argument("--pool-sync", action="store_true", help="c5: classifier on its own stream, pool waits around every batch (the default contract of bb_pool)")
+    ap.add_argument("--hardlinks", action="store_true", help="c5: hard-link the 12 master files instead of copying them (84 GB of page cache at 1000 files otherwise)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

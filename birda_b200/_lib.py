@@ -95,6 +95,7 @@ SIGNATURES = {
     "bb_ctx_stream": (vp, [vp]),
     "bb_sync": (C.c_int32, [vp]),
     "bb_ctx_kernel_launches": (C.c_uint64, [vp]),
+    "bb_ctx_set_blocking_sync": (None, [vp, C.c_int32]),
     "bb_host_alloc": (C.c_int32, [C.c_uint64, C.POINTER(vp)]),
     "bb_host_free": (None, [vp]),
     "bb_plan_create": (C.c_int32, [vp, C.c_uint32, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
@@ -108,6 +109,8 @@ SIGNATURES = {
     "bb_post_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PostCfg), vp, vp, u32p, f32p, u32p]),
     "bb_wav_probe": (C.c_int32, [C.c_char_p, C.POINTER(WavInfo)]),
     "bb_wav_read": (C.c_int32, [C.c_char_p, C.POINTER(WavInfo), C.c_uint64, C.c_uint64, vp]),
+    "bb_wav_read_parallel": (C.c_int32, [C.c_char_p, C.POINTER(WavInfo), C.c_uint64, C.c_uint64, vp, C.c_uint32]),
+    "bb_pipeline_set_read_threads": (None, [vp, C.c_uint32]),
     "bb_pipeline_create": (C.c_int32, [vp, C.POINTER(PipelineCfg), CLASSIFY_FN, vp, C.POINTER(vp)]),
     "bb_pipeline_destroy": (None, [vp]),
     "bb_pipeline_last_error": (C.c_char_p, [vp]),
@@ -123,6 +126,8 @@ SIGNATURES = {
     "bb_pool_process_wavs": (C.c_int32, [vp, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(PoolResult)]),
     "bb_pool_free_results": (None, [C.POINTER(PoolResult), C.c_uint32]),
     "bb_pool_kernel_launches": (C.c_uint64, [vp]),
+    "bb_pool_worker_ctx": (vp, [vp, C.c_uint32]),
+    "bb_pool_set_stream_ordered": (None, [vp, C.c_int32]),
     "bb_dense_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_int32, vp]),
     "bb_melspec_create": (C.c_int32, [vp, C.POINTER(MelSpecCfg), f32p, f32p, C.POINTER(vp)]),
     "bb_melspec_destroy": (None, [vp]),

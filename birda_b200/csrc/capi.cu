@@ -170,6 +170,7 @@ void bb_ctx_destroy(bb_ctx* c) {
     if (!c) return;
     bb::DeviceGuard dev_guard(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->sync_event) cudaEventDestroy(c->sync_event);
     if (c->d_post_index) cudaFree(c->d_post_index);
     if (c->d_post_conf) cudaFree(c->d_post_conf);
     if (c->d_post_count) cudaFree(c->d_post_count);
@@ -180,11 +181,13 @@ void bb_ctx_destroy(bb_ctx* c) {
 const char* bb_last_error(const bb_ctx* c) { return c ? c->last_error.c_str() : g_tls_error.c_str(); }
 void* bb_ctx_stream(bb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 uint64_t bb_ctx_kernel_launches(const bb_ctx* c) { return c ? c->launches : 0; }
+void bb_ctx_set_blocking_sync(bb_ctx* c, int32_t on) { if (c) c->blocking_sync = on != 0; }
 
 int32_t bb_sync(bb_ctx* c) {
     BB_TRY
     if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
-    BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    BB_DEVICE(c, c->device);
+    BB_CUDA_OK(c, bb::ctx_stream_wait(c));
     return BB_OK;
     BB_CATCH((c ? &c->last_error : nullptr))
 }
@@ -474,7 +477,7 @@ int32_t bb_post_run(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t C, ui
     BB_CUDA_OK(c, cudaMemcpyAsync(h_index, c->d_post_index, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     BB_CUDA_OK(c, cudaMemcpyAsync(h_conf, c->d_post_conf, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     BB_CUDA_OK(c, cudaMemcpyAsync(h_count, c->d_post_count, (uint64_t)valid_B * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    BB_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    BB_CUDA_OK(c, bb::ctx_stream_wait(c));
     return BB_OK;
     BB_CATCH((c ? &c->last_error : nullptr))
 }

@@ -14,6 +14,9 @@ struct bb_ctx {
     bool owns_stream = false;
     std::string last_error;
     uint64_t launches = 0;
+    // bb_ctx_set_blocking_sync: waits sleep on an event instead of spinning (a directory run has several worker threads
+    // per GPU and needs the host cores for file reads)
+    bool blocking_sync = false; cudaEvent_t sync_event = nullptr;
     // scratch for bb_post_run (host-output variant)
     uint32_t* d_post_index = nullptr; float* d_post_conf = nullptr; uint32_t* d_post_count = nullptr;
     uint64_t post_capacity_rows = 0; uint32_t post_capacity_k = 0;
@@ -80,6 +83,17 @@ struct DeviceGuard {
 };
 }  // namespace bb
 #define BB_DEVICE(ctx, device) bb::DeviceGuard _bb_dev_guard(device); BB_CUDA_OK(ctx, _bb_dev_guard.err)
+
+namespace bb {
+// wait for the context's stream: spinning cudaStreamSynchronize by default, a blocking-sync event when the context asks
+inline cudaError_t ctx_stream_wait(bb_ctx* c) {
+    if (!c->blocking_sync) return cudaStreamSynchronize(c->stream);
+    if (!c->sync_event) { cudaError_t e = cudaEventCreateWithFlags(&c->sync_event, cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    cudaError_t e = cudaEventRecord(c->sync_event, c->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(c->sync_event);
+}
+}  // namespace bb
 
 #define BB_SET_ERR(ctx, code, msg) do { if (ctx) (ctx)->last_error = (msg); else bb::set_tls_error(msg); return (code); } while (0)
 #define BB_CUDA_OK(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \

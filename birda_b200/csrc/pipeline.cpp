@@ -13,7 +13,10 @@
 #include "watchdog.hpp"
 #include "pipeline_internal.hpp"
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -38,6 +41,7 @@ struct bb_pipeline {
     uint64_t use_clock = 0;
     uint64_t plans_created = 0;
     bool sync_before_classify = false;        // bb_pipeline_set_sync_before_classify
+    uint32_t read_threads = 4;                // bb_pipeline_set_read_threads
     // per-batch seam (processor.rs:263-277): host hooks and / or a library-kept watchdog
     bb_batch_hook before_batch = nullptr, after_batch = nullptr; void* hook_user = nullptr;
     uint64_t batch_timeout_ms = 0; bb_watchdog_fn on_timeout = nullptr; void* timeout_user = nullptr;
@@ -261,7 +265,7 @@ int process_wav(bb_pipeline* p, const char* path, uint64_t piece_frames, Sink* s
     // reader: piece k goes to buffer k % nbuf once piece k - nbuf has been consumed
     std::mutex mu; std::condition_variable cv;
     size_t read_done = 0, consumed_n = 0, fail_at = ~(size_t)0; int read_rc = BB_OK; bool stop = false; std::string read_err;
-    auto read_piece = [&](size_t k) { return bb_wav_read(path, &info, pieces[k].pos, pieces[k].frames, p->pinned[k % nbuf]); };
+    auto read_piece = [&](size_t k) { return bb_wav_read_parallel(path, &info, pieces[k].pos, pieces[k].frames, p->pinned[k % nbuf], p->read_threads); };
     std::thread reader;
     if (nbuf == 2)
         reader = std::thread([&] {
@@ -276,8 +280,13 @@ int process_wav(bb_pipeline* p, const char* path, uint64_t piece_frames, Sink* s
     struct Joiner { std::thread& t; std::mutex& mu; std::condition_variable& cv; bool& stop;
                     ~Joiner() { if (t.joinable()) { { std::lock_guard<std::mutex> l(mu); stop = true; } cv.notify_all(); t.join(); } } } joiner{reader, mu, cv, stop};
 
+    // BIRDA_PIPE_TRACE=1: per-file wall times of the read and of the GPU leg on stderr (tools/prof_c5.py reads them)
+    static const bool trace = [] { const char* e = std::getenv("BIRDA_PIPE_TRACE"); return e && e[0] == '1'; }();
+    using clk = std::chrono::steady_clock;
+    double t_read = 0, t_run = 0;
     uint64_t seg_base = 0;
     for (size_t k = 0; k < pieces.size(); ++k) {
+        const auto t0 = clk::now();
         if (nbuf == 2) {
             std::unique_lock<std::mutex> l(mu);
             cv.wait(l, [&] { return read_done > k; });
@@ -286,14 +295,18 @@ int process_wav(bb_pipeline* p, const char* path, uint64_t piece_frames, Sink* s
             rc = read_piece(k);
             if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
         }
+        const auto t1 = clk::now();
         uint64_t nseg = 0, consumed = 0;
         rc = run_piece(p, p->pinned[k % nbuf], pieces[k].frames, pieces[k].pos, pieces[k].eof, B, seg_base, sink, &nseg, &consumed);
         if (rc != BB_OK) return rc;
+        t_read += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t_run += std::chrono::duration<double, std::milli>(clk::now() - t1).count();
         seg_base += nseg;
         if (!pieces[k].eof && pieces[k].pos + consumed != pieces[k + 1].pos) return fail(p, BB_ERR_INTERNAL, "piece table and front end disagree");
         if (nbuf == 2) { { std::lock_guard<std::mutex> l(mu); consumed_n = k + 1; } cv.notify_all(); }
     }
     if (n_segments) *n_segments = seg_base;
+    if (trace) std::fprintf(stderr, "[pipe] %s %.1f MB read %.2f ms gpu-leg %.2f ms\n", path, (double)info.frames * fb / 1e6, t_read, t_run);
     return BB_OK;
 }
 
@@ -322,6 +335,7 @@ int32_t bb_pipeline_create(bb_ctx* ctx, const bb_pipeline_cfg* cfg, bb_classify_
     bb_pipeline* p = new (std::nothrow) bb_pipeline();
     if (!p) return fail(nullptr, BB_ERR_OOM, "out of host memory");
     p->ctx = ctx; p->cfg = *cfg; p->classify = fn; p->user = user;
+    if (const char* e = std::getenv("BIRDA_READ_THREADS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) p->read_threads = (uint32_t)v; }
     *out = p;
     return BB_OK;
     BB_CATCH(nullptr)
@@ -338,6 +352,8 @@ void bb_pipeline_destroy(bb_pipeline* p) {
 const char* bb_pipeline_last_error(const bb_pipeline* p) { return p ? p->error.c_str() : ""; }
 uint64_t bb_pipeline_plans_created(const bb_pipeline* p) { return p ? p->plans_created : 0; }
 void bb_pipeline_set_sync_before_classify(bb_pipeline* p, int32_t on) { if (p) p->sync_before_classify = on != 0; }
+
+void bb_pipeline_set_read_threads(bb_pipeline* p, uint32_t threads) { if (p) p->read_threads = threads ? threads : 1; }
 
 void bb_pipeline_set_batch_hooks(bb_pipeline* p, bb_batch_hook before, bb_batch_hook after, void* user) {
     if (!p) return;

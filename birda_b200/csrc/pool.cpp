@@ -5,6 +5,7 @@
 // as bb_pipeline's; it is called from the worker thread of its device with that device's `user` pointer.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -50,12 +51,20 @@ int32_t bb_pool_create(const int32_t* devices, uint32_t n_devices, const bb_pipe
         // the pool owns the contexts, so the callback cannot know their streams: the packed windows are complete
         // (stream synchronised) before it is called; it must in turn finish its own work before it returns
         if (rc == BB_OK) bb_pipeline_set_sync_before_classify(w.pipe, 1);
+        if (rc == BB_OK) { const char* e = std::getenv("BIRDA_POOL_SPIN"); bb_ctx_set_blocking_sync(w.ctx, (e && e[0] == '1') ? 0 : 1); }   // workers sleep while the GPU works: the cores read files
         p->workers.push_back(w);
         if (rc != BB_OK) { bb_pool_destroy(p); return rc; }          // the failing call left the message
     }
     *out = p;
     return BB_OK;
     BB_CATCH(nullptr)
+}
+
+bb_ctx* bb_pool_worker_ctx(bb_pool* p, uint32_t worker) { return (p && worker < p->workers.size()) ? p->workers[worker].ctx : nullptr; }
+
+void bb_pool_set_stream_ordered(bb_pool* p, int32_t on) {
+    if (!p) return;
+    for (auto& w : p->workers) bb_pipeline_set_sync_before_classify(w.pipe, on ? 0 : 1);
 }
 
 uint64_t bb_pool_kernel_launches(const bb_pool* p) {
@@ -72,14 +81,16 @@ void bb_pool_free_results(bb_pool_result* results, uint32_t n) {
 int32_t bb_pool_process_wavs(bb_pool* p, const char* const* paths, uint32_t n_files, bb_pool_result* results) {
     BB_TRY
     if (!p || (!paths && n_files) || (!results && n_files)) return pool_fail(BB_ERR_INVALID_ARG, "null argument");
-    // longest first (durations from the WAV headers; unreadable files go last and report their error from the worker)
+    // longest first: by duration (the reference's unit of work, src/lib.rs:694), ties by PCM bytes (what the host side
+    // of this path pays for).  Unreadable files go last and report their error from the worker.
     std::vector<std::pair<double, uint32_t>> order(n_files);
     for (uint32_t i = 0; i < n_files; ++i) {
         std::memset(&results[i], 0, sizeof(results[i]));
         bb_wav_info info{};
-        double dur = -1.0;
-        if (bb_wav_probe(paths[i], &info) == BB_OK && info.sample_rate) dur = (double)info.frames / info.sample_rate;
-        order[i] = {dur, i};
+        double key = -1.0;
+        if (bb_wav_probe(paths[i], &info) == BB_OK && info.sample_rate)
+            key = (double)info.frames / info.sample_rate + 1e-12 * (double)info.frames * info.channels * (info.bits_per_sample / 8);
+        order[i] = {key, i};
     }
     std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
     std::atomic<uint32_t> next{0};

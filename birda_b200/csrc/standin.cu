@@ -50,6 +50,7 @@ struct bb_standin {
     // default: run on `own` and finish before returning (what bb_pool asks of its callback); bb_standin_use_stream:
     // queue asynchronously on the caller's stream (a pipeline on its own context: bb_ctx_stream)
     cudaStream_t own = nullptr, stream = nullptr; bool async = false;
+    cudaEvent_t done = nullptr;                        // blocking-sync event: the calling worker thread sleeps, it does not spin
     uint64_t launches = 0;
 };
 
@@ -60,6 +61,7 @@ void bb_standin_destroy(bb_standin* s) {
     bb::DeviceGuard g(s->device);
     for (float* p : {s->d_W, s->d_bias, s->d_feat, s->d_out}) if (p) cudaFree(p);
     if (s->own) cudaStreamDestroy(s->own);
+    if (s->done) cudaEventDestroy(s->done);
     delete s;
 }
 
@@ -87,6 +89,7 @@ int32_t bb_standin_create(int32_t device, uint32_t samples, uint32_t classes, ui
     if ((e = cudaMemcpy(s->d_W, s->W.data(), s->W.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
     if ((e = cudaMemcpy(s->d_bias, s->bias.data(), s->bias.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
     if ((e = cudaStreamCreateWithFlags(&s->own, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventCreateWithFlags(&s->done, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return fail(e);
     *out = s;
     return BB_OK;
     BB_CATCH(nullptr)
@@ -118,7 +121,7 @@ int32_t bb_standin_classify(void* user, const float* d_segments, uint32_t batch,
     standin_project_kernel<<<dim3((s->classes + 255) / 256, batch), 256, 0, st>>>(s->d_feat, s->d_W, s->d_bias, s->classes, s->d_out);
     if (cudaGetLastError() != cudaSuccess) return 3;
     s->launches += 2;
-    if (!s->async && cudaStreamSynchronize(st) != cudaSuccess) return 4;
+    if (!s->async && (cudaEventRecord(s->done, st) != cudaSuccess || cudaEventSynchronize(s->done) != cudaSuccess)) return 4;
     *d_scores = s->d_out; *classes = s->classes;
     return 0;
 }

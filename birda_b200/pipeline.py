@@ -304,6 +304,40 @@ class NativePool:
         from . import _lib
         return int(_lib.lib.bb_pool_kernel_launches(self._h))
 
+    def worker_stream(self, i: int) -> int:
+        """cudaStream_t (as an int) of worker ``i``'s context."""
+        from . import _lib
+        return int(_lib.lib.bb_ctx_stream(_lib.lib.bb_pool_worker_ctx(self._h, i)) or 0)
+
+    def bind_standins_to_worker_streams(self) -> None:
+        """Native stand-in classifiers queue on their worker's stream; the pool stops waiting around every batch."""
+        from . import _lib
+        from .api import StandIn
+        assert all(isinstance(c, StandIn) for c in self.classifiers)
+        for i, c in enumerate(self.classifiers):
+            _lib.lib.bb_standin_use_stream(c.handle, self.worker_stream(i), 1)
+        _lib.lib.bb_pool_set_stream_ordered(self._h, 1)
+
+    def process_wavs_counts(self, paths: List[str]):
+        """The same run without turning detections into Python objects: [(segments, detections, device)] per file
+        (benches time the library, not the conversion)."""
+        import ctypes as C
+
+        from . import _lib
+        n = len(paths)
+        arr = (C.c_char_p * n)(*[p.encode() for p in paths])
+        res = (_lib.PoolResult * n)()
+        rc = _lib.lib.bb_pool_process_wavs(self._h, arr, n, res)
+        try:
+            for i in range(n):
+                if res[i].status != 0:
+                    raise _lib.BirdaError(int(res[i].status), f"{paths[i]}: {res[i].error.decode('utf-8', 'replace')}")
+            out = [(int(res[i].n_segments), int(res[i].n_detections), int(res[i].device)) for i in range(n)]
+        finally:
+            _lib.lib.bb_pool_free_results(res, n)
+        assert rc == 0
+        return out
+
     def process_wavs(self, paths: List[str]) -> List[ProcessResult]:
         import ctypes as C
 

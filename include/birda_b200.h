@@ -161,6 +161,9 @@ const char* bb_last_error(const bb_ctx*);
 void*       bb_ctx_stream(bb_ctx*);                            /* cudaStream_t                  */
 int32_t     bb_sync(bb_ctx*);                                  /* cudaStreamSynchronize         */
 uint64_t    bb_ctx_kernel_launches(const bb_ctx*);             /* kernels launched so far        */
+/* waits of this context (bb_sync, bb_post_run) sleep on a blocking-sync event instead of spinning on the stream: for hosts
+ * that run several worker threads per GPU and need their cores (bb_pool turns it on for its contexts) */
+void        bb_ctx_set_blocking_sync(bb_ctx*, int32_t on);
 
 /* Page-locked host staging (decode straight into it; H2D copies then run at PCIe rate) */
 int32_t bb_host_alloc(uint64_t bytes, void** out);
@@ -265,6 +268,9 @@ typedef struct {
 } bb_wav_info;
 int32_t bb_wav_probe(const char* path, bb_wav_info* out);
 int32_t bb_wav_read(const char* path, const bb_wav_info* info, uint64_t first_frame, uint64_t frames, void* dst);
+/* the same read cut into slices read by `threads` threads at once (a read from the page cache is a memcpy: one thread
+ * moves 6-10 GB/s, the PCIe link to the GPU takes ~55 GB/s) */
+int32_t bb_wav_read_parallel(const char* path, const bb_wav_info* info, uint64_t first_frame, uint64_t frames, void* dst, uint32_t threads);
 
 /* ------------------------------------------------------------------------------------------
  * Per-file pipeline (C++ host code in the library): the reference's process_file loop
@@ -315,6 +321,8 @@ void        bb_pipeline_set_batch_timeout(bb_pipeline*, uint64_t timeout_ms, bb_
 /* for classifiers that do not run on the ctx stream: synchronise it before every callback (the callback then has to
  * finish its own work before it returns).  Off by default; bb_pool turns it on. */
 void        bb_pipeline_set_sync_before_classify(bb_pipeline*, int32_t on);
+/* threads per file read of bb_pipeline_process_wav (bb_wav_read_parallel); default 4 */
+void        bb_pipeline_set_read_threads(bb_pipeline*, uint32_t threads);
 /* Whole decoded file in host memory.  Detections come back sorted (start_time asc, confidence desc:
  * processor.rs:178-187); BB_ERR_CAPACITY reports the needed count in *n_detections. */
 int32_t bb_pipeline_process_pcm(bb_pipeline*, const void* pcm, uint64_t frames, uint32_t src_rate, uint32_t channels,
@@ -347,6 +355,12 @@ void    bb_pool_destroy(bb_pool*);
 /* returns BB_OK when every file succeeded, else the status of a failed file; results[n_files] is always filled */
 int32_t bb_pool_process_wavs(bb_pool*, const char* const* paths, uint32_t n_files, bb_pool_result* results);
 void    bb_pool_free_results(bb_pool_result* results, uint32_t n);
+/* worker i's context (its stream: bb_ctx_stream).  A classifier that queues its work on that stream (ONNX Runtime with
+ * user_compute_stream, the stand-in after bb_standin_use_stream) needs no synchronisation around the callback:
+ * bb_pool_set_stream_ordered(pool, 1) drops the pool's per-batch waits (default 0: the callback may use any stream and
+ * must finish before it returns). */
+bb_ctx* bb_pool_worker_ctx(bb_pool*, uint32_t worker);
+void    bb_pool_set_stream_ordered(bb_pool*, int32_t on);
 uint64_t bb_pool_kernel_launches(const bb_pool*);      /* kernels the workers' contexts launched so far (classifier's not included) */
 
 /* ------------------------------------------------------------------------------------------

@@ -180,3 +180,21 @@ def test_24bit_odd_offsets_and_tail():
             assert np.array_equal(res.torch().cpu().numpy()[: res.nseg], ref.segments), (channels, off)
             plan.close()
     ctx.close()
+
+
+def test_parallel_read_equals_serial(tmp_path):
+    """bb_wav_read_parallel: slices read by several threads land where one pread would put them (any thread count,
+    ranges that do not divide evenly, reads below the slicing threshold)."""
+    import ctypes as C
+
+    from birda_b200 import _lib
+    pcm = synth_pcm(31, 140.0, 48_000, 2)                          # 26.9 MB: more than a few 4 MB slices
+    p = str(tmp_path / "big.wav"); write_wav(p, pcm, 48_000, 2)
+    info = b.wav_probe(p)
+    for first, frames in ((0, info.frames), (12_345, info.frames - 20_001), (7, 1000)):
+        want = pcm[first * 2: (first + frames) * 2]
+        for threads in (1, 2, 3, 5, 16):
+            got = np.zeros(frames * 2, np.int16)
+            rc = _lib.lib.bb_wav_read_parallel(p.encode(), C.byref(info._c) if hasattr(info, "_c") else C.byref(info), first, frames,
+                                               got.ctypes.data_as(C.c_void_p), threads)
+            assert rc == 0 and np.array_equal(got, want), (first, frames, threads)
