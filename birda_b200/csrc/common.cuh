@@ -35,6 +35,9 @@ struct ResamplerDev {
     float2* d_split_inv = nullptr;  // [n_out]  exp(+2*pi*i*k/(2*n_out))
     float2* d_filt = nullptr;       // [n_keep] filter spectrum
     uint32_t buf_len = 0;           // complex elements per ping/pong buffer
+    // blocks too long for shared memory (rates with a small gcd, e.g. 8 001 Hz -> 48 kHz: 2667 / 16000): the fallback
+    // kernel keeps its tables and buffers in a per-CTA slice of this global workspace instead (slow, but it resamples)
+    unsigned char* d_ws = nullptr; size_t ws_stride = 0; uint32_t ws_ctas = 0;
     // warp-per-block path (runtime plan, k2_warp.cu)
     bool fast = false;
     alignas(8) unsigned char plan_blob[768] = {0};

@@ -49,6 +49,7 @@ struct K2Params {
     const float2 *tw_f, *tw_i, *split_f, *split_i, *filt;
     uint32_t buf_len, G, nblk, R, items_per_row;
     uint64_t nitems;
+    unsigned char* ws; size_t ws_stride;       // global workspace mode (WS kernels): per-CTA slice in place of shared memory
 };
 
 // One Stockham DIF stage over the G blocks of a round:  y[q + s*(r*p + k)] = DFT_r(x[i + j*nb])_k * w^(s*p*k)
@@ -79,8 +80,33 @@ __device__ __forceinline__ void run_stage(const Stage& st, const float2* __restr
     }
 }
 
+// The same stage for any prime radix (block lengths with a prime factor > 31): every output of a butterfly is a direct
+// sum over its R inputs, W_R^(jk) read from the transform's full-length table (tw[m] = exp(-+2 pi i m / n), so
+// W_R^e = tw[e * n / R]).  One thread per (butterfly, k); O(n * R) per stage.
+__device__ __forceinline__ void run_stage_generic(const Stage& st, const float2* __restrict__ src, float2* __restrict__ dst,
+                                                  const float2* __restrict__ tw, uint32_t n, uint32_t buf_stride, uint32_t G, bool last) {
+    const uint32_t R = (uint32_t)st.radix, nb = st.nb, s = st.s, step = n / R;
+    const uint32_t per_block = nb * R;                      // == n
+    for (uint32_t t = threadIdx.x; t < G * per_block; t += kThreads) {
+        const uint32_t g = t / per_block, r = t - g * per_block;
+        const uint32_t k = r / nb, i = r - k * nb;
+        const float2* __restrict__ x = src + (size_t)g * buf_stride;
+        float2 acc = x[i];
+        uint32_t e = 0;                                     // (j * k) mod R
+        for (uint32_t j = 1; j < R; ++j) {
+            e += k; if (e >= R) e -= R;
+            acc = cadd(acc, cmul(x[i + j * nb], tw[e * step]));
+        }
+        const uint32_t q = i - st.div_s.div(i) * s;
+        const uint32_t sp = i - q;
+        const uint32_t ob = i + sp * (R - 1);
+        if (!(last || sp == 0 || k == 0)) acc = cmul(acc, tw[sp * k]);
+        dst[(size_t)g * buf_stride + ob + s * k] = acc;
+    }
+}
+
 template <bool INV>
-__device__ __forceinline__ void run_stage_dispatch(const Stage& st, const float2* src, float2* dst, const float2* tw,
+__device__ __forceinline__ void run_stage_dispatch(const Stage& st, const float2* src, float2* dst, const float2* tw, uint32_t n,
                                                    uint32_t buf_stride, uint32_t G, bool last) {
     switch (st.radix) {
         case 2:  run_stage<2, INV>(st, src, dst, tw, buf_stride, G, last); break;
@@ -96,7 +122,7 @@ __device__ __forceinline__ void run_stage_dispatch(const Stage& st, const float2
         case 23: run_stage<23, INV>(st, src, dst, tw, buf_stride, G, last); break;
         case 29: run_stage<29, INV>(st, src, dst, tw, buf_stride, G, last); break;
         case 31: run_stage<31, INV>(st, src, dst, tw, buf_stride, G, last); break;
-        default: break;
+        default: run_stage_generic(st, src, dst, tw, n, buf_stride, G, last); break;      // the table carries the direction
     }
 }
 
@@ -139,9 +165,11 @@ __device__ __forceinline__ float2 real_bin(const float2* __restrict__ Z, uint32_
     return cadd(fe, cmul(wf, fo));
 }
 
+template <bool WS>
 __global__ void __launch_bounds__(kThreads)
 resample_kernel(const K2Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char* smem_raw = WS ? P.ws + (size_t)blockIdx.x * P.ws_stride : smem_dyn;
     float2* tw_f = reinterpret_cast<float2*>(smem_raw);
     float2* tw_i = tw_f + P.n_in;
     float*  carry = reinterpret_cast<float*>(tw_i + P.n_out);
@@ -198,7 +226,7 @@ resample_kernel(const K2Params P) {
             // ---- forward half-length complex FFT
             float2* src = bufA; float2* dst = bufB;
             for (int s = 0; s < P.nst_f; ++s) {
-                run_stage_dispatch<false>(P.st_f[s], src, dst, tw_f, BL, g_n, s + 1 == P.nst_f);
+                run_stage_dispatch<false>(P.st_f[s], src, dst, tw_f, N, BL, g_n, s + 1 == P.nst_f);
                 __syncthreads();
                 float2* t = src; src = dst; dst = t;
             }
@@ -230,7 +258,7 @@ resample_kernel(const K2Params P) {
             { float2* t = src; src = dst; dst = t; }
             // ---- inverse half-length complex FFT (unnormalised)
             for (int s = 0; s < P.nst_i; ++s) {
-                run_stage_dispatch<true>(P.st_i[s], src, dst, tw_i, BL, g_n, s + 1 == P.nst_i);
+                run_stage_dispatch<true>(P.st_i[s], src, dst, tw_i, M, BL, g_n, s + 1 == P.nst_i);
                 __syncthreads();
                 float2* t = src; src = dst; dst = t;
             }
@@ -269,7 +297,12 @@ cudaError_t resampler_dev_init(const ResamplerSpec& spec, ResamplerDev* rs) {
     if (rs->buf_len & 1) rs->buf_len += 1;        // keep every buffer 16-byte aligned
     // one block in flight must fit
     const size_t min_smem = (size_t)(spec.n_in + spec.n_out) * 8 + (size_t)(spec.n_out + 4) * 4 + (size_t)2 * rs->buf_len * 8;
-    if (min_smem > 220 * 1024) return cudaErrorInvalidConfiguration;
+    if (min_smem > 220 * 1024) {               // global workspace mode
+        rs->ws_stride = (min_smem + 255) & ~(size_t)255;
+        rs->ws_ctas = 304;
+        cudaError_t we = cudaMalloc(&rs->d_ws, rs->ws_stride * rs->ws_ctas);
+        if (we != cudaSuccess) return we;
+    }
     const double pi = 3.14159265358979323846;
     auto upload = [](const std::vector<float2>& h, float2** d) -> cudaError_t {
         cudaError_t e = cudaMalloc(d, h.size() * sizeof(float2));
@@ -303,6 +336,8 @@ void resampler_dev_free(ResamplerDev* rs) {
     if (rs->d_split_fwd) cudaFree(rs->d_split_fwd);
     if (rs->d_split_inv) cudaFree(rs->d_split_inv);
     if (rs->d_filt) cudaFree(rs->d_filt);
+    if (rs->d_ws) cudaFree(rs->d_ws);
+    rs->d_ws = nullptr; rs->ws_stride = 0; rs->ws_ctas = 0;
     warp_tables_free(rs);
     *rs = ResamplerDev();
 }
@@ -344,8 +379,9 @@ cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& r
     size_t budget = 108 * 1024;
     uint32_t G = fixed + per_g <= budget ? (uint32_t)((budget - fixed) / per_g) : 1;
     if (G > 8) G = 8;
-    if (G < 1) G = 1;
+    if (G < 1 || rs.d_ws) G = 1;
     P.G = G;
+    P.ws = rs.d_ws; P.ws_stride = rs.ws_stride;
     // R: blocks per work item.  Whole windows when there are plenty of them, shorter runs otherwise
     const uint64_t ctas = (uint64_t)sm_count * 2;
     uint32_t R = P.nblk;
@@ -368,9 +404,15 @@ cudaError_t launch_resample(cudaStream_t st, int sm_count, const ResamplerDev& r
     const unsigned grid = (unsigned)grid64;
     cudaError_t e = cudaSuccess;
     if (fmt != BB_S16 && fmt != BB_S32 && fmt != BB_F32 && fmt != BB_S24) return cudaErrorInvalidValue;
-    e = cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rs.d_ws) {
+        if (smem > rs.ws_stride) return cudaErrorInvalidConfiguration;
+        resample_kernel<true><<<grid < rs.ws_ctas ? grid : rs.ws_ctas, kThreads, 0, st>>>(P);
+        if (launches) *launches = 1;
+        return cudaGetLastError();
+    }
+    e = cudaFuncSetAttribute(resample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    resample_kernel<<<grid, kThreads, smem, st>>>(P);
+    resample_kernel<false><<<grid, kThreads, smem, st>>>(P);
     if (launches) *launches = 1;
     return cudaGetLastError();
 }

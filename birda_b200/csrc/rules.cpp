@@ -108,7 +108,12 @@ bool factorize(uint32_t n, std::vector<int>* radices) {
     while (n % 8 == 0) { even.push_back(8); n /= 8; }
     while (n % 4 == 0) { even.push_back(4); n /= 4; }
     while (n % 2 == 0) { even.push_back(2); n /= 2; }
-    if (n != 1) return false;
+    // what is left has only prime factors > 31 (rates like 12 345 Hz -> blocks of 2 * 823): they become stages of
+    // their own, evaluated as direct O(p^2) DFTs by the fallback kernel (k2_resample.cu: run_stage_generic) — slow
+    // next to the butterflies, but the reference resamples every pair rubato accepts (src/audio/resample.rs:19-28)
+    for (uint32_t p = 37; n > 1 && (uint64_t)p * p <= n; p += 2)
+        while (n % p == 0) { odd.push_back((int)p); n /= p; }
+    if (n > 1) { if (n > 32768) return false; odd.push_back((int)n); n = 1; }
     // largest odd radix first
     for (size_t i = 0; i < odd.size(); ++i)
         for (size_t j = i + 1; j < odd.size(); ++j)
@@ -164,7 +169,7 @@ bool make_resampler_spec(uint32_t from, uint32_t to, bool want_spectrum, Resampl
     }
     if (!factorize(s->n_in, &s->radix_fwd) || !factorize(s->n_out, &s->radix_inv)) {
         if (err) *err = "resampler block sizes " + std::to_string(n_in) + "/" + std::to_string(n_out) +
-                        " have a prime factor > 31 (rates " + std::to_string(from) + " -> " + std::to_string(to) + ")";
+                        " have a prime factor > 32768 (rates " + std::to_string(from) + " -> " + std::to_string(to) + ")";
         return false;
     }
     if (want_spectrum) {

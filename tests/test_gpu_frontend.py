@@ -172,6 +172,18 @@ def test_resample_generic_kernel_path(ctx, monkeypatch):
     assert rel_err(out[: res.nseg], ref.segments.astype(np.float64)) <= RESAMPLE_TOL
 
 
+@pytest.mark.parametrize("sr,channels", [(12_345, 1), (8_001, 2), (37_000, 1)])
+def test_resample_rates_with_large_prime_blocks(ctx, sr, channels):
+    """Rates whose blocks have a prime factor > 31 (12 345 Hz: 2 * 823; 8 001 Hz: 3 * 7 * 127; 37 kHz: 37 * 28): the
+    reference resamples whatever rubato accepts (src/audio/resample.rs:19-28); here the fallback kernel evaluates the
+    big prime's stage as a direct DFT.  Same gate as every other pair."""
+    pcm = synth_pcm(70 + channels, 7.3, sr, channels)
+    ref = ofe.decode_and_stream(pcm, channels, sr, 48_000, 144_000, 0, precision="f64")
+    res, out = run_gpu(ctx, pcm, channels, sr, 48_000, 144_000, 0, b.FMT_S16)
+    assert_tables(res, ref)
+    assert rel_err(out[: res.nseg], ref.segments.astype(np.float64)) <= RESAMPLE_TOL
+
+
 @pytest.mark.parametrize("dtype,fmt,channels", [(np.int32, b.FMT_S32, 2), (np.float32, b.FMT_F32, 1), (np.int16, b.FMT_S16, 3)])
 def test_resample_other_formats(ctx, dtype, fmt, channels):
     pcm = synth_pcm(40 + channels, 6.4, 44_100, channels, dtype)
