@@ -8,7 +8,7 @@ CPU fallback: importing works anywhere (so the host rules can be used), but crea
 from ._lib import BirdaError, lib, lib_path  # noqa: F401
 from .api import (  # noqa: F401
     ACT_NONE, ACT_SIGMOID, ACT_SOFTMAX, FMT_F32, FMT_S16, FMT_S24, FMT_S32,
-    Context, FrontEndPlan, MelSpec, PostConfig, Segments, StandIn, Watchdog, mask_build, rules, wav_probe, wav_read,
+    Context, FrontEndPlan, MelSpec, PostConfig, Segments, StandIn, Watchdog, FlacDecoder, flac_probe, mask_build, rules, wav_probe, wav_read,
 )
 
 __version__ = "0.1.0"

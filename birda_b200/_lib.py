@@ -59,6 +59,12 @@ class PoolResult(C.Structure):
                 ("batch_used", C.c_uint32), ("detections", C.POINTER(DetectionC)), ("error", C.c_char * 200)]
 
 
+class FlacInfo(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bits_per_sample", C.c_uint32),
+                ("min_block", C.c_uint32), ("max_block", C.c_uint32), ("min_frame_bytes", C.c_uint32), ("max_frame_bytes", C.c_uint32),
+                ("frames", C.c_uint64), ("first_frame_offset", C.c_uint64), ("file_bytes", C.c_uint64), ("fmt", C.c_int32)]
+
+
 WATCHDOG_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64, C.c_uint32)
 BATCH_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64)
 CLASSIFY_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32))
@@ -133,6 +139,11 @@ SIGNATURES = {
     "bb_melspec_destroy": (None, [vp]),
     "bb_melspec_info": (C.c_int32, [vp, u32p, u32p, u32p]),
     "bb_melspec_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp]),
+    "bb_flac_probe": (C.c_int32, [C.c_char_p, C.POINTER(FlacInfo)]),
+    "bb_flac_probe_bytes": (C.c_int32, [vp, C.c_uint64, C.POINTER(FlacInfo)]),
+    "bb_flac_create": (C.c_int32, [vp, C.POINTER(vp)]),
+    "bb_flac_destroy": (None, [vp]),
+    "bb_flac_decode": (C.c_int32, [vp, vp, C.c_uint64, C.POINTER(FlacInfo), C.POINTER(vp), u64p]),
     "bb_standin_create": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(vp)]),
     "bb_standin_destroy": (None, [vp]),
     "bb_standin_use_stream": (None, [vp, vp, C.c_int32]),

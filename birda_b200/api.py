@@ -122,6 +122,54 @@ def mask_build(classifier_labels, geomodel_labels, scores) -> Tuple[np.ndarray, 
     return mask[: len(classifier_labels)], mapped.value, unmatched.value
 
 
+def flac_probe(path_or_bytes):
+    """STREAMINFO of a FLAC file (path) or stream (bytes): ``_lib.FlacInfo``."""
+    info = _lib.FlacInfo()
+    if isinstance(path_or_bytes, (bytes, bytearray)):
+        raw = bytes(path_or_bytes)
+        check(lib.bb_flac_probe_bytes(raw, len(raw), C.byref(info)))
+    else:
+        check(lib.bb_flac_probe(str(path_or_bytes).encode(), C.byref(info)))
+    return info
+
+
+class FlacDecoder:
+    """``bb_flac``: the compressed file goes to the GPU, one thread per frame decodes it into the interleaved PCM the
+    front end consumes.  ``decode(bytes)`` -> (device pointer, frames, info); the buffer is valid until the next decode."""
+
+    def __init__(self, ctx: "Context"):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        check(lib.bb_flac_create(ctx.handle, C.byref(self._h)), ctx.handle)
+
+    def decode(self, data: bytes):
+        info = flac_probe(data)
+        ptr, frames = C.c_void_p(), C.c_uint64()
+        check(lib.bb_flac_decode(self._h, data, len(data), C.byref(info), C.byref(ptr), C.byref(frames)), self.ctx.handle)
+        return ptr.value or 0, int(frames.value), info
+
+    def decode_to_numpy(self, data: bytes) -> Tuple[np.ndarray, "_lib.FlacInfo"]:
+        """Decoded PCM copied back to the host: int16 / packed-24 (uint8) / int32, interleaved (tests)."""
+        ptr, frames, info = self.decode(data)
+        dt, per = {FMT_S16: (np.int16, 1), FMT_S24: (np.uint8, 3), FMT_S32: (np.int32, 1)}[info.fmt]
+        out = np.zeros(frames * info.channels * per, dt)
+        if out.size:
+            check(lib.bb_memcpy_d2h(self.ctx.handle, out.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), out.nbytes), self.ctx.handle)
+            self.ctx.sync()
+        return out, info
+
+    def close(self):
+        if self._h:
+            lib.bb_flac_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class StandIn:
     """``bb_standin``: the library's stand-in classifier (NOT a model) — [B, samples] windows -> [B, classes] logits on
     the device, as a native ``bb_classify_fn`` for NativePipeline / NativePool and the benches.  ``stream``: queue on

@@ -50,6 +50,7 @@ struct bb_pipeline {
     void* pinned[2] = {nullptr, nullptr}; uint64_t pinned_bytes[2] = {0, 0};
     // post-step results of one piece stay on the device and come back in ONE copy per piece (bb_post_run_device per
     // batch); with batch hooks or a watchdog set every batch is synchronous instead, as in the reference
+    bb_flac* flac = nullptr;                  // FLAC files: decoder state (device buffers), created on first use
     uint32_t* d_index = nullptr; float* d_conf = nullptr; uint32_t* d_count = nullptr; uint64_t d_res_rows = 0; uint32_t d_res_k = 0;
     std::vector<uint32_t> h_index; std::vector<float> h_conf; std::vector<uint32_t> h_count;
     std::vector<float> st, et; std::vector<uint64_t> ss;
@@ -124,14 +125,14 @@ int ensure_results(bb_pipeline* p, uint64_t rows, uint32_t K) {
 
 // one piece of PCM already in host memory -> detections appended to the sink
 int run_piece(bb_pipeline* p, const void* pcm, uint64_t frames, uint64_t first_start, bool eof, uint32_t B,
-              uint64_t seg_base, Sink* sink, uint64_t* nseg_out, uint64_t* consumed) {
+              uint64_t seg_base, Sink* sink, uint64_t* nseg_out, uint64_t* consumed, bool pcm_is_device = false) {
     uint64_t src_seg = 0, src_ovl = 0, nmax = 0;
     bb_plan_source_window(p->plan, &src_seg, &src_ovl);
     bb_rule_segment_count(frames, src_seg, src_ovl, &nmax);
     const uint64_t cap = (nmax / B + 1) * B;
     p->st.resize(cap); p->et.resize(cap); p->ss.resize(cap);
     float* d_seg = nullptr; uint64_t nseg = 0, rows = 0;
-    int rc = bb_frontend_run(p->plan, pcm, frames, 0, first_start, eof ? 1 : 0, B, nullptr, cap, &d_seg, p->ss.data(),
+    int rc = bb_frontend_run(p->plan, pcm, frames, pcm_is_device ? 1 : 0, first_start, eof ? 1 : 0, B, nullptr, cap, &d_seg, p->ss.data(),
                              p->st.data(), p->et.data(), &nseg, &rows, consumed);
     if (rc != BB_OK) return fail(p, rc, bb_last_error(p->ctx));
     *nseg_out = nseg;
@@ -225,7 +226,42 @@ int ensure_pinned(bb_pipeline* p, int slot, uint64_t bytes) {
 // whole number of batches (only the file's LAST batch is padded, processor.rs:132-170).  A file of several pieces is
 // read by a second thread into the other pinned buffer while the GPU works on the current piece (the reference's decode
 // thread, processor.rs:20-47).  run_piece ends with the stream synchronised, so a buffer is free again two pieces later.
+// A FLAC file: the compressed bytes are read into pinned memory and copied to the GPU, decoded there (K6) and handed to
+// the front end as device-resident PCM — one piece, whatever the length (an hour of 44.1 kHz stereo is 0.6 GB decoded).
+int process_flac(bb_pipeline* p, const char* path, Sink* sink, uint64_t* n_segments, uint32_t* batch_used) {
+    bb_flac_info info;
+    int rc = bb_flac_probe(path, &info);
+    if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
+    rc = ensure_plan(p, info.sample_rate, info.channels, info.fmt);
+    if (rc != BB_OK) return rc;
+    if (bb_sync(p->ctx) != BB_OK) return fail(p, BB_ERR_CUDA, bb_last_error(p->ctx));
+    if (ensure_pinned(p, 0, info.file_bytes) != BB_OK) return fail(p, BB_ERR_OOM, "pinned staging allocation failed");
+    rc = bb::read_range_parallel(path, 0, info.file_bytes, p->pinned[0], p->read_threads);
+    if (rc != BB_OK) return fail(p, rc, std::string("cannot read ") + path);
+    if (!p->flac && bb_flac_create(p->ctx, &p->flac) != BB_OK) return fail(p, BB_ERR_OOM, "FLAC decoder state");
+    void* d_pcm = nullptr; uint64_t frames = 0;
+    rc = bb_flac_decode(p->flac, p->pinned[0], info.file_bytes, &info, &d_pcm, &frames);
+    if (rc != BB_OK) return fail(p, rc, bb_last_error(p->ctx));
+    const uint32_t B = effective_batch(p, info.frames ? info.frames : frames, info.sample_rate);      // duration hint: STREAMINFO's count
+    if (batch_used) *batch_used = B;
+    uint64_t nseg = 0, consumed = 0;
+    rc = run_piece(p, d_pcm, frames, 0, true, B, 0, sink, &nseg, &consumed, true);
+    if (rc != BB_OK) return rc;
+    if (n_segments) *n_segments = nseg;
+    return BB_OK;
+}
+
+bool is_flac(const char* path) {
+    unsigned char m[4] = {0, 0, 0, 0};
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return false;
+    const size_t n = std::fread(m, 1, 4, f);
+    std::fclose(f);
+    return n == 4 && std::memcmp(m, "fLaC", 4) == 0;
+}
+
 int process_wav(bb_pipeline* p, const char* path, uint64_t piece_frames, Sink* sink, uint64_t* n_segments, uint32_t* batch_used) {
+    if (is_flac(path)) return process_flac(p, path, sink, n_segments, batch_used);
     bb_wav_info info;
     int rc = bb_wav_probe(path, &info);
     if (rc != BB_OK) return fail(p, rc, bb_last_error(nullptr));
@@ -345,6 +381,7 @@ void bb_pipeline_destroy(bb_pipeline* p) {
     if (!p) return;
     for (auto& c : p->cache) bb_plan_destroy(c.plan);
     for (void* b : p->pinned) if (b) bb_host_free(b);
+    if (p->flac) bb_flac_destroy(p->flac);
     free_results(p);
     delete p;
 }

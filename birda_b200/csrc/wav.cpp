@@ -12,6 +12,7 @@
 #include "../../include/birda_b200.h"
 #include "rules.hpp"
 #include "guard.hpp"
+#include "pipeline_internal.hpp"
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -28,6 +29,47 @@ uint16_t rd16(const unsigned char* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 uint64_t rd64(const unsigned char* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
 int fail(int code, const std::string& m) { bb::set_tls_error(m); return code; }
 }  // namespace
+
+namespace bb {
+// bytes [off0, off0 + total) of a file into dst, cut into slices read by `threads` threads at once (pread is positional)
+int32_t read_range_parallel(const char* path, uint64_t off0, uint64_t total, void* dst, uint32_t threads) {
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return fail(BB_ERR_IO, std::string("cannot open ") + path);
+    auto read_range = [&](uint64_t lo, uint64_t hi) -> bool {
+        char* p = static_cast<char*>(dst) + lo;
+        uint64_t off = off0 + lo, left = hi - lo;
+        while (left) {
+            const ssize_t n = ::pread(fd, p, left > (1u << 30) ? (1u << 30) : (size_t)left, (off_t)off);
+            if (n <= 0) return false;
+            p += n; off += (uint64_t)n; left -= (uint64_t)n;
+        }
+        return true;
+    };
+    constexpr uint64_t kMinSlice = 4ull << 20;
+    uint64_t n = threads ? threads : 1;
+    if (n > total / kMinSlice) n = total / kMinSlice;
+    if (n > 64) n = 64;
+    bool ok = true;
+    if (n <= 1) ok = read_range(0, total);
+    else {
+        std::vector<char> good(n, 1);
+        std::vector<std::thread> th;
+        const uint64_t slice = ((total + n - 1) / n + 4095) & ~4095ull;
+        auto lo_of = [&](uint64_t i) { return i * slice < total ? i * slice : total; };
+        try {
+            for (uint64_t i = 1; i < n; ++i) th.emplace_back([&, i] { good[i] = read_range(lo_of(i), lo_of(i + 1)) ? 1 : 0; });
+        } catch (...) {                                        // could not start a thread: read what is left here
+            for (uint64_t i = th.size() + 1; i < n; ++i) good[i] = read_range(lo_of(i), lo_of(i + 1)) ? 1 : 0;
+        }
+        good[0] = read_range(0, lo_of(1)) ? 1 : 0;
+        for (auto& t : th) t.join();
+        for (char g : good) ok = ok && g;
+    }
+    ::close(fd);
+    if (!ok) return fail(BB_ERR_IO, std::string("short read from ") + path);
+    return BB_OK;
+}
+}  // namespace bb
 
 extern "C" {
 
@@ -111,42 +153,7 @@ int32_t bb_wav_read_parallel(const char* path, const bb_wav_info* info, uint64_t
     if (info->fmt == 0) return fail(BB_ERR_UNSUPPORTED_FORMAT, "unsupported sample format");
     if (first_frame > info->frames || frames > info->frames - first_frame) return fail(BB_ERR_INVALID_ARG, "frame range outside the data chunk");
     const uint64_t fb = (uint64_t)info->channels * bb::sample_bytes(info->fmt);
-    int fd = ::open(path, O_RDONLY);
-    if (fd < 0) return fail(BB_ERR_IO, std::string("cannot open ") + path);
-    const uint64_t off0 = info->data_offset + first_frame * fb, total = frames * fb;
-    auto read_range = [&](uint64_t lo, uint64_t hi) -> bool {
-        char* p = static_cast<char*>(dst) + lo;
-        uint64_t off = off0 + lo, left = hi - lo;
-        while (left) {
-            const ssize_t n = ::pread(fd, p, left > (1u << 30) ? (1u << 30) : (size_t)left, (off_t)off);
-            if (n <= 0) return false;
-            p += n; off += (uint64_t)n; left -= (uint64_t)n;
-        }
-        return true;
-    };
-    constexpr uint64_t kMinSlice = 4ull << 20;
-    uint64_t n = threads ? threads : 1;
-    if (n > total / kMinSlice) n = total / kMinSlice;
-    if (n > 64) n = 64;
-    bool ok = true;
-    if (n <= 1) ok = read_range(0, total);
-    else {
-        std::vector<char> good(n, 1);
-        std::vector<std::thread> th;
-        const uint64_t slice = ((total + n - 1) / n + 4095) & ~4095ull;
-        auto lo_of = [&](uint64_t i) { return i * slice < total ? i * slice : total; };
-        try {
-            for (uint64_t i = 1; i < n; ++i) th.emplace_back([&, i] { good[i] = read_range(lo_of(i), lo_of(i + 1)) ? 1 : 0; });
-        } catch (...) {                                        // could not start a thread: read what is left here
-            for (uint64_t i = th.size() + 1; i < n; ++i) good[i] = read_range(lo_of(i), lo_of(i + 1)) ? 1 : 0;
-        }
-        good[0] = read_range(0, lo_of(1)) ? 1 : 0;
-        for (auto& t : th) t.join();
-        for (char g : good) ok = ok && g;
-    }
-    ::close(fd);
-    if (!ok) return fail(BB_ERR_IO, std::string("short read from ") + path);
-    return BB_OK;
+    return bb::read_range_parallel(path, info->data_offset + first_frame * fb, frames * fb, dst, threads);
     BB_CATCH(nullptr)
 }
 

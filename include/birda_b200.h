@@ -402,6 +402,31 @@ int32_t bb_melspec_info(const bb_melspec*, uint32_t* bin_lo, uint32_t* n_bins, u
 int32_t bb_melspec_run(bb_melspec*, const float* d_segments, uint32_t rows, uint32_t samples, float* d_out);
 
 /* ------------------------------------------------------------------------------------------
+ * FLAC ingest (the reference decodes FLAC through symphonia on its decode thread:
+ * src/audio/decode.rs:54-128, :205-245, extension list src/pipeline/coordinator.rs:181-190).  The compressed file is
+ * what crosses PCIe; the host finds the frame boundaries, the GPU decodes (one thread per frame) into the interleaved
+ * PCM K1/K2 consume: streams of up to 16 bits -> BB_S16 (left-justified), 17..24 -> BB_S24, 32 -> BB_S32 — the values
+ * append_samples converts (symphonia presents FLAC as left-justified S32, decode.rs:386-402).  Every frame's CRC-16 is
+ * verified on the device.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t sample_rate, channels, bits_per_sample;
+    uint32_t min_block, max_block, min_frame_bytes, max_frame_bytes;
+    uint64_t frames;               /* samples per channel from STREAMINFO (0 = unknown)   */
+    uint64_t first_frame_offset;   /* where the metadata blocks end                        */
+    uint64_t file_bytes;
+    int32_t  fmt;                  /* bb_sample_fmt of the decoded PCM                     */
+} bb_flac_info;
+typedef struct bb_flac bb_flac;
+int32_t bb_flac_probe(const char* path, bb_flac_info* out);
+int32_t bb_flac_probe_bytes(const void* bytes, uint64_t n_bytes, bb_flac_info* out);
+int32_t bb_flac_create(bb_ctx*, bb_flac** out);
+void    bb_flac_destroy(bb_flac*);
+/* the whole compressed file in host memory -> *d_pcm (device, interleaved info->fmt, valid until the next decode on this
+ * object), *frames_out samples per channel.  Returns once the decode has completed. */
+int32_t bb_flac_decode(bb_flac*, const void* file_bytes, uint64_t n_bytes, const bb_flac_info* info, void** d_pcm, uint64_t* frames_out);
+
+/* ------------------------------------------------------------------------------------------
  * Stand-in classifier (benches and tests; NOT a model, nothing of the reference's is replaced by it): the I/O contract
  * of BirdClassifier::predict_batch (src/inference/classifier.rs:469-582) — [batch, samples] f32 windows on the device
  * in, [batch, classes] f32 logits on the device out — with trivial arithmetic (48 band energies times a fixed
