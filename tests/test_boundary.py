@@ -231,8 +231,8 @@ def test_every_extern_c_body_is_guarded():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     unguarded = []
     # one-line delegations to a guarded implementation, and a getter that only copies three integers
-    nothrow = {"bb_ctx_create", "bb_ctx_create_on_stream", "bb_melspec_info"}
-    for fn in ("capi.cu", "pipeline.cpp", "pool.cpp", "wav.cpp", "mask.cpp", "watchdog.cpp", "k5_melspec.cu", "flac.cpp"):
+    nothrow = {"bb_ctx_create", "bb_ctx_create_on_stream", "bb_melspec_info", "bb_wav_read", "bb_standin_classify", "bb_standin_weights"}
+    for fn in ("capi.cu", "pipeline.cpp", "pool.cpp", "wav.cpp", "mask.cpp", "watchdog.cpp", "k5_melspec.cu", "k6_flac.cu", "standin.cu"):
         p = os.path.join(root, "birda_b200", "csrc", fn)
         if not os.path.exists(p):
             continue
