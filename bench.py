@@ -507,7 +507,9 @@ def run_c5(args):
     if world > 1:
         dist.barrier()
     paths = [os.path.join(directory, f"file_{i:04d}.wav") for i in range(args.files)]
-    mine = shard_files([seconds] * args.files, world)[rank]
+    # longest-processing-time-first by BYTES: the files are equally long, what a rank pays for is their PCM (16 kHz mono
+    # to 96 kHz stereo: 19 - 230 MB) — by duration alone a round robin would hand one rank all the stereo files
+    mine = shard_files([float(os.path.getsize(p)) for p in paths], world)[rank]
     my_paths = [paths[i] for i in mine]
     my_bytes = sum(os.path.getsize(p) for p in my_paths)
     g = torch.Generator(device=device); g.manual_seed(5)

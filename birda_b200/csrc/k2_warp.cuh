@@ -37,6 +37,9 @@ constexpr int kMaxStages = 8;
 #define BB_K2W_TABLE_RADIX 9
 #endif
 BB_HD constexpr bool tw_table_mode(int radix) { return radix >= BB_K2W_TABLE_RADIX; }
+#ifndef BB_K2W_SPLIT_UNROLL
+#define BB_K2W_SPLIT_UNROLL BB_K2W_UNROLL
+#endif
 #define BB_PRAGMA(x) _Pragma(#x)
 #define BB_UNROLL_N(n) BB_PRAGMA(unroll n)
 
@@ -315,7 +318,7 @@ BB_HD uint4 ld_entry128(const uint4* p) {
 template <class C, class TB>
 BB_HD void split_pass(const typename Mem<C>::T* __restrict__ A, typename Mem<C>::T* __restrict__ B, const TB& T,
                       int L, int lane, int nl) {
-BB_UNROLL_N(BB_K2W_UNROLL)
+BB_UNROLL_N(BB_K2W_SPLIT_UNROLL)
     for (int idx = lane; idx < L; idx += nl) {
         const uint4 e = ld_entry128(T.sidx + idx);      // the tables live in shared memory in every kernel that runs this pass
         const unsigned fl = e.w;

@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "guard.hpp"
 #include "k2_warp.cuh"
+#include <cuda.h>               // CUtensorMap and its enums only: the encoder is looked up at run time (cudaGetDriverEntryPoint)
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -349,6 +351,143 @@ mel_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ K5b, TMA-fed
+// The same GEMM with its operands moved by the TMA unit: one elected thread issues four cp.async.bulk.tensor.2d boxes
+// per K chunk (P hi, P lo, W hi, W lo: [rows, 32 tf32] with the 128-byte swizzle the UMMA descriptors expect) and
+// arms the stage's mbarrier with the byte count; frames past the end of the launch are zero-filled by the unit.  No
+// thread touches operand data, the four epilogue warps only wait for the accumulator, and stages are as deep as
+// shared memory allows.  SASS: UTMALDG.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int32_t x, int32_t y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 2)
+mel_gemm_tma_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmW) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = kBM * 128, b_bytes = p.n_mels * 128;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    __shared__ __align__(8) uint64_t s_full[kGemmMaxStages], s_empty[kGemmMaxStages], s_done;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t nk = p.kpad / kBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < kGemmMaxStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        mbar_init(&s_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kBM;
+
+    if (warp < 4) {
+        if (tid == 0) {
+            // ===== producer: one thread, TMA
+            const uint32_t S = p.stages;
+            for (uint32_t kc = 0; kc < nk; ++kc) {
+                const uint32_t s = kc % S;
+                if (kc >= S) mbar_wait(&s_empty[s], ((kc / S) & 1u) ^ 1u);       // the MMAs that read this slot have retired
+                const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                mbar_expect_tx(&s_full[s], stage_bytes);
+                tma_load_2d(st, &tmP, (int32_t)(kc * 64), (int32_t)tile0, &s_full[s]);
+                tma_load_2d(st + a_bytes, &tmP, (int32_t)(kc * 64 + 32), (int32_t)tile0, &s_full[s]);
+                tma_load_2d(st + 2 * a_bytes, &tmW, (int32_t)(kc * 64), 0, &s_full[s]);
+                tma_load_2d(st + 2 * a_bytes + b_bytes, &tmW, (int32_t)(kc * 64 + 32), 0, &s_full[s]);
+            }
+        }
+        __syncwarp();
+        // ===== epilogue: TMEM -> registers -> scaling -> [rows, n_mels, n_frames]
+        mbar_wait(&s_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t fr = tile0 + (uint32_t)(warp * 32 + lane);             // this thread's frame = TMEM lane
+        const bool live = fr < p.nframes;
+        const uint64_t f = p.frame0 + fr;
+        const uint64_t row = f / p.n_frames;
+        const uint32_t t = (uint32_t)(f - row * p.n_frames);
+        float* __restrict__ o = p.out + (row * p.n_mels) * (uint64_t)p.n_frames + t;
+        for (uint32_t c0 = 0; c0 < p.n_mels; c0 += 16) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float v = __uint_as_float(r[j]);
+                    if (p.log_mode == 1) v = logf(v + p.log_eps);
+                    else if (p.log_mode == 2) v = 10.0f * log10f(fmaxf(v, p.log_eps));
+                    o[(uint64_t)(c0 + j) * p.n_frames] = v;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===== MMA issuer: one elected lane
+        if (lane == 0) {
+            for (uint32_t kc = 0; kc < nk; ++kc) {
+                const uint32_t s = kc % p.stages, ph = (kc / p.stages) & 1u;
+                mbar_wait(&s_full[s], ph);                     // the unit has written all four boxes of the stage
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+#pragma unroll
+                for (uint32_t k4 = 0; k4 < 4; ++k4) {
+                    const uint64_t a_hi = umma_desc(base + k4 * 32u), a_lo = umma_desc(base + a_bytes + k4 * 32u);
+                    const uint64_t b_hi = umma_desc(base + 2 * a_bytes + k4 * 32u), b_lo = umma_desc(base + 2 * a_bytes + b_bytes + k4 * 32u);
+                    umma_tf32(tmem, a_hi, b_hi, p.idesc, (kc | k4) != 0u ? 1u : 0u);
+                    umma_tf32(tmem, a_lo, b_hi, p.idesc, 1u);
+                    umma_tf32(tmem, a_hi, b_lo, p.idesc, 1u);
+                }
+                umma_commit(&s_empty[s]);
+            }
+            umma_commit(&s_done);
+        }
+        __syncwarp();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart statically, not libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// [rows, cols] f32 row-major, boxes of [box_rows, 32] with the 128-byte swizzle; rows past the end read as zeros
+bool make_tile_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || box_rows == 0 || box_rows > 256) return false;
+    const cuuint64_t dims[2] = {cols, rows}, strides[1] = {cols * sizeof(float)};
+    const cuuint32_t box[2] = {32, box_rows}, estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 }  // namespace bb
 
@@ -477,8 +616,20 @@ int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, ui
     const size_t stage_bytes = 2 * (size_t)kBM * 128 + 2 * (size_t)cfg.n_mels * 128;
     gp.stages = 2;
     if (2 * (2 * stage_bytes + 2048) > 227 * 1024) { gp.stages = (uint32_t)((220 * 1024) / stage_bytes); if (gp.stages > kGemmMaxStages) gp.stages = kGemmMaxStages; }
+    // operands by TMA (default) when the W tiles keep their 1024-byte alignment; BIRDA_K5_CPASYNC=1 keeps the cp.async producers
+    bool use_tma = cfg.n_mels % 8 == 0 && encode_tiled_fn() != nullptr;
+    if (const char* e = std::getenv("BIRDA_K5_CPASYNC")) if (e[0] == '1') use_tma = false;
+    CUtensorMap tmW;
+    if (use_tma && !make_tile_map(&tmW, m->d_w, cfg.n_mels, 2ull * m->kpad, cfg.n_mels)) use_tma = false;
+    if (use_tma) {                         // nobody stages by hand: as many stages as two CTAs per SM allow, at least 3 when one fits
+        gp.stages = (uint32_t)((113 * 1024 - 1024) / stage_bytes);
+        if (gp.stages < 3) gp.stages = (uint32_t)((220 * 1024) / stage_bytes);
+        if (gp.stages > kGemmMaxStages) gp.stages = kGemmMaxStages;
+        if (gp.stages < 2) use_tma = false;
+    }
     const size_t gemm_smem = (size_t)gp.stages * stage_bytes + 1024;
-    BB_CUDA_OK(c, cudaFuncSetAttribute(mel_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    if (use_tma) BB_CUDA_OK(c, cudaFuncSetAttribute(mel_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    else BB_CUDA_OK(c, cudaFuncSetAttribute(mel_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
     for (uint64_t r0 = 0; r0 < rows; r0 += rows_per_chunk) {
         const uint64_t nr = rows - r0 < rows_per_chunk ? rows - r0 : rows_per_chunk;
         const uint64_t nframes = nr * cfg.n_frames;
@@ -509,7 +660,13 @@ int32_t bb_melspec_run(bb_melspec* m, const float* d_segments, uint32_t rows, ui
 #undef BB_STFT2
         }
         gp.frame0 = sp.frame0; gp.nframes = nframes;
-        mel_gemm_kernel<<<(unsigned)((nframes + kBM - 1) / kBM), kGemmThreads, gemm_smem, c->stream>>>(gp);
+        CUtensorMap tmP;
+        if (use_tma && make_tile_map(&tmP, m->d_P, nframes, 2ull * m->kpad, kBM))
+            mel_gemm_tma_kernel<<<(unsigned)((nframes + kBM - 1) / kBM), kGemmThreads, gemm_smem, c->stream>>>(gp, tmP, tmW);
+        else {
+            if (use_tma) BB_SET_ERR(c, BB_ERR_INTERNAL, "tensor map for the power spectra could not be encoded");
+            mel_gemm_kernel<<<(unsigned)((nframes + kBM - 1) / kBM), kGemmThreads, gemm_smem, c->stream>>>(gp);
+        }
         BB_CUDA_OK(c, cudaGetLastError());
         c->launches += 2;
     }

@@ -8,7 +8,7 @@ mkdir -p $D
 cd $ROOT/birda_b200/csrc
 INC=""
 if [ -n "$3" ]; then INC="-include $3"; fi
-for f in capi k1_pack k2_resample k2_warp k3_post k4_dense k5_melspec; do
+for f in capi k1_pack k2_resample k2_warp k3_post k4_dense k5_melspec standin k6_flac; do
   if [ "$f" = "k2_warp" ] || [ ! -f $D/$f.o ]; then
     X=""; if [ "$f" = "k2_warp" ]; then X="$INC"; fi
     nvcc $2 $X -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -diag-suppress 20011,20014 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O2,-fno-fast-math -Xptxas -v -c $f.cu -o $D/$f.o 2> $D/$f.log &
