@@ -189,3 +189,86 @@ extern "C" {
     pub fn bb_pool_process_wavs(p: *mut bb_pool, paths: *const *const c_char, n_files: u32, results: *mut bb_pool_result) -> i32;
     pub fn bb_pool_free_results(results: *mut bb_pool_result, n: u32);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Round-2 additions of the C ABI (include/birda_b200.h): range-filter label projection, watchdog
+// seam, FLAC ingest, pool options.  Untested source like the rest of this file (no Rust toolchain
+// in the build image); the C side is exercised by tests/test_boundary.py, tests/test_flac.py and
+// tests/test_gpu_pipeline.py.
+pub const BB_ERR_TIMEOUT: i32 = -11;
+pub const BB_S24: i32 = 4; // 3-byte packed PCM, converted as the S32 `<< 8` values symphonia presents
+
+pub type bb_batch_hook = Option<unsafe extern "C" fn(user: *mut c_void, batch_rows: u32, valid_rows: u32, first_segment: u64)>;
+pub type bb_watchdog_fn = Option<unsafe extern "C" fn(user: *mut c_void, timeout_secs: u64, batch_size: u32)>;
+
+#[repr(C)]
+pub struct bb_watchdog {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct bb_flac {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct bb_flac_info {
+    pub sample_rate: u32,
+    pub channels: u32,
+    pub bits_per_sample: u32,
+    pub min_block: u32,
+    pub max_block: u32,
+    pub min_frame_bytes: u32,
+    pub max_frame_bytes: u32,
+    pub frames: u64,
+    pub first_frame_offset: u64,
+    pub file_bytes: u64,
+    pub fmt: i32,
+}
+
+extern "C" {
+    // src/inference/geomodel.rs:58-87, :140-157 -> the dense [C] mask K3 reads (NaN = no geomodel entry)
+    pub fn bb_mask_build(classifier_labels: *const *const c_char, n_classifier: u32,
+                         geomodel_labels: *const *const c_char, n_geomodel: u32,
+                         score_species: *const *const c_char, score_values: *const f32, n_scores: u32,
+                         mask: *mut f32, mapped: *mut u32, unmatched: *mut u32) -> i32;
+    pub fn bb_rule_scientific_name_len(label: *const c_char) -> u32;
+    // src/pipeline/processor.rs:194-211
+    pub fn bb_rule_inference_timeout_secs(env_value: *const c_char) -> u64;
+    // src/gpu/watchdog.rs:22-66
+    pub fn bb_watchdog_start(timeout_ms: u64, batch_size: u32, on_fire: bb_watchdog_fn, user: *mut c_void, out: *mut *mut bb_watchdog) -> i32;
+    pub fn bb_watchdog_cancel(w: *mut bb_watchdog);
+    // the per-batch seam of the library's per-file loop (processor.rs:263-277)
+    pub fn bb_pipeline_set_batch_hooks(p: *mut bb_pipeline, before: bb_batch_hook, after: bb_batch_hook, user: *mut c_void);
+    pub fn bb_pipeline_set_batch_timeout(p: *mut bb_pipeline, timeout_ms: u64, on_fire: bb_watchdog_fn, user: *mut c_void);
+    pub fn bb_pipeline_set_read_threads(p: *mut bb_pipeline, threads: u32);
+    // FLAC decoded on the GPU (src/audio/decode.rs:54-128 for that container)
+    pub fn bb_flac_probe(path: *const c_char, out: *mut bb_flac_info) -> i32;
+    pub fn bb_flac_create(ctx: *mut bb_ctx, out: *mut *mut bb_flac) -> i32;
+    pub fn bb_flac_destroy(f: *mut bb_flac);
+    pub fn bb_flac_decode(f: *mut bb_flac, file_bytes: *const c_void, n_bytes: u64, info: *const bb_flac_info,
+                          d_pcm: *mut *mut c_void, frames_out: *mut u64) -> i32;
+    // pool: a classifier that queues on its worker's stream (ORT user_compute_stream) needs no waits around a batch
+    pub fn bb_pool_worker_ctx(p: *mut bb_pool, worker: u32) -> *mut bb_ctx;
+    pub fn bb_pool_set_stream_ordered(p: *mut bb_pool, on: i32);
+    pub fn bb_ctx_set_blocking_sync(ctx: *mut bb_ctx, on: i32);
+    pub fn bb_plan_describe(plan: *const bb_plan, buf: *mut c_char, buf_len: u32) -> i32;
+}
+
+/// `start_inference_watchdog` (src/gpu/watchdog.rs:22-52) over the library's timer: dropping the guard cancels it.
+pub struct WatchdogGuard(*mut bb_watchdog);
+impl WatchdogGuard {
+    pub fn start(timeout: std::time::Duration, batch_size: usize) -> Option<Self> {
+        let mut w: *mut bb_watchdog = std::ptr::null_mut();
+        // on_fire = None: the reference's behaviour (FATAL block on stderr, exit status 1)
+        let rc = unsafe { bb_watchdog_start(timeout.as_millis() as u64, batch_size as u32, None, std::ptr::null_mut(), &mut w) };
+        if rc == 0 { Some(Self(w)) } else { None }
+    }
+}
+impl Drop for WatchdogGuard {
+    fn drop(&mut self) {
+        unsafe { bb_watchdog_cancel(self.0) }
+    }
+}
+// the guard is only ever dropped, never shared: same contract as the reference's (watchdog.rs:86-91)
+unsafe impl Send for WatchdogGuard {}
