@@ -5,7 +5,8 @@
 // value converted is sample / 2^(bps-1) (decode.rs:386-402).  FLAC is lossless, so the decoded PCM is a property of
 // the file, not of the decoder: here the compressed file crosses PCIe (roughly half the bytes of its PCM), the host
 // only finds the frame boundaries, and the GPU decodes — one thread per frame (frames are independent, the subframes of
-// a frame are not: each starts where the previous one ends) — into the interleaved buffers K1/K2 already consume:
+// a frame are not: each starts where the previous one ends; the lanes of a warp decode 32 frames in lockstep through a
+// flat, loop-free per-sample path) — into the interleaved buffers K1/K2 already consume:
 // 16-bit and narrower streams -> BB_S16 (left-shifted to 16 bits), 17..24-bit -> BB_S24 (packed), 32-bit -> BB_S32.
 //
 // Format: RFC 9639.  Every frame's CRC-16 is checked on the device; a mismatch (corrupt file, or a false sync that
@@ -18,6 +19,9 @@
 #include <string>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <vector>
 
 namespace bb {
@@ -86,64 +90,104 @@ __host__ __device__ inline bool parse_header(const uint8_t* p, uint64_t n, uint3
 }
 
 // ---------------------------------------------------------------------------------------------- device decode
+// MSB-first bit reader over aligned 32-bit words: the top n bits of acc are valid; a refill appends one big-endian word
+// (one load + one byte permute) whenever fewer than the requested bits are left, so every request of up to 33 bits is
+// one predicated refill — no loops on the common path, which is what lets the lanes of a warp (one frame each) run
+// the per-sample code in lockstep.  Reads past the end of the frame see the next frame's bytes (the file buffer has
+// slack after its end); the CRC-16 check has already vouched for the frame.
 struct BitReader {
-    const uint8_t* p; const uint8_t* end; uint64_t acc; int n;      // the top n bits of acc are valid
-    __device__ __forceinline__ void refill() {
-        while (n <= 56 && p < end) { acc |= (uint64_t)__ldg(p++) << (56 - n); n += 8; }
+    const uint32_t* w; uint64_t acc; int n;
+    __device__ __forceinline__ void init(const uint8_t* p) {
+        acc = 0; n = 0;
+        while (reinterpret_cast<uintptr_t>(p) & 3) { acc |= (uint64_t)__ldg(p++) << (56 - n); n += 8; }      // up to three head bytes
+        w = reinterpret_cast<const uint32_t*>(p);
     }
-    __device__ __forceinline__ uint32_t read(int k) {               // k <= 32
+    __device__ __forceinline__ void need(int bits) {                  // bits <= 32; afterwards n >= bits
+        if (n < bits) { acc |= (uint64_t)__byte_perm(__ldg(w++), 0, 0x0123) << (32 - n); n += 32; }
+    }
+    __device__ __forceinline__ uint32_t read(int k) {                 // k <= 32
         if (k == 0) return 0;
-        if (n < k) refill();
+        need(k);
         const uint32_t v = (uint32_t)(acc >> (64 - k));
         acc <<= k; n -= k;
         return v;
     }
-    __device__ __forceinline__ int32_t read_signed(int k) {          // k <= 32
+    __device__ __forceinline__ int32_t read_signed(int k) {
         if (k == 0) return 0;
         const uint32_t v = read(k);
         return k == 32 ? (int32_t)v : (int32_t)(v << (32 - k)) >> (32 - k);
     }
-    __device__ __forceinline__ int64_t read_signed_wide(int k) {     // k <= 33 (side channel of a 32-bit stream)
-        if (k <= 32) return read_signed(k);
-        const int64_t hi = read_signed(k - 32);
-        return (hi << 32) | read(32);
-    }
-    __device__ __forceinline__ uint32_t unary() {                    // zeros up to and including the terminating one
-        uint32_t q = 0;
-        for (;;) {
-            if (n == 0) { refill(); if (n == 0) return 0xFFFFFFFFu; }
-            const int z = acc ? __clzll((long long)acc) : 64;
-            if (z < n) { acc <<= (z + 1); n -= z + 1; return q + (uint32_t)z; }
-            q += (uint32_t)n; acc = 0; n = 0;
+    __device__ __forceinline__ uint32_t unary() {                     // zeros before the terminating one (which is consumed)
+        need(32);
+        uint32_t hi = (uint32_t)(acc >> 32);
+        if (hi != 0) { const int z = __clz((int)hi); acc <<= (z + 1); n -= z + 1; return (uint32_t)z; }
+        uint32_t q = 0;                                               // 32 or more zeros: rare
+        for (int guard = 0; guard < (1 << 16); ++guard) {
+            q += 32; acc <<= 32; n -= 32;
+            need(32);
+            hi = (uint32_t)(acc >> 32);
+            if (hi != 0) { const int z = __clz((int)hi); acc <<= (z + 1); n -= z + 1; return q + (uint32_t)z; }
         }
+        return 0xFFFFFFFFu;
     }
-    __device__ __forceinline__ bool overrun() const { return p >= end && n < 0; }
 };
 
 struct FrameMeta { int32_t mode; int32_t status; };      // status: 0 ok, else what failed
 
 __constant__ uint16_t c_crc16[256];
 
-// One thread per frame: header, subframes (into the planar int32 scratch of the frame), CRC-16.
-__global__ void __launch_bounds__(64)
-flac_decode_kernel(const uint8_t* __restrict__ file, const FrameRef* __restrict__ frames, uint32_t nframes, uint32_t si_rate, uint32_t si_bps,
-                   uint32_t channels, int32_t* __restrict__ scratch, FrameMeta* __restrict__ meta) {
+// CRC-16 of every frame, one thread per frame: the same short loop for every thread of a warp (they differ only in
+// the frame length), so this part runs at full SIMT width.
+__global__ void __launch_bounds__(128)
+flac_crc_kernel(const uint8_t* __restrict__ file, const FrameRef* __restrict__ frames, uint32_t nframes, FrameMeta* __restrict__ meta) {
+    __shared__ uint16_t tab[256];                    // lanes look up different entries: shared memory, not the constant cache
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = c_crc16[i];
+    __syncthreads();
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     const FrameRef fr = frames[f];
     const uint8_t* base = file + fr.offset;
+    const uint32_t len = fr.bytes >= 2 ? fr.bytes - 2 : 0;
+    uint32_t c = 0, i = 0;
+    auto step = [&](uint32_t byte) { c = ((c << 8) & 0xFFFFu) ^ tab[((c >> 8) ^ byte) & 0xFF]; };
+    for (; i < len && ((reinterpret_cast<uintptr_t>(base + i)) & 3); ++i) step(__ldg(base + i));
+    for (; i + 4 <= len; i += 4) {                   // aligned words: one load per four table steps
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + i));
+        step(w & 0xFF); step((w >> 8) & 0xFF); step((w >> 16) & 0xFF); step(w >> 24);
+    }
+    for (; i < len; ++i) step(__ldg(base + i));
     FrameMeta m{0, 0};
+    if (fr.bytes < 2 || c != (((uint32_t)base[fr.bytes - 2] << 8) | base[fr.bytes - 1])) m.status = 2;
+    meta[f] = m;
+}
+
+// The entropy decode: one LANE per frame, 32 frames per warp.  A frame's bit stream is serial, so the parallelism is
+// across frames; for the lanes of a warp to stay together the per-sample code has no data-dependent loops or early
+// exits: ONE flat loop over the samples of a subframe (partition boundaries are a per-lane counter, not a nested loop),
+// a bit reader that refills by predicated word appends, the unary run from one clz, history in registers (fixed
+// predictors) or a thread-local ring (LPC), eight samples per pair of 16-byte stores.  Lanes diverge only in the
+// subframe headers (once per 4 096 samples) and on rare events (escape partitions, runs of 32+ zeros).  First version
+// (nested loops, byte-wise refills): 6.2 ms for a 10-minute stereo file, issue-bound with the lanes serialised.
+__global__ void __launch_bounds__(128)
+flac_decode_kernel(const uint8_t* __restrict__ file, const FrameRef* __restrict__ frames, uint32_t nframes, uint32_t si_rate, uint32_t si_bps,
+                   uint32_t channels, int32_t* __restrict__ scratch, FrameMeta* __restrict__ meta, uint32_t lanes_per_warp) {
+    // lanes_per_warp frames per warp (the other lanes idle): a short file has too few frames to hide the latency of
+    // each warp's serial chain with 32 per warp (a 10-minute stereo file is 202 warps on 148 SMs), so the launcher
+    // trades SIMT width for warps until there are several per SM
+    const uint32_t lane = threadIdx.x & 31u;
+    if (lane >= lanes_per_warp) return;
+    const uint32_t f = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * lanes_per_warp + lane;
+    if (f >= nframes) return;
+    const FrameRef fr = frames[f];
+    const uint8_t* base = file + fr.offset;
+    FrameMeta m = meta[f];
+    if (m.status) return;
     Header h;
     if (!parse_header(base, fr.bytes, si_rate, si_bps, &h) || h.blocksize != fr.blocksize || h.channels != channels || fr.bytes < h.header_bytes + 2) {
         m.status = 1; meta[f] = m; return;
     }
     m.mode = h.mode;
-    {   // CRC-16 of everything but the last two bytes
-        uint32_t c = 0;
-        for (uint32_t i = 0; i + 2 < fr.bytes; ++i) c = ((c << 8) & 0xFFFFu) ^ c_crc16[((c >> 8) ^ __ldg(base + i)) & 0xFF];
-        if (c != (((uint32_t)base[fr.bytes - 2] << 8) | base[fr.bytes - 1])) { m.status = 2; meta[f] = m; return; }
-    }
-    BitReader br{base + h.header_bytes, base + fr.bytes - 2, 0, 0};
+    BitReader br; br.init(base + h.header_bytes);
     const uint32_t bs = h.blocksize;
     int32_t* __restrict__ out0 = scratch + fr.first_sample * channels;
     for (uint32_t ch = 0; ch < channels && m.status == 0; ++ch) {
@@ -155,67 +199,92 @@ flac_decode_kernel(const uint8_t* __restrict__ file, const FrameRef* __restrict_
         if (br.read(1)) { const uint32_t u = br.unary(); if (u > 31) { m.status = 3; break; } wasted = (int)u + 1; }
         bps -= wasted;
         if (bps <= 0 || bps > 32) { m.status = 3; break; }      // a 33-bit side channel (32-bit stereo-decorrelated stream) does not fit the scratch
-        int order = 0;
         if (type == 0) {                                   // CONSTANT
-            const int32_t v = (int32_t)br.read_signed_wide(bps);
+            const int32_t v = (int32_t)((uint32_t)br.read_signed(bps) << wasted);
             for (uint32_t i = 0; i < bs; ++i) s[i] = v;
-        } else if (type == 1) {                            // VERBATIM
-            for (uint32_t i = 0; i < bs; ++i) s[i] = (int32_t)br.read_signed_wide(bps);
-        } else if ((type & 0x38) == 0x08 || (type & 0x20)) {
-            const bool lpc = (type & 0x20) != 0;
-            order = lpc ? (int)(type & 31) + 1 : (int)(type & 7);
-            if ((!lpc && order > 4) || (uint32_t)order > bs) { m.status = 3; break; }
-            for (int i = 0; i < order; ++i) s[i] = (int32_t)br.read_signed_wide(bps);
-            int coef[32]; int shift = 0;
-            if (lpc) {
-                const int prec = (int)br.read(4) + 1;
-                if (prec == 16) { m.status = 3; break; }
-                shift = br.read_signed(5);
-                if (shift < 0) { m.status = 3; break; }
-                for (int j = 0; j < order; ++j) coef[j] = br.read_signed(prec);
-            }
-            // residual
+            continue;
+        }
+        const bool verbatim = type == 1, lpc = (type & 0x20) != 0;
+        if (!verbatim && !lpc && (type & 0x38) != 0x08) { m.status = 3; break; }
+        const int order = verbatim ? 0 : lpc ? (int)(type & 31) + 1 : (int)(type & 7);
+        if ((!lpc && order > 4) || (uint32_t)order > bs) { m.status = 3; break; }
+        int32_t hist[32];
+        for (int i = 0; i < order; ++i) { const int32_t v = br.read_signed(bps); hist[i] = v; s[i] = (int32_t)((uint32_t)v << wasted); }
+        int coef[32]; int shift = 0; bool wide = false;
+        if (lpc) {
+            const int prec = (int)br.read(4) + 1;
+            if (prec == 16) { m.status = 3; break; }
+            shift = br.read_signed(5);
+            if (shift < 0) { m.status = 3; break; }
+            for (int j = 0; j < order; ++j) coef[j] = br.read_signed(prec);
+            wide = bps + prec + (32 - __clz(order)) > 32;              // the sums may leave 32 bits (libFLAC's rule)
+        }
+        int32_t p1 = order >= 1 ? hist[order - 1] : 0, p2 = order >= 2 ? hist[order - 2] : 0,
+                p3 = order >= 3 ? hist[order - 3] : 0, p4 = order >= 4 ? hist[order - 4] : 0;
+        int c1 = 0, c2 = 0, c3 = 0, c4 = 0;                            // fixed predictors as four coefficients
+        if (!lpc) {
+            if (order == 1) { c1 = 1; } else if (order == 2) { c1 = 2; c2 = -1; } else if (order == 3) { c1 = 3; c2 = -3; c3 = 1; }
+            else if (order == 4) { c1 = 4; c2 = -6; c3 = 4; c4 = -1; }
+        }
+        // residual coding: verbatim samples are read like an escape partition of `bps` bits with no predictor
+        int pbits = 4; uint32_t esc = 15u, part_len = bs, next_boundary = 0;
+        if (!verbatim) {
             const uint32_t method = br.read(2);
             if (method > 1) { m.status = 3; break; }
-            const int pbits = method ? 5 : 4; const uint32_t esc = method ? 31u : 15u;
+            pbits = method ? 5 : 4; esc = method ? 31u : 15u;
             const uint32_t porder = br.read(4);
             if ((bs >> porder) << porder != bs || (bs >> porder) < (uint32_t)order) { m.status = 3; break; }
-            uint32_t i = (uint32_t)order;
-            for (uint32_t part = 0; part < (1u << porder) && m.status == 0; ++part) {
-                const uint32_t cnt = (bs >> porder) - (part == 0 ? (uint32_t)order : 0u);
-                const uint32_t k = br.read(pbits);
-                const uint32_t stop = i + cnt;
-                if (k == esc) {
-                    const int nb = (int)br.read(5);
-                    for (; i < stop; ++i) s[i] = br.read_signed(nb);
-                } else {
-                    for (; i < stop; ++i) {
-                        const uint32_t q = br.unary();
-                        if (q == 0xFFFFFFFFu) { m.status = 4; break; }
-                        const uint32_t u = (q << k) | br.read((int)k);
-                        s[i] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
-                    }
-                }
+            part_len = bs >> porder;
+        }
+        uint32_t k = 0; int raw_bits = verbatim ? bps : -1;            // raw_bits >= 0: samples of this partition are raw
+        uint32_t hpos = (uint32_t)order;
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(s) & 15) == 0;
+        int32_t g[8];                                                  // the 32-byte group being filled
+#pragma unroll
+        for (int t = 0; t < 8; ++t) g[t] = 0;
+        if (vec_ok) for (uint32_t t = (uint32_t)order & ~7u; t < (uint32_t)order; ++t) g[t & 7u] = s[t];
+        for (uint32_t i = (uint32_t)order; i < bs; ++i) {
+            if (!verbatim && (i == (uint32_t)order || i == next_boundary)) {   // a partition starts here
+                if (i == (uint32_t)order) next_boundary = part_len; else next_boundary += part_len;
+                k = br.read(pbits);
+                raw_bits = -1;
+                if (k == esc) raw_bits = (int)br.read(5);
             }
-            if (m.status) break;
-            // prediction: residuals in s[order..) become samples in place
+            int32_t r;
+            if (raw_bits >= 0) r = br.read_signed(raw_bits);
+            else {
+                const uint32_t q = br.unary();
+                if (q == 0xFFFFFFFFu) { m.status = 4; break; }
+                const uint32_t u = (q << k) | br.read((int)k);
+                r = (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+            }
+            int32_t v;
             if (!lpc) {
-                switch (order) {
-                    case 0: break;
-                    case 1: for (uint32_t t = 1; t < bs; ++t) s[t] += s[t - 1]; break;
-                    case 2: for (uint32_t t = 2; t < bs; ++t) s[t] += 2 * s[t - 1] - s[t - 2]; break;
-                    case 3: for (uint32_t t = 3; t < bs; ++t) s[t] += 3 * s[t - 1] - 3 * s[t - 2] + s[t - 3]; break;
-                    default: for (uint32_t t = 4; t < bs; ++t) s[t] += 4 * s[t - 1] - 6 * s[t - 2] + 4 * s[t - 3] - s[t - 4]; break;
-                }
+                v = r + c1 * p1 + c2 * p2 + c3 * p3 + c4 * p4;
+                p4 = p3; p3 = p2; p2 = p1; p1 = v;
             } else {
-                for (uint32_t t = (uint32_t)order; t < bs; ++t) {
+                if (wide) {
                     long long acc = 0;
-                    for (int j = 0; j < order; ++j) acc += (long long)coef[j] * (long long)s[t - 1 - j];
-                    s[t] += (int32_t)(acc >> shift);
+                    for (int j = 0; j < order; ++j) acc += (long long)coef[j] * (long long)hist[(hpos - 1 - (uint32_t)j) & 31u];
+                    v = r + (int32_t)(acc >> shift);
+                } else {
+                    int32_t acc = 0;
+                    for (int j = 0; j < order; ++j) acc += coef[j] * hist[(hpos - 1 - (uint32_t)j) & 31u];
+                    v = r + (acc >> shift);
                 }
+                hist[hpos & 31u] = v; ++hpos;
             }
-        } else { m.status = 3; break; }
-        if (wasted) for (uint32_t i = 0; i < bs; ++i) s[i] = (int32_t)((uint32_t)s[i] << wasted);
+            const int32_t o = (int32_t)((uint32_t)v << wasted);
+            if (!vec_ok) { s[i] = o; continue; }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) if ((i & 7u) == (uint32_t)t) g[t] = o;
+            if ((i & 7u) == 7u) {
+                *reinterpret_cast<int4*>(s + i - 7) = make_int4(g[0], g[1], g[2], g[3]);
+                *reinterpret_cast<int4*>(s + i - 3) = make_int4(g[4], g[5], g[6], g[7]);
+            }
+        }
+        if (m.status) break;
+        if (vec_ok) for (uint32_t t = bs & ~7u; t < bs; ++t) s[t] = g[t & 7u];      // the last, partial group
     }
     meta[f] = m;
 }
@@ -273,7 +342,7 @@ int flac_fail(bb_ctx* c, int code, const std::string& m) { if (c) c->last_error 
 // tests cannot yield wrong samples silently.
 int index_frames(const uint8_t* p, uint64_t n, const bb_flac_info& info, std::vector<FrameRef>* out, std::string* err) {
     out->clear();
-    uint64_t pos = info.first_frame_offset, sample = 0;
+    uint64_t pos = info.first_frame_offset, sample = 0, prev_len = 0;
     Header h;
     if (pos >= n) return BB_OK;                          // no audio frames
     if (!parse_header(p + pos, n - pos, info.sample_rate, info.bits_per_sample, &h)) { *err = "no FLAC frame where the metadata ends"; return BB_ERR_IO; }
@@ -282,18 +351,25 @@ int index_frames(const uint8_t* p, uint64_t n, const bb_flac_info& info, std::ve
         const uint64_t first = h.variable ? h.number : sample;
         if (first != sample) { *err = "frame numbers are not contiguous"; return BB_ERR_IO; }
         const uint64_t next_number = h.variable ? sample + h.blocksize : h.number + 1;
-        // search for the header of the next frame
-        uint64_t q = pos + h.header_bytes + 2;
-        if (info.min_frame_bytes > h.header_bytes + 2 && pos + info.min_frame_bytes > q) q = pos + info.min_frame_bytes;
+        // search for the header of the next frame.  STREAMINFO's minimum frame size is of little help (the short last
+        // block of a file drags it down), so the search first starts three quarters of the previous frame's length in —
+        // frames of one stream are similar in size — and falls back to the safe start when that finds nothing acceptable.
+        const uint64_t safe = std::max<uint64_t>(pos + h.header_bytes + 2, info.min_frame_bytes > h.header_bytes + 2 ? pos + info.min_frame_bytes : 0);
         uint64_t next = n; Header hn;
-        while (q + 1 < n) {
-            const void* m = std::memchr(p + q, 0xFF, n - 1 - q);
-            if (!m) break;
-            q = (uint64_t)(static_cast<const uint8_t*>(m) - p);
-            if ((p[q + 1] & 0xFE) == 0xF8 && parse_header(p + q, n - q, info.sample_rate, info.bits_per_sample, &hn) &&
-                hn.number == next_number && hn.variable == h.variable) { next = q; break; }
-            ++q;
-        }
+        auto scan_from = [&](uint64_t q) -> bool {
+            while (q + 1 < n) {
+                const void* m = std::memchr(p + q, 0xFF, n - 1 - q);
+                if (!m) break;
+                q = (uint64_t)(static_cast<const uint8_t*>(m) - p);
+                if ((p[q + 1] & 0xFE) == 0xF8 && parse_header(p + q, n - q, info.sample_rate, info.bits_per_sample, &hn) &&
+                    hn.number == next_number && hn.variable == h.variable) { next = q; return true; }
+                ++q;
+            }
+            return false;
+        };
+        const uint64_t guess = prev_len ? pos + prev_len - prev_len / 4 : 0;
+        if (!(guess > safe && scan_from(guess))) scan_from(safe);
+        prev_len = next - pos;
         if (next - pos > 0xFFFFFFFFull) { *err = "frame too large"; return BB_ERR_IO; }
         out->push_back({pos, (uint32_t)(next - pos), h.blocksize, sample});
         sample += h.blocksize;
@@ -392,7 +468,10 @@ int32_t bb_flac_decode(bb_flac* f, const void* file_bytes, uint64_t n, const bb_
     if (info->channels == 0 || info->channels > 8 || info->bits_per_sample < 4 || info->bits_per_sample > 32)
         return flac_fail(c, BB_ERR_UNSUPPORTED_FORMAT, "unsupported FLAC channel count or sample size");
     std::string err;
+    static const bool dbg = [] { const char* e = std::getenv("BIRDA_K6_DEBUG"); return e && e[0] == '1'; }();
+    const auto t_idx0 = std::chrono::steady_clock::now();
     int rc = index_frames(static_cast<const uint8_t*>(file_bytes), n, *info, &f->frames, &err);
+    const double ms_index = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_idx0).count();
     if (rc != BB_OK) return flac_fail(c, rc, err);
     uint64_t total = 0;
     for (const auto& fr : f->frames) total += fr.blocksize;
@@ -427,19 +506,36 @@ int32_t bb_flac_decode(bb_flac* f, const void* file_bytes, uint64_t n, const bb_
     BB_CUDA_OK(c, grow((void**)&f->d_scratch, &scratch_bytes, total * info->channels * 4));
     f->scratch_elems = scratch_bytes / 4;
     BB_CUDA_OK(c, grow(&f->d_pcm, &f->d_pcm_bytes, total * info->channels * out_bytes + 16));
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (dbg) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], st); }
     BB_CUDA_OK(c, cudaMemcpyAsync(f->d_file, file_bytes, n, cudaMemcpyHostToDevice, st));
     BB_CUDA_OK(c, cudaMemcpyAsync(f->d_frames, f->frames.data(), nfr * sizeof(FrameRef), cudaMemcpyHostToDevice, st));
-    flac_decode_kernel<<<(unsigned)((nfr + 63) / 64), 64, 0, st>>>(f->d_file, f->d_frames, (uint32_t)nfr, info->sample_rate, info->bits_per_sample,
-                                                                    info->channels, f->d_scratch, f->d_meta);
+    if (dbg) cudaEventRecord(ev[1], st);
+    flac_crc_kernel<<<(unsigned)((nfr + 127) / 128), 128, 0, st>>>(f->d_file, f->d_frames, (uint32_t)nfr, f->d_meta);
+    if (dbg) cudaEventRecord(ev[2], st);
+    uint32_t lpw = 32;
+    while (lpw > 4 && nfr / lpw < (uint64_t)c->sm_count * 8) lpw >>= 1;          // at least ~8 warps per SM, at most 8x the issue slots
+    if (const char* e = std::getenv("BIRDA_K6_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= 32) lpw = (uint32_t)v; }
+    const uint64_t nwarps = (nfr + lpw - 1) / lpw;
+    flac_decode_kernel<<<(unsigned)((nwarps + 3) / 4), 128, 0, st>>>(f->d_file, f->d_frames, (uint32_t)nfr, info->sample_rate, info->bits_per_sample,
+                                                                      info->channels, f->d_scratch, f->d_meta, lpw);
+    if (dbg) cudaEventRecord(ev[3], st);
     const int shift = info->fmt == BB_S16 ? 16 - (int)info->bits_per_sample : info->fmt == BB_S24 ? 24 - (int)info->bits_per_sample : 32 - (int)info->bits_per_sample;
     if (info->fmt == BB_S16) flac_interleave_kernel<BB_S16><<<(unsigned)nfr, 256, 0, st>>>(f->d_frames, f->d_meta, info->channels, shift, f->d_scratch, f->d_pcm);
     else if (info->fmt == BB_S24) flac_interleave_kernel<BB_S24><<<(unsigned)nfr, 256, 0, st>>>(f->d_frames, f->d_meta, info->channels, shift, f->d_scratch, f->d_pcm);
     else flac_interleave_kernel<BB_S32><<<(unsigned)nfr, 256, 0, st>>>(f->d_frames, f->d_meta, info->channels, shift, f->d_scratch, f->d_pcm);
     BB_CUDA_OK(c, cudaGetLastError());
-    c->launches += 2;
+    c->launches += 3;
     f->meta.resize(nfr);
     BB_CUDA_OK(c, cudaMemcpyAsync(f->meta.data(), f->d_meta, nfr * sizeof(FrameMeta), cudaMemcpyDeviceToHost, st));
+    if (dbg) cudaEventRecord(ev[4], st);
     BB_CUDA_OK(c, bb::ctx_stream_wait(c));
+    if (dbg) {
+        float a = 0, b2 = 0, d = 0, e2 = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b2, ev[1], ev[2]); cudaEventElapsedTime(&d, ev[2], ev[3]); cudaEventElapsedTime(&e2, ev[3], ev[4]);
+        std::fprintf(stderr, "[k6] %llu frames: host index %.2f ms, H2D %.2f, crc %.2f, decode %.2f, interleave + D2H %.2f\n", (unsigned long long)nfr, ms_index, a, b2, d, e2);
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     for (uint64_t i = 0; i < nfr; ++i)
         if (f->meta[i].status) {
             static const char* what[] = {"", "frame header does not parse", "frame CRC-16 mismatch", "invalid subframe", "bitstream ends inside a frame"};

@@ -208,11 +208,11 @@ RATE_CODES = {88200: 1, 176400: 2, 192000: 3, 8000: 4, 16000: 5, 22050: 6, 24000
 BPS_CODES = {8: 1, 12: 2, 16: 4, 20: 5, 24: 6, 32: 7}
 
 
-def encode_frame(block: np.ndarray, frame_no: int, rate: int, bps: int, style: dict) -> bytes:
-    """block: [n, channels] int64."""
+def encode_frame(block: np.ndarray, frame_no: int, rate: int, bps: int, style: dict, first_sample: int | None = None) -> bytes:
+    """block: [n, channels] int64.  first_sample: variable-blocksize stream (the header carries the sample number)."""
     n, ch = block.shape
     w = BitWriter()
-    w.put(0b11111111111110, 14); w.put(0, 1); w.put(0, 1)
+    w.put(0b11111111111110, 14); w.put(0, 1); w.put(1 if first_sample is not None else 0, 1)
     bcode = BLOCK_CODES.get(n)
     if bcode is None:
         bcode = 6 if n <= 256 else 7
@@ -224,7 +224,7 @@ def encode_frame(block: np.ndarray, frame_no: int, rate: int, bps: int, style: d
     mode = style.get("stereo", "independent") if ch == 2 else "independent"
     w.put({"independent": ch - 1, "left_side": 8, "right_side": 9, "mid_side": 10}[mode], 4)
     w.put(BPS_CODES[bps] if style.get("bps_in_header", True) else 0, 3); w.put(0, 1)
-    for b in utf8_number(frame_no):
+    for b in utf8_number(frame_no if first_sample is None else first_sample):
         w.put(b, 8)
     if bcode == 6:
         w.put(n - 1, 8)
@@ -264,9 +264,19 @@ def encode(pcm: np.ndarray, rate: int, bps: int, blocksize: int = 4096, style: d
     if pcm.ndim == 1:
         pcm = pcm[:, None]
     total, ch = pcm.shape
-    frames = [encode_frame(pcm[s: s + blocksize], i, rate, bps, style) for i, s in enumerate(range(0, total, blocksize))]
+    sizes = style.get("variable_blocks")
+    if sizes:                                        # variable-blocksize stream: block sizes cycle through `sizes`
+        frames, pos, i = [], 0, 0
+        while pos < total:
+            n = min(sizes[i % len(sizes)], total - pos)
+            frames.append(encode_frame(pcm[pos: pos + n], i, rate, bps, style, first_sample=pos))
+            pos += n; i += 1
+        min_bs, max_bs = min(sizes), max(sizes)
+    else:
+        frames = [encode_frame(pcm[s: s + blocksize], i, rate, bps, style) for i, s in enumerate(range(0, total, blocksize))]
+        min_bs = max_bs = blocksize
     info = BitWriter()
-    info.put(blocksize, 16); info.put(blocksize, 16)
+    info.put(min_bs, 16); info.put(max_bs, 16)
     info.put(min(len(f) for f in frames) if frames else 0, 24); info.put(max(len(f) for f in frames) if frames else 0, 24)
     info.put(rate, 20); info.put(ch - 1, 3); info.put(bps - 1, 5); info.put(total, 36)
     for _ in range(16):

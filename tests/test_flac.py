@@ -70,6 +70,20 @@ def test_gpu_decode_is_bit_exact(style, rate, channels, bps, blocksize):
 
 
 @pytest.mark.gpu
+def test_variable_blocksize_stream_and_long_file():
+    """Blocking strategy 1 (the header carries the first sample's number, up to 36 bits in 7 bytes) with block sizes
+    that change from frame to frame; long enough that sample numbers need 3- and 4-byte codes."""
+    pcm = synth_pcm(17, 30.0, 44_100, 2).reshape(-1, 2).astype(np.int64)
+    data = flac_enc.encode(pcm, 44_100, 16, style=dict(kinds=["fixed2", "lpc"], stereo="left_side", variable_blocks=[4096, 1152, 256, 4608, 777]))
+    ctx = b.Context(0)
+    dec = b.FlacDecoder(ctx)
+    out, info = dec.decode_to_numpy(data)
+    assert (info.min_block, info.max_block) == (256, 4608)
+    assert np.array_equal(out.reshape(-1, 2).astype(np.int64), pcm)
+    dec.close(); ctx.close()
+
+
+@pytest.mark.gpu
 def test_corrupt_frame_is_reported():
     pcm = synth_pcm(9, 1.0, 44_100, 2).reshape(-1, 2)
     data = bytearray(flac_enc.encode(pcm, 44_100, 16))
