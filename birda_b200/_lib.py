@@ -135,6 +135,7 @@ SIGNATURES = {
     "bb_pool_worker_ctx": (vp, [vp, C.c_uint32]),
     "bb_pool_set_stream_ordered": (None, [vp, C.c_int32]),
     "bb_dense_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_int32, vp]),
+    "bb_calibrate_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp]),
     "bb_melspec_create": (C.c_int32, [vp, C.POINTER(MelSpecCfg), f32p, f32p, C.POINTER(vp)]),
     "bb_melspec_destroy": (None, [vp]),
     "bb_melspec_info": (C.c_int32, [vp, u32p, u32p, u32p]),

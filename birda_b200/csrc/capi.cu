@@ -498,4 +498,16 @@ int32_t bb_dense_run(bb_ctx* c, const float* d_x, uint32_t B, uint32_t K, const 
     BB_CATCH((c ? &c->last_error : nullptr))
 }
 
+int32_t bb_calibrate_run(bb_ctx* c, const float* d_scores, uint32_t B, uint32_t C, const float* d_a, const float* d_b, float* d_out) {
+    BB_TRY
+    if (!c) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null context");
+    if ((uint64_t)B * C == 0) return BB_OK;
+    if (!d_scores || !d_a || !d_out) BB_SET_ERR(c, BB_ERR_INVALID_ARG, "null argument");
+    BB_DEVICE(c, c->device);
+    BB_CUDA_OK(c, launch_affine_classes(c->stream, d_scores, B, C, d_a, d_b, d_out));
+    c->launches += 1;
+    return BB_OK;
+    BB_CATCH((c ? &c->last_error : nullptr))
+}
+
 }  // extern "C"

@@ -130,6 +130,7 @@ cudaError_t launch_resample_warp(cudaStream_t st, int sm_count, const ResamplerD
 void        resampler_dev_free(ResamplerDev* rs);
 
 // K4: tiny dense heads (geomodel forward, bat head).  k4_dense.cu
+cudaError_t launch_affine_classes(cudaStream_t st, const float* d_x, uint32_t B, uint32_t C, const float* d_a, const float* d_b, float* d_out);
 cudaError_t launch_dense(cudaStream_t st, const float* d_x, uint32_t B, uint32_t K, const float* d_W, const float* d_b,
                          uint32_t N, int activation, float* d_out, int* launches);
 

@@ -7,6 +7,7 @@
 // f32 throughout, one warp per output element with a shuffle reduction over K (left-to-right partial
 // sums per lane, so results are deterministic).  Latency-bound by design (kilobytes of work).
 #include "common.cuh"
+#include <algorithm>
 #include <cfloat>
 
 namespace bb {
@@ -48,7 +49,25 @@ softmax_rows_kernel(float* __restrict__ out, uint32_t B, uint32_t N) {
     for (uint32_t i = lane; i < N; i += 32) p[i] = expf(p[i] - m) / s;
 }
 
+// per-class affine map of the scores: out[b, c] = a[c] * x[b, c] + b[c]
+__global__ void __launch_bounds__(256)
+affine_classes_kernel(const float* __restrict__ x, uint64_t total, uint32_t C, const float* __restrict__ a, const float* __restrict__ bias,
+                      float* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i % C);
+        out[i] = fmaf(__ldg(a + c), x[i], bias ? __ldg(bias + c) : 0.f);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_affine_classes(cudaStream_t st, const float* d_x, uint32_t B, uint32_t C, const float* d_a, const float* d_b, float* d_out) {
+    const uint64_t total = (uint64_t)B * C;
+    if (total == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148ull * 16);
+    affine_classes_kernel<<<blocks, 256, 0, st>>>(d_x, total, C, d_a, d_b, d_out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_dense(cudaStream_t st, const float* d_x, uint32_t B, uint32_t K, const float* d_W, const float* d_b,
                          uint32_t N, int activation, float* d_out, int* launches) {

@@ -371,6 +371,12 @@ uint64_t bb_pool_kernel_launches(const bb_pool*);      /* kernels the workers' c
  * ---------------------------------------------------------------------------------------- */
 int32_t bb_dense_run(bb_ctx*, const float* d_x, uint32_t B, uint32_t K, const float* d_W, const float* d_b, uint32_t N,
                      int32_t activation, float* d_out);
+/* Per-class logistic (Platt) calibration of logits ahead of the post step: out[b,c] = a[c] * scores[b,c] + b[c]
+ * (then bb_post_run with BB_ACT_SIGMOID).  This is the standard form of the "per-species calibration" the reference
+ * applies to BSG models (src/pipeline/processor.rs:281-314 -> birdnet_onnx::BsgPostProcessor::calibrate); that crate's
+ * source and its CSV format are not in the image, so the form is stated, not pinned, and the SDM adjustment (location /
+ * day-of-year prior) is not restated.  d_out may equal d_scores; b may be NULL.  Asynchronous on the ctx stream. */
+int32_t bb_calibrate_run(bb_ctx*, const float* d_scores, uint32_t B, uint32_t C, const float* d_a, const float* d_b, float* d_out);
 
 /* ------------------------------------------------------------------------------------------
  * Spectrogram prefix on the device: framed STFT power + mel projection for classifiers

@@ -54,3 +54,29 @@ def test_dense_shapes(B, K, N, act):
         ref = z
     assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
     ctx.close()
+
+
+def test_per_class_calibration_then_post():
+    """bb_calibrate_run: out = a[c] * logit + b[c] per class (the standard Platt form; the reference's BSG calibration is
+    inside birdnet-onnx and unpinned), in place, then the usual sigmoid post step on the calibrated logits."""
+    import ctypes as C
+
+    import torch
+    from birda_b200 import _lib
+    from oracle import post as opost
+    ctx = b.Context(0)
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal((40, 265)) * 2 - 4).astype(np.float32)
+    a = (0.5 + rng.random(265)).astype(np.float32); bb = (rng.standard_normal(265) * 0.5).astype(np.float32)
+    d = torch.from_numpy(x).cuda(); da = torch.from_numpy(a).cuda(); db = torch.from_numpy(bb).cuda()
+    _lib.check(_lib.lib.bb_calibrate_run(ctx.handle, C.c_void_p(d.data_ptr()), 40, 265, C.c_void_p(da.data_ptr()), C.c_void_p(db.data_ptr()),
+                                         C.c_void_p(d.data_ptr())), ctx.handle)
+    ctx.sync()
+    want = np.float32(a) * x + bb                       # fmaf vs mul+add: one rounding apart
+    got = d.cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    idx, conf, cnt = ctx.post_run(d.data_ptr(), 40, 265, 40, b.PostConfig(min_confidence=0.1))
+    ref = opost.post_process(got, 40, opost.ACT_SIGMOID, 0.1, 5)
+    for r in range(40):
+        assert [int(i) for i in idx[r, : cnt[r]]] == [i for i, _ in ref[r]]
+    ctx.close()
