@@ -207,3 +207,24 @@ def test_c5_mixed_rate_directory_sharded(ctx):
     print(f"C5 100 files, all rows vs C oracle: worst {worst_all[0]:.3e} at {worst_all[1]}")
     for p in plans.values():
         p.close()
+
+
+def test_k2_linearity_and_shift_properties_bit_exact(ctx):
+    """Size-independent properties of the resampling path, checked bit for bit on 10 minutes of C2 audio:
+    (1) homogeneity — every operation between the PCM and the packed window is linear and scaling by two is exact in
+    binary floating point, so K2(2 x) == 2 K2(x) exactly; (2) shift — window i of a file is window 0 of the file cut at
+    i * hop: windows are independent of their neighbours and of which of the two packed streams carries them."""
+    import torch
+    pcm = (synth_pcm(8, 600.0, 44_100, 2).astype(np.int32) // 2).astype(np.int16)          # |x| <= 16384: 2x fits
+    plan = b.FrontEndPlan(ctx, 44_100, 2, b.FMT_S16, 48_000, 144_000, 72_000)
+    r1 = plan.run(pcm); ctx.sync()
+    a = r1.torch()[: r1.nseg].clone()
+    r2 = plan.run((pcm * 2).astype(np.int16)); ctx.sync()
+    assert r2.nseg == r1.nseg == 400
+    assert torch.equal(r2.torch()[: r2.nseg], a * 2.0)
+    src_seg, hop = 132_300, 66_150
+    for i in (1, 2, 7, 198, 333):
+        cut = pcm[i * hop * 2: (i * hop + src_seg) * 2]
+        r3 = plan.run(cut); ctx.sync()
+        assert r3.nseg >= 1 and torch.equal(r3.torch()[0], a[i]), i
+    plan.close()
