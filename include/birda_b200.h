@@ -328,7 +328,11 @@ void        bb_pipeline_set_read_threads(bb_pipeline*, uint32_t threads);
 int32_t bb_pipeline_process_pcm(bb_pipeline*, const void* pcm, uint64_t frames, uint32_t src_rate, uint32_t channels,
                                 int32_t fmt, bb_detection* out, uint64_t capacity, uint64_t* n_detections,
                                 uint64_t* n_segments, uint32_t* batch_used);
-/* WAV / RF64 file streamed through a pinned staging buffer in pieces of ~piece_frames (0 = default). */
+/* An audio file (by content: RIFF / RF64 WAVE, or FLAC).  WAV is streamed through two pinned staging buffers in pieces
+ * of ~piece_frames (0 = default, ~256 MB of PCM): a reader thread fills one while the GPU works on the other, pieces
+ * are cut so that only the file's last batch is padded, and the post-step results of a piece come back in one copy
+ * (per batch while hooks or a batch timeout are set).  A FLAC file goes to the GPU compressed and is decoded there
+ * (bb_flac_*), in one piece. */
 int32_t bb_pipeline_process_wav(bb_pipeline*, const char* path, uint64_t piece_frames, bb_detection* out, uint64_t capacity,
                                 uint64_t* n_detections, uint64_t* n_segments, uint32_t* batch_used);
 
