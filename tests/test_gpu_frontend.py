@@ -134,7 +134,8 @@ def test_streaming_pieces_equal_whole_file(ctx):
 
 # ------------------------------------------------------------------ K2: resampled, 1e-5 relative
 @pytest.mark.parametrize("sr,tr,seg,ovl,channels,seconds", [
-    (44_100, 48_000, 144_000, 72_000, 2, 9.3),     # C2 shape
+    (44_100, 48_000, 144_000, 72_000, 2, 9.3),     # C2 shape (K2's own blocking, s16 stereo staging)
+    (44_100, 48_000, 144_000, 36_001, 1, 8.7),     # the same plan from mono s16 (word-pair staging, odd block starts)
     (48_000, 32_000, 160_000, 0, 1, 12.1),         # C3 shape (radix 19)
     (22_050, 48_000, 144_000, 0, 1, 7.0),
     (96_000, 48_000, 144_000, 48_000, 2, 7.5),
