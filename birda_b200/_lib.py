@@ -142,6 +142,7 @@ SIGNATURES = {
     "bb_melspec_run": (C.c_int32, [vp, vp, C.c_uint32, C.c_uint32, vp]),
     "bb_flac_probe": (C.c_int32, [C.c_char_p, C.POINTER(FlacInfo)]),
     "bb_flac_probe_bytes": (C.c_int32, [vp, C.c_uint64, C.POINTER(FlacInfo)]),
+    "bb_flac_index": (C.c_int32, [vp, C.c_uint64, C.POINTER(FlacInfo), u64p, u64p, u32p, C.c_uint64, u64p]),
     "bb_flac_create": (C.c_int32, [vp, C.POINTER(vp)]),
     "bb_flac_destroy": (None, [vp]),
     "bb_flac_decode": (C.c_int32, [vp, vp, C.c_uint64, C.POINTER(FlacInfo), C.POINTER(vp), u64p]),

@@ -356,9 +356,10 @@ int index_frames(const uint8_t* p, uint64_t n, const bb_flac_info& info, std::ve
         // frames of one stream are similar in size — and falls back to the safe start when that finds nothing acceptable.
         const uint64_t safe = std::max<uint64_t>(pos + h.header_bytes + 2, info.min_frame_bytes > h.header_bytes + 2 ? pos + info.min_frame_bytes : 0);
         uint64_t next = n; Header hn;
-        auto scan_from = [&](uint64_t q) -> bool {
-            while (q + 1 < n) {
-                const void* m = std::memchr(p + q, 0xFF, n - 1 - q);
+        auto scan_from = [&](uint64_t q, uint64_t limit) -> bool {
+            if (limit > n) limit = n;
+            while (q + 1 < limit) {
+                const void* m = std::memchr(p + q, 0xFF, limit - 1 - q);
                 if (!m) break;
                 q = (uint64_t)(static_cast<const uint8_t*>(m) - p);
                 if ((p[q + 1] & 0xFE) == 0xF8 && parse_header(p + q, n - q, info.sample_rate, info.bits_per_sample, &hn) &&
@@ -367,8 +368,10 @@ int index_frames(const uint8_t* p, uint64_t n, const bb_flac_info& info, std::ve
             }
             return false;
         };
+        // the guess only looks a bounded distance ahead: if this frame is much shorter than the last one the true header
+        // lies before the guess, and an unbounded search would run to the end of the file before the fallback finds it
         const uint64_t guess = prev_len ? pos + prev_len - prev_len / 4 : 0;
-        if (!(guess > safe && scan_from(guess))) scan_from(safe);
+        if (!(guess > safe && scan_from(guess, guess + 2 * prev_len + 65536))) scan_from(safe, n);
         prev_len = next - pos;
         if (next - pos > 0xFFFFFFFFull) { *err = "frame too large"; return BB_ERR_IO; }
         out->push_back({pos, (uint32_t)(next - pos), h.blocksize, sample});
@@ -436,6 +439,25 @@ int32_t bb_flac_probe(const char* path, bb_flac_info* out) {
     ::close(fd);
     if (rc == BB_OK) out->file_bytes = (uint64_t)st.st_size;
     return rc;
+    BB_CATCH(nullptr)
+}
+
+// Frame index of a FLAC stream (host only): byte offset, first sample and block size of every frame, found as the
+// decoder finds them.  Returns the number of frames in *n_frames; arrays may be NULL or shorter (capacity) to count only.
+int32_t bb_flac_index(const void* bytes, uint64_t n, const bb_flac_info* info, uint64_t* offsets, uint64_t* first_samples,
+                      uint32_t* block_sizes, uint64_t capacity, uint64_t* n_frames) {
+    BB_TRY
+    if (!bytes || !info || !n_frames) return flac_fail(nullptr, BB_ERR_INVALID_ARG, "null argument");
+    std::vector<FrameRef> fr; std::string err;
+    const int rc = index_frames(static_cast<const uint8_t*>(bytes), n, *info, &fr, &err);
+    if (rc != BB_OK) return flac_fail(nullptr, rc, err);
+    *n_frames = fr.size();
+    for (uint64_t i = 0; i < fr.size() && i < capacity; ++i) {
+        if (offsets) offsets[i] = fr[i].offset;
+        if (first_samples) first_samples[i] = fr[i].first_sample;
+        if (block_sizes) block_sizes[i] = fr[i].blocksize;
+    }
+    return BB_OK;
     BB_CATCH(nullptr)
 }
 

@@ -430,6 +430,9 @@ typedef struct {
 typedef struct bb_flac bb_flac;
 int32_t bb_flac_probe(const char* path, bb_flac_info* out);
 int32_t bb_flac_probe_bytes(const void* bytes, uint64_t n_bytes, bb_flac_info* out);
+/* frame index (host only): offsets / first samples / block sizes as the decoder finds them; arrays may be NULL */
+int32_t bb_flac_index(const void* bytes, uint64_t n_bytes, const bb_flac_info* info, uint64_t* offsets, uint64_t* first_samples,
+                      uint32_t* block_sizes, uint64_t capacity, uint64_t* n_frames);
 int32_t bb_flac_create(bb_ctx*, bb_flac** out);
 void    bb_flac_destroy(bb_flac*);
 /* the whole compressed file in host memory -> *d_pcm (device, interleaved info->fmt, valid until the next decode on this

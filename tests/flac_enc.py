@@ -257,8 +257,10 @@ def encode_frame(block: np.ndarray, frame_no: int, rate: int, bps: int, style: d
     return body + crc16(body).to_bytes(2, "big")
 
 
-def encode(pcm: np.ndarray, rate: int, bps: int, blocksize: int = 4096, style: dict | None = None, junk_metadata: bool = True) -> bytes:
-    """pcm: [frames, channels] integers of `bps` bits.  Fixed-blocksize stream (the last block may be short)."""
+def encode(pcm: np.ndarray, rate: int, bps: int, blocksize: int = 4096, style: dict | None = None, junk_metadata: bool = True,
+           return_frames: bool = False):
+    """pcm: [frames, channels] integers of `bps` bits.  Fixed-blocksize stream (the last block may be short) unless
+    style["variable_blocks"] is set.  return_frames: also the list of (byte offset, bytes) of every frame."""
     style = dict(style or {})
     pcm = np.asarray(pcm).astype(np.int64)
     if pcm.ndim == 1:
@@ -288,6 +290,8 @@ def encode(pcm: np.ndarray, rate: int, bps: int, blocksize: int = 4096, style: d
         out += bytes([0x01]) + (10).to_bytes(3, "big") + bytes(10)
         vc = b"\x04\x00\x00\x00test" + b"\x00\x00\x00\x00"
         out += bytes([0x84]) + len(vc).to_bytes(3, "big") + vc
+    where = []
     for f in frames:
+        where.append((len(out), len(f)))
         out += f
-    return bytes(out)
+    return (bytes(out), where) if return_frames else bytes(out)

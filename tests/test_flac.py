@@ -28,6 +28,37 @@ def test_encoder_self_check():
     assert list(flac_enc.zigzag(np.array([0, -1, 1, -2, 2]))) == [0, 1, 2, 3, 4]
 
 
+def flac_index(data):
+    import ctypes as C
+
+    from birda_b200 import _lib
+    info = b.flac_probe(data)
+    n = C.c_uint64()
+    _lib.check(_lib.lib.bb_flac_index(data, len(data), C.byref(info), None, None, None, 0, C.byref(n)))
+    off = np.zeros(n.value, np.uint64); first = np.zeros(n.value, np.uint64); bs = np.zeros(n.value, np.uint32)
+    _lib.check(_lib.lib.bb_flac_index(data, len(data), C.byref(info), off.ctypes.data_as(_lib.u64p), first.ctypes.data_as(_lib.u64p),
+                                      bs.ctypes.data_as(_lib.u32p), n.value, C.byref(n)))
+    return off, first, bs
+
+
+@pytest.mark.parametrize("variable", [False, True])
+def test_frame_index_finds_every_frame(variable):
+    """The host's frame index (header CRC-8 + number continuity, search from a guessed offset with a bounded look-ahead and a
+    safe fallback) against the offsets the encoder wrote — fixed and wildly varying block sizes, with the sync pattern
+    planted inside the audio (0xFFF8 as a sample value) so that false candidates exist."""
+    pcm = synth_pcm(5, 6.0, 44_100, 2).reshape(-1, 2).astype(np.int64)
+    pcm[::97, 0] = -8                                             # 0xFFF8: a verbatim subframe carries the sync code itself
+    style = dict(kinds=["verbatim", "fixed2", "lpc"], stereo="independent")
+    if variable:
+        style["variable_blocks"] = [4096, 192, 4608, 256, 16, 1152, 777]
+    data, where = flac_enc.encode(pcm, 44_100, 16, blocksize=1024, style=style, return_frames=True)
+    off, first, bs = flac_index(data)
+    assert list(off) == [w[0] for w in where]
+    assert int(bs.sum()) == pcm.shape[0] and first[0] == 0 and np.array_equal(first[1:], np.cumsum(bs)[:-1].astype(np.uint64))
+    with pytest.raises(b.BirdaError):                             # a stream cut inside the metadata
+        b.flac_probe(data[:30])
+
+
 STYLES = [
     dict(kinds=["fixed0", "fixed1", "fixed2", "fixed3", "fixed4"], part_order=3),
     dict(kinds=["lpc"], lpc_order=8, lpc_precision=12, part_order=4, stereo="mid_side"),
