@@ -306,9 +306,9 @@ struct DualStream { uint64_t base; int valid; int shift; bool active; };
 
 template <int KIND>
 __device__ __forceinline__ void conv_pair(int a, int b, int shift, float& re, float& im) {
-    if constexpr (KIND == 0) {           // two packed L|R words: exact integer channel sum, then * 2^-15 / 2
-        re = __fmul_rn(__int2float_rn((int)(short)(a & 0xffff) + (a >> 16)), 1.0f / 65536.0f);
-        im = __fmul_rn(__int2float_rn((int)(short)(b & 0xffff) + (b >> 16)), 1.0f / 65536.0f);
+    if constexpr (KIND == 0) {           // two packed L|R words: exact integer channel sum (one dp2a: L*1 + R*1), then * 2^-15 / 2
+        re = __fmul_rn(__int2float_rn(__dp2a_lo(a, 0x0101, 0)), 1.0f / 65536.0f);
+        im = __fmul_rn(__int2float_rn(__dp2a_lo(b, 0x0101, 0)), 1.0f / 65536.0f);
     } else {                             // mono: the aligned word(s) covering the frame pair
         const int w = __funnelshift_r(a, b, shift);
         re = __fmul_rn(__int2float_rn((int)(short)(w & 0xffff)), 1.0f / 32768.0f);
