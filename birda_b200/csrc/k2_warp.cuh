@@ -230,7 +230,9 @@ BB_UNROLL_N(BB_K2W_UNROLL)
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int n = q + j * m;
-            a[j] = n < half_in ? ld(n) : czero<C>();
+            // j * m >= half_in: this input lies in the zero padding for every q (a compile-time fact for compile-time
+            // plans: the load, its conversion and the butterfly terms it feeds fold away)
+            a[j] = (j * m < half_in && n < half_in) ? ld(n) : czero<C>();
         }
         Dft<R, false>::run(a);
         if (s.TWOFF_() >= 0) apply_twiddles<R, C>(a, tw + s.TWOFF_(), m, q);
