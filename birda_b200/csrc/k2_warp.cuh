@@ -139,6 +139,7 @@ struct RtPlan {
     int twf_len, twi_len;        // compact twiddle table sizes (float2 entries)
     int pad_a, pad_b;            // 1: the forward (A) / inverse (B) buffer uses MapPad8 (one slot of padding after every eight)
     int split_len;               // pairs (k, M-k) the split pass visits = M/2 + 1 (order and addresses come from a host-built table)
+    int n_regular;               // the first n_regular pairs of the visiting order need no flag tests (split_regular_count)
     // Blocking (overlap-add geometry).  The transforms are 2N real points in, 2M real points out; a block consumes
     // adv_in input samples and emits adv_out output samples.  rubato's own blocking is adv_in = N, adv_out = M (the
     // filter is N taps long); up-sampling plans may use LONGER transforms over the same taps (adv_in + taps - 1 <= 2N):
@@ -287,9 +288,18 @@ BB_UNROLL_N(BB_K2W_UNROLL)
     }
 }
 
+// Pairs (k, M-k) with both spectra present, two outputs and no DC special case: k in [max(1, M - nkeep + 1), M/2 - 1].
+// They come first in the visiting order and take a branch-free path.
+BB_HD constexpr int split_regular_count(int M, int nkeep) {
+    const int lo = (M - nkeep + 1) > 1 ? (M - nkeep + 1) : 1, hi = M / 2 - 1;
+    return hi >= lo ? hi - lo + 1 : 0;
+}
+
 // Split-pass entry of one (k, M-k) pair, built on the host (build_split_layout): the positions of the four forward
 // results it reads and of the two inverse inputs it writes (digit reversal folded in), plus flags.
-//   x = posA(Z[k]) | posA(Z[N-k]) << 16     y = posA(Z[k2]) | posA(Z[N-k2]) << 16     z = posB(k) | posB(k2) << 16
+//   x = offA(Z[k]) | offA(Z[N-k]) << 16     y = offA(Z[k2]) | offA(Z[N-k2]) << 16     z = offB(k) | offB(k2) << 16
+//   (offsets in units of 8 bytes: position for single-stream elements, scaled by sizeof(element) / 8 at the access —
+//    one LEA; below 64 K for every plan the warp kernels take)
 //   w = flags: 1 = Y(k) present (k < nkeep), 2 = Y(k2) present, 4 = k == 0 (DC / Nyquist are real), 8 = write Z'(k2)
 constexpr unsigned kSplitHasK = 1u, kSplitHasK2 = 2u, kSplitDc = 4u, kSplitStore2 = 8u;
 
@@ -317,22 +327,49 @@ BB_HD uint4 ld_entry128(const uint4* p) {
 #endif
 }
 
+template <class C> BB_HD const typename Mem<C>::T* at_off(const typename Mem<C>::T* base, unsigned off) {
+    return reinterpret_cast<const typename Mem<C>::T*>(reinterpret_cast<const char*>(base) + (size_t)off * (sizeof(typename Mem<C>::T) / 8));
+}
+template <class C> BB_HD typename Mem<C>::T* at_off(typename Mem<C>::T* base, unsigned off) {
+    return reinterpret_cast<typename Mem<C>::T*>(reinterpret_cast<char*>(base) + (size_t)off * (sizeof(typename Mem<C>::T) / 8));
+}
+
 template <class C, class TB>
 BB_HD void split_pass(const typename Mem<C>::T* __restrict__ A, typename Mem<C>::T* __restrict__ B, const TB& T,
-                      int L, int lane, int nl) {
+                      int L, int lane, int nl, int n_regular) {
+    // regular pairs: both Y(k) and Y(M-k) exist, both outputs are written, nothing is forced real
 BB_UNROLL_N(BB_K2W_SPLIT_UNROLL)
-    for (int idx = lane; idx < L; idx += nl) {
+    for (int idx = lane; idx < n_regular; idx += nl) {
+        const uint4 e = ld_entry128(T.sidx + idx);
+        const float4 pa = T.pq1[idx], pb = T.pq2[idx];
+        const C zk = Mem<C>::ld(at_off<C>(A, e.x & 0xffffu)), zn = cconj(Mem<C>::ld(at_off<C>(A, e.x >> 16)));
+        const C zk2 = Mem<C>::ld(at_off<C>(A, e.y & 0xffffu)), zn2 = cconj(Mem<C>::ld(at_off<C>(A, e.y >> 16)));
+        const C yk = cadd(cmul(Mem<C>::bcast(make_float2(pa.x, pa.y)), zk), cmul(Mem<C>::bcast(make_float2(pa.z, pa.w)), zn));
+        const C yk2 = cadd(cmul(Mem<C>::bcast(make_float2(pb.x, pb.y)), zk2), cmul(Mem<C>::bcast(make_float2(pb.z, pb.w)), zn2));
+        const C wi = Mem<C>::bcast(T.WI[idx]);
+        {
+            const C ev = cadd(yk, cconj(yk2)), o = cmul(wi, csub(yk, cconj(yk2)));
+            Mem<C>::st(at_off<C>(B, e.z & 0xffffu), Cx<C>::make(ksub(Cx<C>::re(ev), Cx<C>::im(o)), kadd(Cx<C>::im(ev), Cx<C>::re(o))));
+        }
+        {
+            const C wi2 = Cx<C>::make(kneg(Cx<C>::re(wi)), Cx<C>::im(wi));    // exp(i pi (M-k)/M) = -conj(wi)
+            const C ev = cadd(yk2, cconj(yk)), o = cmul(wi2, csub(yk2, cconj(yk)));
+            Mem<C>::st(at_off<C>(B, e.z >> 16), Cx<C>::make(ksub(Cx<C>::re(ev), Cx<C>::im(o)), kadd(Cx<C>::im(ev), Cx<C>::re(o))));
+        }
+    }
+    // the rest (k = 0, k = M/2, pairs whose Y(M-k) lies beyond the kept bins): flags decide
+    for (int idx = n_regular + lane; idx < L; idx += nl) {
         const uint4 e = ld_entry128(T.sidx + idx);      // the tables live in shared memory in every kernel that runs this pass
         const unsigned fl = e.w;
         C yk = czero<C>(), yk2 = czero<C>();
         if (fl & kSplitHasK) {
             const float4 pq = T.pq1[idx];
-            const C zk = Mem<C>::ld(A + (e.x & 0xffffu)), zn = cconj(Mem<C>::ld(A + (e.x >> 16)));
+            const C zk = Mem<C>::ld(at_off<C>(A, e.x & 0xffffu)), zn = cconj(Mem<C>::ld(at_off<C>(A, e.x >> 16)));
             yk = cadd(cmul(Mem<C>::bcast(make_float2(pq.x, pq.y)), zk), cmul(Mem<C>::bcast(make_float2(pq.z, pq.w)), zn));
         }
         if (fl & kSplitHasK2) {
             const float4 pq = T.pq2[idx];
-            const C zk = Mem<C>::ld(A + (e.y & 0xffffu)), zn = cconj(Mem<C>::ld(A + (e.y >> 16)));
+            const C zk = Mem<C>::ld(at_off<C>(A, e.y & 0xffffu)), zn = cconj(Mem<C>::ld(at_off<C>(A, e.y >> 16)));
             yk2 = cadd(cmul(Mem<C>::bcast(make_float2(pq.x, pq.y)), zk), cmul(Mem<C>::bcast(make_float2(pq.z, pq.w)), zn));
         }
         if (fl & kSplitDc) {                            // DC / Nyquist are real (realfft ignores their imag)
@@ -342,12 +379,12 @@ BB_UNROLL_N(BB_K2W_SPLIT_UNROLL)
         const C wi = Mem<C>::bcast(T.WI[idx]);
         {
             const C ev = cadd(yk, cconj(yk2)), o = cmul(wi, csub(yk, cconj(yk2)));
-            Mem<C>::st(B + (e.z & 0xffffu), Cx<C>::make(ksub(Cx<C>::re(ev), Cx<C>::im(o)), kadd(Cx<C>::im(ev), Cx<C>::re(o))));
+            Mem<C>::st(at_off<C>(B, e.z & 0xffffu), Cx<C>::make(ksub(Cx<C>::re(ev), Cx<C>::im(o)), kadd(Cx<C>::im(ev), Cx<C>::re(o))));
         }
         if (fl & kSplitStore2) {
             const C wi2 = Cx<C>::make(kneg(Cx<C>::re(wi)), Cx<C>::im(wi));    // exp(i pi (M-k)/M) = -conj(wi)
             const C ev = cadd(yk2, cconj(yk)), o = cmul(wi2, csub(yk2, cconj(yk)));
-            Mem<C>::st(B + (e.z >> 16), Cx<C>::make(ksub(Cx<C>::re(ev), Cx<C>::im(o)), kadd(Cx<C>::im(ev), Cx<C>::re(o))));
+            Mem<C>::st(at_off<C>(B, e.z >> 16), Cx<C>::make(ksub(Cx<C>::re(ev), Cx<C>::im(o)), kadd(Cx<C>::im(ev), Cx<C>::re(o))));
         }
     }
 }
@@ -383,7 +420,7 @@ BB_HD void forward_half(const Exec& ex, const RtPlan& P, const TB& T, typename M
     for (int t = 1; t < P.nf; ++t)
         ex.each([&](int lane, int nl) { BB_K2W_RADIX_SWITCH(P.f[t].radix, (dif_stage<R, C, AM>(A, T.twf, P.f[t], lane, nl, T.order_f))) });
     before_split();
-    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.split_len, lane, nl); });
+    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, P.split_len, lane, nl, P.n_regular); });
 }
 // inverse half: in-place DIT in B -> overlap-add with the carry -> sink
 template <class C, class AM = MapId, class Exec, class Sink, class TB>
@@ -583,7 +620,7 @@ BB_HD void forward_half_ct(const Exec& ex, const TB& T, typename Mem<C>::T* A, t
     }, 0);
     CtFwdRest<PL, C, Exec, 1>::run(ex, A, T.twf, T.order_f);
     before_split();
-    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::M / 2 + 1, lane, nl); });
+    ex.each([&](int lane, int nl) { split_pass<C>(A, B, T, PL::M / 2 + 1, lane, nl, split_regular_count(PL::M, PL::NKEEP)); });
 }
 template <class PL, class C, class Exec, class Sink, class TB>
 BB_HD void inverse_half_ct(const Exec& ex, const TB& T, typename Mem<C>::T* B, typename Mem<C>::T* carry, const Sink& sink) {
@@ -692,6 +729,7 @@ inline bool build_plan_from_radices(int N, int M, int nkeep, RtPlan* P, const st
     if (adv_out % 2 != 0 || (adv_out / 2) % m_last != 0 || adv_in > 2 * N || M - adv_out / 2 > adv_out / 2 || adv_out / 2 > M) return false;
     P->adv_in = adv_in; P->adv_out = adv_out; P->carry_slots = M - adv_out / 2; P->emit_k = (adv_out / 2) / m_last;
     P->N = N; P->M = M; P->nkeep = nkeep; P->half_in = (adv_in + 1) / 2; P->split_len = M / 2 + 1;
+    P->n_regular = split_regular_count(M, nkeep);
     P->pad_a = 0; P->pad_b = 0;            // set by the caller: ct_plan_pads / rt_plan_pads
     P->nf = (int)fwd->size(); P->ni = (int)inv->size();
     int span = N, off = 0;
@@ -832,6 +870,7 @@ inline void build_stage_orders(RtPlan* P, int group, bool set_offsets, std::vect
 struct SplitLayout {
     std::vector<uint4> sidx; std::vector<float4> pq1, pq2; std::vector<float2> wi;
     int extra_wavefronts = 0;      // residual conflicts of the chosen order (diagnostic)
+    int n_regular = 0;             // leading entries that take the branch-free path (== split_regular_count(M, nkeep))
 };
 
 inline void build_split_layout(int N, int M, int nkeep, const uint16_t* pos_f_log, const uint16_t* pos_i_log,
@@ -870,69 +909,82 @@ inline void build_split_layout(int N, int M, int nkeep, const uint16_t* pos_f_lo
         }
         return c;
     };
-    // greedy: fill one group at a time with the pair that collides least with what the group already holds
-    std::vector<int> order; order.reserve(L);
-    std::vector<char> used(L, 0);
-    int left = L;
-    while (left > 0) {
-        bool seen[6][16] = {{false}};
-        for (int n = 0; n < G && left > 0; ++n) {
-            int best = -1, bc = 99;
-            for (int i = 0; i < L && bc > 0; ++i) {
-                if (used[i]) continue;
-                int c = 0;
-                for (int a = 0; a < 6; ++a) if (it[i].v[a] >= 0 && seen[a][it[i].v[a] % G]) ++c;
-                if (c < bc) { bc = c; best = i; }
-            }
-            used[best] = 1; --left; order.push_back(best);
-            for (int a = 0; a < 6; ++a) if (it[best].v[a] >= 0) seen[a][it[best].v[a] % G] = true;
-        }
-    }
-    // polish: swap pairs between a conflicting group and a random other one when that does not raise the cost
-    const int ng = (L + G - 1) / G;
-    auto gsize = [&](int g) { return g + 1 < ng ? G : L - g * G; };
-    std::vector<int> cost(ng);
-    int total = 0;
-    for (int g = 0; g < ng; ++g) { cost[g] = group_cost(&order[(size_t)g * G], gsize(g)); total += cost[g]; }
+    // The visiting order of one list of pairs: greedy (fill one group at a time with the pair that collides least with
+    // what the group already holds), then polish (a colliding pair of a conflicting group is offered to every seat of
+    // a random other group; the best exchange is taken when it does not raise the cost — ties keep the walk moving).
     uint64_t rng = 0x9E3779B97F4A7C15ull;
     auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); };
-    // a colliding pair of a conflicting group is offered to every seat of a random other group; the best exchange is
-    // taken when it does not raise the cost (ties keep the walk moving)
-    const int polish_iters = BB_SPLIT_POLISH_ITERS_PER_PAIR * L;
-    for (int iter = 0; iter < polish_iters && total > 0; ++iter) {
-        int g1 = (int)(next() % ng);
-        for (int tries = 0; tries < 16 && cost[g1] == 0; ++tries) g1 = (int)(next() % ng);
-        if (cost[g1] == 0) continue;
-        const int n1 = gsize(g1);
-        int cand[16], nc = 0;
-        for (int a = 0; a < 6; ++a) {
-            int cnt[16] = {0};
-            for (int i = 0; i < n1; ++i) { const unsigned r = res[(size_t)order[(size_t)g1 * G + i] * 6 + a]; if (r != 255) ++cnt[r]; }
-            for (int i = 0; i < n1 && nc < 16; ++i) { const unsigned r = res[(size_t)order[(size_t)g1 * G + i] * 6 + a]; if (r != 255 && cnt[r] > 1) cand[nc++] = i; }
+    auto optimise = [&](const std::vector<int>& ids, std::vector<int>* order_out) -> int {
+        const int Ln = (int)ids.size();
+        std::vector<int> order; order.reserve(Ln);
+        if (Ln == 0) return 0;
+        std::vector<char> used(Ln, 0);
+        int left = Ln;
+        while (left > 0) {
+            bool seen[6][16] = {{false}};
+            for (int n = 0; n < G && left > 0; ++n) {
+                int best = -1, bc = 99;
+                for (int i = 0; i < Ln && bc > 0; ++i) {
+                    if (used[i]) continue;
+                    int c = 0;
+                    for (int a = 0; a < 6; ++a) { const unsigned r = res[(size_t)ids[i] * 6 + a]; if (r != 255 && seen[a][r]) ++c; }
+                    if (c < bc) { bc = c; best = i; }
+                }
+                used[best] = 1; --left; order.push_back(ids[best]);
+                for (int a = 0; a < 6; ++a) { const unsigned r = res[(size_t)ids[best] * 6 + a]; if (r != 255) seen[a][r] = true; }
+            }
         }
-        if (nc == 0) continue;
-        const int i1 = g1 * G + cand[next() % nc];
-        const int g2 = (int)(next() % ng);
-        if (g1 == g2) continue;
-        int best_j = -1, best_c = cost[g1] + cost[g2] + 1, best_c1 = 0, best_c2 = 0;
-        for (int j = 0; j < gsize(g2); ++j) {
-            const int i2 = g2 * G + j;
-            std::swap(order[i1], order[i2]);
-            const int c1 = group_cost(&order[(size_t)g1 * G], n1), c2 = group_cost(&order[(size_t)g2 * G], gsize(g2));
-            std::swap(order[i1], order[i2]);
-            if (c1 + c2 < best_c) { best_c = c1 + c2; best_j = j; best_c1 = c1; best_c2 = c2; }
+        const int ng = (Ln + G - 1) / G;
+        auto gsize = [&](int g) { return g + 1 < ng ? G : Ln - g * G; };
+        std::vector<int> cost(ng);
+        int total = 0;
+        for (int g = 0; g < ng; ++g) { cost[g] = group_cost(&order[(size_t)g * G], gsize(g)); total += cost[g]; }
+        const int polish_iters = BB_SPLIT_POLISH_ITERS_PER_PAIR * Ln;
+        for (int iter = 0; iter < polish_iters && total > 0 && ng > 1; ++iter) {
+            int g1 = (int)(next() % ng);
+            for (int tries = 0; tries < 16 && cost[g1] == 0; ++tries) g1 = (int)(next() % ng);
+            if (cost[g1] == 0) continue;
+            const int n1 = gsize(g1);
+            int cand[16], nc = 0;
+            for (int a = 0; a < 6; ++a) {
+                int cnt[16] = {0};
+                for (int i = 0; i < n1; ++i) { const unsigned r = res[(size_t)order[(size_t)g1 * G + i] * 6 + a]; if (r != 255) ++cnt[r]; }
+                for (int i = 0; i < n1 && nc < 16; ++i) { const unsigned r = res[(size_t)order[(size_t)g1 * G + i] * 6 + a]; if (r != 255 && cnt[r] > 1) cand[nc++] = i; }
+            }
+            if (nc == 0) continue;
+            const int i1 = g1 * G + cand[next() % nc];
+            const int g2 = (int)(next() % ng);
+            if (g1 == g2) continue;
+            int best_j = -1, best_c = cost[g1] + cost[g2] + 1, best_c1 = 0, best_c2 = 0;
+            for (int j = 0; j < gsize(g2); ++j) {
+                const int i2 = g2 * G + j;
+                std::swap(order[i1], order[i2]);
+                const int c1 = group_cost(&order[(size_t)g1 * G], n1), c2 = group_cost(&order[(size_t)g2 * G], gsize(g2));
+                std::swap(order[i1], order[i2]);
+                if (c1 + c2 < best_c) { best_c = c1 + c2; best_j = j; best_c1 = c1; best_c2 = c2; }
+            }
+            if (best_j >= 0 && best_c <= cost[g1] + cost[g2]) {
+                std::swap(order[i1], order[g2 * G + best_j]);
+                total += best_c - cost[g1] - cost[g2]; cost[g1] = best_c1; cost[g2] = best_c2;
+            }
         }
-        if (best_j >= 0 && best_c <= cost[g1] + cost[g2]) {
-            std::swap(order[i1], order[g2 * G + best_j]);
-            total += best_c - cost[g1] - cost[g2]; cost[g1] = best_c1; cost[g2] = best_c2;
-        }
-    }
+        order_out->insert(order_out->end(), order.begin(), order.end());
+        return total;
+    };
+    // regular pairs (both spectra present, two outputs, not DC) first: the device runs them without flag tests; each
+    // list is visited by its own loop (lane 0 starts at the head of the list), so each is laid out on its own
+    std::vector<int> regular, rest;
+    for (int k = 0; k < L; ++k) ((it[k].flags == (kSplitHasK | kSplitHasK2 | kSplitStore2)) ? regular : rest).push_back(k);
+    std::vector<int> order; order.reserve(L);
+    int total = optimise(regular, &order);
+    total += optimise(rest, &order);
+    out->n_regular = (int)regular.size();
     out->extra_wavefronts = total;
     out->sidx.resize(L); out->pq1.resize(L); out->pq2.resize(L); out->wi.resize(L);
     for (int idx = 0; idx < L; ++idx) {
         const int k = order[idx], k2 = M - k;
         const Item& e = it[k];
-        auto u = [](int p) { return (unsigned)(p < 0 ? 0 : p); };
+        auto u = [&](int p) { return (unsigned)(p < 0 ? 0 : p) * 8u; };   // units of 8 bytes (at_off scales by the element size)
         out->sidx[idx] = make_uint4(u(e.v[0]) | (u(e.v[1]) << 16), u(e.v[2]) | (u(e.v[3]) << 16), u(e.v[4]) | (u(e.v[5]) << 16), e.flags);
         out->pq1[idx] = (e.flags & kSplitHasK) ? make_float4(Pt[k].x, Pt[k].y, Qt[k].x, Qt[k].y) : make_float4(0.f, 0.f, 0.f, 0.f);
         out->pq2[idx] = (e.flags & kSplitHasK2) ? make_float4(Pt[k2].x, Pt[k2].y, Qt[k2].x, Qt[k2].y) : make_float4(0.f, 0.f, 0.f, 0.f);

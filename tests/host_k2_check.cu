@@ -60,6 +60,7 @@ static int check_impl(int N, int M, int nl, int AI = 0, int AO = 0, int taps = 0
     if constexpr (kCompact) { twf_e = twf; twi_e = twi; } else { twf_e = expand_table<C>(twf); twi_e = expand_table<C>(twi); }
     SplitLayout SL;
     build_split_layout(N, M, NKEEP, pos_f.data(), pos_i.data(), Pt.data(), Qt.data(), WI.data(), NS == 2 ? 8 : 16, &SL, P.pad_a, P.pad_b);
+    if (SL.n_regular != split_regular_count(M, NKEEP) || SL.n_regular != P.n_regular) { printf("regular pair count differs\n"); return 1; }
     Tables<C, kCompact> T{{twf_e.data()}, {twi_e.data()}, SL.sidx.data(), SL.pq1.data(), SL.pq2.data(), SL.wi.data(),
                 ordf.empty() ? nullptr : ordf.data(), ordi.empty() ? nullptr : ordi.data()};
 
