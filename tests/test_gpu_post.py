@@ -136,3 +136,84 @@ def test_post_errors(ctx):
         ctx.post_run(d.data_ptr(), 4, 10, 4, b.PostConfig(top_k=9))
     with pytest.raises(b.BirdaError):
         ctx.post_run(d.data_ptr(), 4, 10, 4, b.PostConfig(), d.data_ptr(), d.data_ptr())
+
+
+def _plateau_rows(C, seed):
+    """Rows where the order is decided on a plateau of the activation: saturated sigmoids (every score above ~16.7 is
+    exactly 1.0f, the class index decides), scores around the 8.0 knee of the kernel's threshold rule, confidences that
+    underflow to 0 (index order again), and a row with fewer non-trivial scores than top_k."""
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((12, C)) * 2.0 - 6.0).astype(np.float32)
+    x[0, :] = -20.0; x[0, rng.choice(C, 40, replace=False)] = rng.uniform(18.0, 30.0, 40).astype(np.float32)   # all exactly 1.0f
+    x[1, :] = -20.0; x[1, rng.choice(C, 40, replace=False)] = rng.uniform(7.9, 8.2, 40).astype(np.float32)
+    x[2, :] = -100.0; x[2, rng.choice(C, 3, replace=False)] = 2.0
+    x[3, :] = -200.0
+    x[4, :] = -20.0; x[4, C - 1] = 25.0; x[4, 1] = 20.0; x[4, 0] = 12.0          # 1.0f, 1.0f, clearly below
+    x[5, rng.choice(C, 300, replace=False)] = rng.uniform(18.0, 40.0, 300).astype(np.float32)   # 300 ties at 1.0f
+    x[6, :] = np.float32(np.log(0.1 / 0.9))                                      # the whole row at the threshold
+    x[7, :] = -np.inf; x[7, 5] = 0.0
+    x[8, ::2] = np.nan                                                           # NaN scores never win
+    return x
+
+
+@pytest.mark.parametrize("rows", [12, 1100])
+@pytest.mark.parametrize("min_conf,top_k", [(0.1, 5), (0.0, 5), (0.0, 8), (0.5, 1)])
+def test_post_activation_plateaus_exact(ctx, rows, min_conf, top_k):
+    """K3 filters a row with a threshold derived from the row itself (csrc/k3_post.cu: lowered()); wherever confidences tie
+    the winner is the lower class index, whatever the scores behind the tie were.  Index lists must match exactly."""
+    C = 6522
+    x = _plateau_rows(C, 3)
+    if rows > 12:                                           # the 64-thread CTA variant: threshold from a third of the row
+        x = np.concatenate([x, synth_logits(9, rows - 12, C)], axis=0)
+    got = gpu_post(ctx, x, rows, b.PostConfig(min_confidence=min_conf, top_k=top_k))
+    ref = opost.post_process(x, rows, opost.ACT_SIGMOID, min_conf, top_k)
+    for r in (0, 2, 3, 4, 5, 7):                            # ties that are exact by construction
+        assert [i for i, _ in got[r]] == [i for i, _ in ref[r]], (r, got[r], ref[r])
+    assert [i for i, _ in got[4]][:2] == [1, C - 1][:top_k]
+    compare(got, ref, np.nan_to_num(opost.activate(x, opost.ACT_SIGMOID), nan=-1.0), min_conf)
+
+
+@pytest.mark.parametrize("rows", [10, 1100])
+def test_post_softmax_underflow_and_ties(ctx, rows):
+    C = 1001
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((rows, C)).astype(np.float32)
+    x[0, 500] = 200.0                                       # everything else underflows to exactly 0: index order after the peak
+    x[1, :] = 3.0                                           # uniform row: 1/C everywhere
+    x[2, 7] = 200.0; x[2, 9] = 200.0                        # two equal peaks, the rest exactly 0
+    x[3, :] = -np.inf; x[3, 4] = 1.0
+    for min_conf, k in ((0.0, 5), (0.0005, 5), (0.3, 3)):
+        got = gpu_post(ctx, x, rows, b.PostConfig(activation=b.ACT_SOFTMAX, min_confidence=min_conf, top_k=k))
+        ref = opost.post_process(x, rows, opost.ACT_SOFTMAX, min_conf, k)
+        for r in range(4):
+            assert [i for i, _ in got[r]] == [i for i, _ in ref[r]], (min_conf, r, got[r], ref[r])
+        compare(got, ref, opost.activate(x, opost.ACT_SOFTMAX), min_conf)
+
+
+def test_post_identity_activation_negative_scores(ctx):
+    """ACT_NONE with scores and a threshold below zero (graph outputs that are not probabilities)."""
+    C = 777
+    rng = np.random.default_rng(13)
+    x = (rng.standard_normal((1100, C)) - 3.0).astype(np.float32)
+    x[0, :] = -7.0                                          # all tied: lowest indices
+    got = gpu_post(ctx, x, 1100, b.PostConfig(activation=b.ACT_NONE, min_confidence=-2.5, top_k=4))
+    ref = opost.post_process(x, 1100, opost.ACT_NONE, -2.5, 4)
+    assert got[0] == [] and ref[0] == []
+    compare(got, ref, x, -2.5)
+    got = gpu_post(ctx, x, 1100, b.PostConfig(activation=b.ACT_NONE, min_confidence=-10.0, top_k=4))
+    ref = opost.post_process(x, 1100, opost.ACT_NONE, -10.0, 4)
+    assert [i for i, _ in got[0]] == [0, 1, 2, 3]
+    compare(got, ref, x, -10.0)
+
+
+@pytest.mark.parametrize("classes,act", [(6522, b.ACT_SIGMOID), (14795, b.ACT_SOFTMAX)])
+def test_post_few_hundred_rows(ctx, classes, act):
+    """128..1023 rows take the 128-thread-CTA variant of K3."""
+    rows = 300
+    x = synth_logits(classes + 2, rows, classes)
+    if act == b.ACT_SOFTMAX:
+        x[6:, :] *= 3.0
+    got = gpu_post(ctx, x, rows, b.PostConfig(activation=act, min_confidence=0.1))
+    ref = opost.post_process(x, rows, act, 0.1, 5)
+    compare(got, ref, opost.activate(x, act), 0.1)
+    assert sum(len(r) for r in ref) > 100

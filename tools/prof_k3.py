@@ -2,7 +2,7 @@
 """K3 timing on C2-shaped scores (2400 x 6522, SURVEY 8d's logit distribution): the same buffer over and over (62.6 MB:
 L2-resident after the first pass) and four buffers in rotation (250 MB > the 126 MB L2: every pass comes from DRAM, as in
 the real step where K2 streams 2 GB between two post steps).  BIRDA_B200_LIB selects an A/B build.
-usage: python tools/prof_k3.py [rows] [classes] [sigmoid|softmax]"""
+usage: python tools/prof_k3.py [auto,64,128,256]   (BIRDA_K3_THREADS values to run, default auto)"""
 import os
 import sys
 
@@ -11,44 +11,49 @@ import torch
 
 import birda_b200 as b
 
-rows = int(sys.argv[1]) if len(sys.argv) > 1 else 2400
-C = int(sys.argv[2]) if len(sys.argv) > 2 else 6522
-act = sys.argv[3] if len(sys.argv) > 3 else "sigmoid"
 dev = torch.device("cuda", 0)
 ctx = b.Context(0, stream=torch.cuda.current_stream().cuda_stream)
-g = torch.Generator(device=dev); g.manual_seed(5)
-bufs = [torch.randn((rows, C), device=dev, generator=g) * 2 - 6 for _ in range(4)]
-mask = torch.rand((C,), device=dev, generator=g)
-d_idx = torch.empty((rows, 5), dtype=torch.int32, device=dev)
-d_conf = torch.empty((rows, 5), dtype=torch.float32, device=dev)
-d_cnt = torch.empty((rows,), dtype=torch.int32, device=dev)
-cfg = b.PostConfig(activation=b.ACT_SOFTMAX if act == "softmax" else b.ACT_SIGMOID, min_confidence=0.1 if act == "sigmoid" else 0.001,
-                   top_k=5, range_threshold=0.01, keep_unmatched=True, rerank=False)
-
-
 import ctypes as ct
 
 from birda_b200 import _lib
 
-ccfg = cfg.to_c()
-args = [(ctx._h, ct.c_void_p(x.data_ptr()), rows, C, rows, ct.byref(ccfg), ct.c_void_p(mask.data_ptr()), None,
-         ct.c_void_p(d_idx.data_ptr()), ct.c_void_p(d_conf.data_ptr()), ct.c_void_p(d_cnt.data_ptr())) for x in bufs]
 fn = _lib.lib.bb_post_run_device
 
 
-def run(i):                      # arguments built once: the host side must stay well under the kernel's 20-30 us
-    assert fn(*args[i]) == 0
+def one(rows, C, act):
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    bufs = [torch.randn((rows, C), device=dev, generator=g) * 2 - 6 for _ in range(4)]
+    mask = torch.rand((C,), device=dev, generator=g)
+    d_idx = torch.empty((rows, 5), dtype=torch.int32, device=dev)
+    d_conf = torch.empty((rows, 5), dtype=torch.float32, device=dev)
+    d_cnt = torch.empty((rows,), dtype=torch.int32, device=dev)
+    cfg = b.PostConfig(activation=b.ACT_SOFTMAX if act == "softmax" else b.ACT_SIGMOID, min_confidence=0.1 if act == "sigmoid" else 0.001,
+                       top_k=5, range_threshold=0.01, keep_unmatched=True, rerank=False)
+    ccfg = cfg.to_c()
+    # arguments built once: the host side must stay well under the kernel's 20-30 us
+    args = [(ctx._h, ct.c_void_p(x.data_ptr()), rows, C, rows, ct.byref(ccfg), ct.c_void_p(mask.data_ptr()), None,
+             ct.c_void_p(d_idx.data_ptr()), ct.c_void_p(d_conf.data_ptr()), ct.c_void_p(d_cnt.data_ptr())) for x in bufs]
+    for name, pick in (("same buffer (L2)", lambda k: 0), ("4 buffers in rotation (DRAM)", lambda k: k % 4)):
+        for k in range(8):
+            assert fn(*args[pick(k)]) == 0
+        torch.cuda.synchronize()
+        n = 200
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(n):
+            fn(*args[pick(k)])
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / n * 1e3
+        print(f"K3 {act} {rows} x {C} threads {os.environ.get('BIRDA_K3_THREADS', 'auto')}, {name}: {us:.1f} us -> {rows * C * 4 / us / 1e3:.0f} GB/s   "
+              f"checksum {int(d_cnt.sum())} {float(d_conf.sum()):.6f}", flush=True)
 
 
-for name, pick in (("same buffer (L2)", lambda k: 0), ("4 buffers in rotation (DRAM)", lambda k: k % 4)):
-    for k in range(8):
-        run(pick(k))
-    torch.cuda.synchronize()
-    n = 200
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(n):
-        run(pick(k))
-    e1.record(); torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / n * 1e3
-    print(f"K3 {act} {rows} x {C}, {name}: {us:.1f} us -> {rows * C * 4 / us / 1e3:.0f} GB/s   checksum {int(d_cnt.sum())} {float(d_conf.sum()):.6f}")
+threads = sys.argv[1].split(",") if len(sys.argv) > 1 else ["auto"]
+for t in threads:
+    if t == "auto":
+        os.environ.pop("BIRDA_K3_THREADS", None)
+    else:
+        os.environ["BIRDA_K3_THREADS"] = t
+    one(2400, 6522, "sigmoid")
+    one(720, 14795, "softmax")
+    one(64, 6522, "sigmoid")
