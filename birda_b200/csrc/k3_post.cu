@@ -151,7 +151,6 @@ post_kernel(const float* __restrict__ scores, uint32_t C, bb_post_cfg cfg,
     __shared__ Cand     s_win[K];
     __shared__ Cand     s_list[kCap];
     __shared__ Cand     s_fin[NW * K];
-    __shared__ float    s_mask[K];
     __shared__ int      s_count;
 
     const uint32_t row = blockIdx.x;
@@ -326,43 +325,46 @@ post_kernel(const float* __restrict__ scores, uint32_t C, bb_post_cfg cfg,
         }
     }
     __syncthreads();
-    // the winners' mask entries are fetched in parallel; one thread then walks the short list
-    if (tid < K && mask != nullptr && s_win[tid].idx != 0xFFFFFFFFu) s_mask[tid] = __ldg(mask + s_win[tid].idx);
-    __syncthreads();
-
-    if (tid == 0) {
-        Cand out[K];
-        uint32_t n = 0;
-        for (uint32_t r = 0; r < topk; ++r) {
-            Cand w = s_win[r];
-            if (w.idx == 0xFFFFFFFFu) break;
+    // Tail, one lane per winner (the list is at most BB_MAX_TOP_K long): mask / species test, rerank, second threshold.
+    if (warp == 0) {
+        const bool in = (uint32_t)lane < topk;
+        Cand w; w.conf = 0.f; w.idx = 0xFFFFFFFFu;
+        if (in) w = s_win[lane];
+        bool kept = w.idx != 0xFFFFFFFFu;                           // winners are contiguous from slot 0
+        const bool rerank = mask != nullptr && cfg.rerank;
+        if (kept) {
             if (mask != nullptr) {                                  // geomodel_filter.rs:54-71
-                const float s = s_mask[r];
-                if (isnan(s)) { if (!(cfg.keep_unmatched && !cfg.rerank)) continue; }
-                else if (s >= cfg.range_threshold) { if (cfg.rerank) w.conf = __fmul_rn(w.conf, s); }
-                else continue;
+                const float sc = __ldg(mask + w.idx);
+                if (isnan(sc)) kept = cfg.keep_unmatched && !cfg.rerank;
+                else if (sc >= cfg.range_threshold) { if (cfg.rerank) w.conf = __fmul_rn(w.conf, sc); }
+                else kept = false;
             } else if (keep != nullptr) {                           // classifier.rs:616-641
-                if (!keep[w.idx]) continue;
-            }
-            out[n++] = w;
-        }
-        if (mask != nullptr && cfg.rerank) {                        // geomodel_filter.rs:74-76 (stable here)
-            for (uint32_t a = 1; a < n; ++a) {
-                Cand t = out[a]; int b = (int)a - 1;
-                while (b >= 0 && out[b].conf < t.conf) { out[b + 1] = out[b]; --b; }
-                out[b + 1] = t;
+                kept = keep[w.idx] != 0;
             }
         }
-        uint32_t m = 0;
-        for (uint32_t a = 0; a < n; ++a) {                          // processor.rs:374
-            if (out[a].conf >= min_conf) {
-                o_index[(uint64_t)row * topk + m] = out[a].idx;
-                o_conf[(uint64_t)row * topk + m]  = out[a].conf;
-                ++m;
+        // position among the kept entries: list order, or (rerank) a stable sort by confidence, geomodel_filter.rs:74-76
+        const unsigned km = __ballot_sync(0xffffffffu, kept);
+        int pos = __popc(km & ((1u << lane) - 1u));
+        if (rerank) {
+            pos = 0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float cj = __shfl_sync(0xffffffffu, w.conf, j);
+                pos += (((km >> j) & 1u) && (cj > w.conf || (cj == w.conf && j < lane))) ? 1 : 0;
             }
         }
-        o_count[row] = m;
-        for (; m < topk; ++m) { o_index[(uint64_t)row * topk + m] = 0xFFFFFFFFu; o_conf[(uint64_t)row * topk + m] = 0.f; }
+        const bool pass = kept && w.conf >= min_conf;               // processor.rs:374, order preserved
+        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+        int slot = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int pj = __shfl_sync(0xffffffffu, pos, j);
+            slot += (((pm >> j) & 1u) && pj < pos) ? 1 : 0;
+        }
+        const uint32_t cnt = (uint32_t)__popc(pm);
+        if (pass) { o_index[(uint64_t)row * topk + slot] = w.idx; o_conf[(uint64_t)row * topk + slot] = w.conf; }
+        if (in && (uint32_t)lane >= cnt) { o_index[(uint64_t)row * topk + lane] = 0xFFFFFFFFu; o_conf[(uint64_t)row * topk + lane] = 0.f; }
+        if (lane == 0) o_count[row] = cnt;
     }
 }
 
