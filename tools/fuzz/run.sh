@@ -1,5 +1,5 @@
 #!/bin/bash
-# Build the parsers with ASan + UBSan and fuzz them (CPU only, ~1 min): tools/fuzz/run.sh [iterations]
+# Build the parsers with ASan + UBSan and fuzz them, then the watchdog under TSan (CPU only, ~1 min): tools/fuzz/run.sh [iterations]
 set -e
 ROOT=$(cd "$(dirname "$0")/../.." && pwd)
 W=$(mktemp -d)
@@ -21,4 +21,9 @@ pc = synth_pcm(3, 0.5, 16000, 2).reshape(-1, 2)
 open(w + "/a.flac", "wb").write(flac_enc.encode(pc, 16000, 16, style=dict(kinds=["lpc"], stereo="mid_side", part_order=2)))
 PY
 ASAN_OPTIONS=detect_leaks=0 $W/drv $W/a.wav $W/a.flac ${1:-20000}
+cd $ROOT/birda_b200/csrc
+g++ -O1 -g -std=c++17 -fsanitize=thread -fPIC -pthread -c watchdog.cpp -o $W/watchdog.o
+cd $ROOT/tools/fuzz
+g++ -O1 -g -std=c++17 -fsanitize=thread -pthread -o $W/wd watchdog_tsan.cpp stubs.cpp $W/watchdog.o
+$W/wd
 rm -rf $W
