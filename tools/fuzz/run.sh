@@ -26,4 +26,10 @@ g++ -O1 -g -std=c++17 -fsanitize=thread -fPIC -pthread -c watchdog.cpp -o $W/wat
 cd $ROOT/tools/fuzz
 g++ -O1 -g -std=c++17 -fsanitize=thread -pthread -o $W/wd watchdog_tsan.cpp stubs.cpp $W/watchdog.o
 $W/wd
+cd $ROOT/birda_b200/csrc
+g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-omit-frame-pointer -fPIC -c mask.cpp -o $W/mask.o
+g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fPIC -fno-fast-math -ffp-contract=off -c rules.cpp -o $W/rules.o
+cd $ROOT/tools/fuzz
+g++ -O1 -g -std=c++17 -fsanitize=address,undefined -o $W/mk mask_asan.cpp stubs.cpp $W/mask.o $W/rules.o
+$W/mk
 rm -rf $W
