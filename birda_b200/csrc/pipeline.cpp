@@ -11,6 +11,7 @@
 #include "rules.hpp"
 #include "guard.hpp"
 #include "watchdog.hpp"
+#include "pieces.hpp"
 #include "pipeline_internal.hpp"
 #include <algorithm>
 #include <chrono>
@@ -275,23 +276,9 @@ int process_wav(bb_pipeline* p, const char* path, uint64_t piece_frames, Sink* s
     if (piece_frames == 0) piece_frames = (256ull << 20) / fb;
     if (piece_frames < 2 * src_seg) piece_frames = 2 * src_seg;
     const uint64_t hop = src_seg - src_ovl;
-    // the piece table is a pure function of the header: (first frame, frames, last piece)
-    struct Piece { uint64_t pos, frames; bool eof; };
-    std::vector<Piece> pieces;
-    for (uint64_t pos = 0;;) {
-        uint64_t want = std::min<uint64_t>(piece_frames, info.frames - pos);
-        bool eof = pos + want >= info.frames;
-        if (!eof) {                                                                // trim to k*B full windows
-            uint64_t nfull = want >= src_seg ? (want - src_seg) / hop + 1 : 0;
-            nfull = nfull / B * B;
-            if (nfull == 0) { want = std::min<uint64_t>(info.frames - pos, src_seg + (uint64_t)(B - 1) * hop); eof = pos + want >= info.frames; }
-            else want = (nfull - 1) * hop + src_seg;
-        }
-        pieces.push_back({pos, want, eof});
-        if (eof) break;
-        const uint64_t nwin = (want - src_seg) / hop + 1;                         // windows of a non-final piece: all full
-        pos += nwin * hop;
-    }
+    // the piece table is a pure function of the header: (first frame, frames, last piece) — pieces.hpp
+    using Piece = bb::Piece;
+    const std::vector<Piece> pieces = bb::plan_pieces(info.frames, piece_frames, src_seg, hop, B);
     uint64_t max_bytes = 0;
     for (const Piece& pc : pieces) max_bytes = std::max(max_bytes, pc.frames * fb);
     const int nbuf = pieces.size() > 1 ? 2 : 1;
